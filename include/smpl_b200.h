@@ -1,0 +1,147 @@
+/*
+ * smpl_b200.h — C ABI of the B200-native SMPL decode -> project -> mask -> part-seg / silhouette path.
+ *
+ * The reference (akashsengupta1997/indirect_learning_pose-shape) has no native code: its hot path is a
+ * chain of stock TensorFlow ops driven from Python (keras_smpl/).  This header is therefore the boundary a
+ * Python/ctypes (or cffi / pybind) binding of that path binds; every entry point names the reference
+ * function (file:line, relative to the reference tree) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - plain C: opaque handles, raw DEVICE pointers, sizes; no C++ types, no exceptions, no torch types.
+ *  - every function returns 0 on success or a negative SmplB200Status; smpl_b200_last_error() returns a
+ *    thread-local human-readable message for the last failure on the calling thread.
+ *  - all compute entry points are asynchronous on the given cudaStream_t (passed as void*), never allocate,
+ *    never synchronise; the caller owns inputs, outputs and the workspace (size from smpl_b200_workspace_bytes).
+ *  - there is no CPU fallback: without a CUDA device every create/compute call fails.
+ *  - tensors are dense row-major fp32 unless stated.  N = batch, V = 6890 vertices,
+ *    Vs = ceil(V / vertex_sampling) sampled vertices (projection.py:67-68), wh = img_wh.
+ *  - params layout (N,86): [k_u, k_v, u0, v0 | theta 24x3 axis-angle | beta 10]
+ *    (model.py:33-35, batch_smpl.py:98-99, projection.py:62-65).
+ */
+#ifndef SMPL_B200_H_
+#define SMPL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPL_B200_ABI_VERSION 1
+#define SMPL_B200_NUM_PARAMS 86
+#define SMPL_B200_NUM_JOINTS 24
+#define SMPL_B200_VPOSED_LD(num_verts) ((((num_verts) * 3 + 127) / 128) * 128) /* row stride (floats) of the saved v_posed */
+
+typedef enum SmplB200Status {
+  SMPL_B200_OK = 0,
+  SMPL_B200_ERR_BAD_ARG = -1,      /* null pointer, negative size, misaligned buffer */
+  SMPL_B200_ERR_UNSUPPORTED = -2,  /* size outside what the kernels were built for */
+  SMPL_B200_ERR_CUDA = -3,         /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  SMPL_B200_ERR_WORKSPACE = -4,    /* workspace too small */
+  SMPL_B200_ERR_NO_DEVICE = -5     /* no usable CUDA device (there is no CPU path) */
+} SmplB200Status;
+
+/* Host-side description of the SMPL constants, in the layouts SMPLLayer.build produces
+ * (keras_smpl/batch_smpl.py:31-94).  All pointers are HOST pointers, read during model_create only. */
+typedef struct SmplB200HostModel {
+  int32_t num_verts;            /* V, 6890 */
+  int32_t num_joints;           /* must be 24 */
+  int32_t num_betas;            /* must be 10 */
+  int32_t num_pose_basis;       /* must be 207 */
+  int32_t num_reg_joints;       /* columns of joint_regressor (19 cocoplus / 14 lsp), 0 if absent */
+  const float* v_template;      /* [V][3]                      batch_smpl.py:38-41 */
+  const float* shapedirs;       /* [10][V*3]                   batch_smpl.py:50-55 */
+  const float* posedirs;        /* [207][V*3]                  batch_smpl.py:64-68 */
+  const float* J_regressor;     /* [V][24]                     batch_smpl.py:58-61 */
+  const float* lbs_weights;     /* [V][24]                     batch_smpl.py:76-79 */
+  const int32_t* parents;       /* [24], parents[0] ignored    batch_smpl.py:71 */
+  const float* joint_regressor; /* [V][num_reg_joints] or NULL batch_smpl.py:82-87 */
+} SmplB200HostModel;
+
+typedef struct SmplB200Model SmplB200Model; /* immutable after create; one per device */
+typedef struct SmplB200Parts SmplB200Parts; /* immutable part->vertex table on one device */
+
+/* ---- library -------------------------------------------------------------------------------------- */
+int smpl_b200_abi_version(void);
+const char* smpl_b200_last_error(void);
+/* number of kernel launches issued through this library by the calling process since load (all threads) */
+uint64_t smpl_b200_launch_count(void);
+
+/* ---- handles ---------------------------------------------------------------------------------------- */
+/* SMPLLayer.__init__/build (batch_smpl.py:24-94): uploads and repacks the constants on `device`. */
+int smpl_b200_model_create(const SmplB200HostModel* host, int device, SmplB200Model** out);
+void smpl_b200_model_destroy(SmplB200Model* model);
+int smpl_b200_model_num_verts(const SmplB200Model* model);
+int smpl_b200_model_lbs_width(const SmplB200Model* model); /* max non-zeros per LBS weight row */
+
+/* The unpickled part list of projects_to_seg.py:18-24 with indices already divided by vertex_sampling
+ * (projects_to_seg.py:36-37), as CSR: part k owns part_idx[part_ptr[k] .. part_ptr[k+1]).  HOST pointers. */
+int smpl_b200_parts_create(int device, int num_parts, const int32_t* part_ptr, const int32_t* part_idx,
+                           int num_sampled_verts, SmplB200Parts** out);
+void smpl_b200_parts_destroy(SmplB200Parts* parts);
+
+/* ---- workspace ---------------------------------------------------------------------------------------- */
+typedef enum SmplB200Op {
+  SMPL_B200_OP_DECODE_FWD = 0,
+  SMPL_B200_OP_DECODE_BWD = 1,
+  SMPL_B200_OP_SILHOUETTE_FWD = 2,
+  SMPL_B200_OP_SILHOUETTE_BWD = 3
+} SmplB200Op;
+/* bytes of device scratch the op needs for batch N (16-byte aligned buffer); vertex_sampling <= 1 = none */
+size_t smpl_b200_workspace_bytes(const SmplB200Model* model, int op, int N, int img_wh, int vertex_sampling);
+
+/* ---- SMPLLayer.call (batch_smpl.py:96-153) ------------------------------------------------------------- */
+/* params (N,86) -> verts (N,V,3).  Optional outputs (NULL to skip):
+ *   joints24     (N,24,3)  J_transformed, the side attribute of batch_smpl.py:131
+ *   joints_reg   (N,R,3)   the commented-out cocoplus/LSP regression of batch_smpl.py:147-151 (R = num_reg_joints)
+ *   v_posed_save (N,LD)    rest-pose vertices after both blend shapes, row stride LD = SMPL_B200_VPOSED_LD(V);
+ *                          the tensor decode_bwd needs (saved-for-backward)
+ *   projects     (N,Vs,3)  fused orthographic_project (projection.py:54-81) with `vertex_sampling` */
+int smpl_b200_decode_fwd(const SmplB200Model* model, const float* params, int N, float* verts, float* joints24,
+                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* projects,
+                         int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above (TF autodiff of batch_smpl.py:96-153 and projection.py:54-81).
+ *   g_verts    (N,V,3)  or NULL
+ *   g_projects (N,Vs,3) or NULL (gradient w.r.t. the fused projection output, sampled with vertex_sampling)
+ *   g_joints24 (N,24,3) or NULL
+ *   g_params   (N,86)   written (not accumulated): camera, pose and shape gradients
+ * With g_verts == NULL only the sampled vertices carry gradient and the kernels skip the rest. */
+int smpl_b200_decode_bwd(const SmplB200Model* model, const float* params, int N, const float* v_posed_save,
+                         const float* g_verts, const float* g_projects, int vertex_sampling,
+                         const float* g_joints24, float* g_params, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- orthographic_project (projection.py:54-81), stand-alone ---------------------------------------- */
+int smpl_b200_project_fwd(const float* verts, const float* params, int N, int V, int vertex_sampling,
+                          float* projects, void* stream);
+/* g_verts (N,V,3) is fully written (zeros at unsampled vertices); g_params (N,86) is fully written
+ * (zeros outside the four camera slots). */
+int smpl_b200_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V,
+                          int vertex_sampling, float* g_verts, float* g_params, void* stream);
+
+/* ---- compute_mask (compute_mask.py:12-108) ----------------------------------------------------------- */
+/* projects (N,Vs,3) -> mask (N,Vs) in {1,500}; 64x64 grid, round-half-even, largest z wins, first index on
+ * ties, vertex 1 always visible when any grid cell is empty.  Stateless per sample.  No gradient. */
+int smpl_b200_mask_fwd(const float* projects, int N, int Vs, float* mask, void* stream);
+
+/* ---- projects_to_seg (projects_to_seg.py:9-69) -------------------------------------------------------- */
+/* projects (N,Vs,3), mask (N,Vs) -> seg (N,wh,wh,num_parts+1): channel 0 background, rows flipped. */
+int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs,
+                      int img_wh, float* seg, void* stream);
+/* g_seg (N,wh,wh,P+1) -> g_projects (N,Vs,3), fully written (z column and untouched vertices are 0). */
+int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg,
+                      int N, int Vs, int img_wh, float* g_projects, void* stream);
+
+/* ---- projects_to_silhouette (projects_to_silhouette.py:14-44) ------------------------------------------ */
+/* projects (N,Vs,3) -> sil (N,wh,wh,2): channel 0 = 1-s, channel 1 = s, rows flipped. */
+int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, int Vs, int img_wh,
+                             float* g_projects, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPL_B200_H_ */

@@ -1,0 +1,482 @@
+// C-ABI entry points, handles and host-side repacking (see include/smpl_b200.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace smplb200 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::mutex g_vs_mutex;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SMPL_B200_ERR_CUDA;                                                             \
+    }                                                                                        \
+  } while (0)
+
+template <typename T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)dptr, bytes);
+  if (e != cudaSuccess) return e;
+  if (!h.empty()) e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
+  const int V = m->V;
+  const int Vs = (V + vs - 1) / vs;
+  const int ncols = Vs * 3;
+  std::vector<float> bt((size_t)ncols * kKPad, 0.f);
+  for (int c = 0; c < ncols; ++c) {
+    const int col = 3 * vs * (c / 3) + (c % 3);
+    for (int k = 0; k < kK; ++k) bt[(size_t)c * kKPad + k] = m->h_Bm[(size_t)k * (3 * V) + col];
+  }
+  std::vector<int> ptr(kJ + 1, 0), vert;
+  std::vector<float> w;
+  for (int j = 0; j < kJ; ++j) {
+    for (int v = 0; v < V; v += vs) {
+      float x = m->h_W[(size_t)v * kJ + j];
+      if (x != 0.f) { vert.push_back(v); w.push_back(x); }
+    }
+    ptr[j + 1] = (int)vert.size();
+  }
+  CU_TRY(upload(&t->BmT, bt));
+  CU_TRY(upload(&t->csc_ptr, ptr));
+  CU_TRY(upload(&t->csc_vert, vert));
+  CU_TRY(upload(&t->csc_w, w));
+  t->Vs = Vs;
+  t->ncols = ncols;
+  t->vs = vs;  // publish last
+  return 0;
+}
+
+const VsTables* get_vs_tables(const SmplB200Model* m, int vs) {
+  if (vs < 1) vs = 1;
+  for (int i = 0; i < kMaxVsCache; ++i)
+    if (m->vst[i].vs == vs) return &m->vst[i];
+  std::lock_guard<std::mutex> lk(g_vs_mutex);
+  SmplB200Model* mm = const_cast<SmplB200Model*>(m);
+  for (int i = 0; i < kMaxVsCache; ++i) {
+    if (mm->vst[i].vs == vs) return &mm->vst[i];
+    if (mm->vst[i].vs == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaSetDevice(m->device);
+      int rc = build_vs_tables(mm, vs, &mm->vst[i]);
+      cudaSetDevice(dev);
+      return rc == 0 ? &mm->vst[i] : nullptr;
+    }
+  }
+  set_error("vertex_sampling cache full (max %d distinct values per model)", kMaxVsCache);
+  return nullptr;
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace smplb200
+
+using namespace smplb200;
+
+extern "C" {
+
+int smpl_b200_abi_version(void) { return SMPL_B200_ABI_VERSION; }
+const char* smpl_b200_last_error(void) { return g_err; }
+uint64_t smpl_b200_launch_count(void) { return g_launches.load(); }
+
+int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model** out) {
+  if (!h || !out) { set_error("model_create: null argument"); return SMPL_B200_ERR_BAD_ARG; }
+  *out = nullptr;
+  if (!h->v_template || !h->shapedirs || !h->posedirs || !h->J_regressor || !h->lbs_weights || !h->parents) {
+    set_error("model_create: null constant array"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (h->num_joints != kJ || h->num_betas != kBetas || h->num_pose_basis != kPoseBasis || h->num_verts < 2 ||
+      h->num_verts > 65535) {
+    set_error("model_create: unsupported sizes V=%d J=%d betas=%d pose_basis=%d (need J=24, 10, 207, 2<=V<=65535)",
+              h->num_verts, h->num_joints, h->num_betas, h->num_pose_basis);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("model_create: no usable CUDA device %d (found %d); this library has no CPU path", device, ndev);
+    return SMPL_B200_ERR_NO_DEVICE;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU_TRY(cudaSetDevice(device));
+  const int V = h->num_verts;
+  SmplB200Model* m = new SmplB200Model();
+  m->device = device;
+  m->V = V;
+  m->LD = SMPL_B200_VPOSED_LD(V);
+  m->R = h->joint_regressor ? h->num_reg_joints : 0;
+  // kinematic tree
+  for (int j = 0; j < kJ; ++j) {
+    int p = (j == 0) ? -1 : h->parents[j];
+    if (j > 0 && (p < 0 || p >= j)) {
+      set_error("model_create: parents[%d]=%d is not a topologically ordered tree", j, p);
+      delete m; cudaSetDevice(prev); return SMPL_B200_ERR_BAD_ARG;
+    }
+    m->tree.parent[j] = p;
+    m->tree.depth[j] = (j == 0) ? 0 : m->tree.depth[p] + 1;
+    for (int c = 0; c < 4; ++c) m->tree.child[j][c] = -1;
+  }
+  m->tree.max_depth = 0;
+  for (int j = 1; j < kJ; ++j) {
+    m->tree.max_depth = std::max(m->tree.max_depth, m->tree.depth[j]);
+    int p = m->tree.parent[j], c = 0;
+    while (c < 4 && m->tree.child[p][c] >= 0) ++c;
+    if (c == 4) {
+      set_error("model_create: joint %d has more than 4 children", p);
+      delete m; cudaSetDevice(prev); return SMPL_B200_ERR_UNSUPPORTED;
+    }
+    m->tree.child[p][c] = j;
+  }
+  // blend matrix [kKPad][LD], template [LD]
+  const size_t C = (size_t)3 * V;
+  m->h_Bm = (float*)malloc(sizeof(float) * kK * C);
+  m->h_W = (float*)malloc(sizeof(float) * (size_t)V * kJ);
+  memcpy(m->h_Bm, h->shapedirs, sizeof(float) * kBetas * C);
+  memcpy(m->h_Bm + kBetas * C, h->posedirs, sizeof(float) * kPoseBasis * C);
+  memcpy(m->h_W, h->lbs_weights, sizeof(float) * (size_t)V * kJ);
+  {
+    std::vector<float> bm((size_t)kKPad * m->LD, 0.f), vt(m->LD, 0.f);
+    for (int k = 0; k < kK; ++k) memcpy(&bm[(size_t)k * m->LD], m->h_Bm + (size_t)k * C, sizeof(float) * C);
+    memcpy(vt.data(), h->v_template, sizeof(float) * C);
+    CU_TRY(upload(&m->Bm, bm));
+    CU_TRY(upload(&m->vt_pad, vt));
+  }
+  // folded joint regression: J = Jt + Jd * beta   (exact algebra of batch_smpl.py:106-115, evaluated in fp64)
+  {
+    std::vector<double> jt(kJ * 3, 0.0), jd((size_t)kJ * 3 * kBetas, 0.0);
+    for (int v = 0; v < V; ++v)
+      for (int j = 0; j < kJ; ++j) {
+        const double r = h->J_regressor[(size_t)v * kJ + j];
+        if (r == 0.0) continue;
+        for (int c = 0; c < 3; ++c) {
+          jt[j * 3 + c] += r * (double)h->v_template[v * 3 + c];
+          for (int k = 0; k < kBetas; ++k)
+            jd[((size_t)j * 3 + c) * kBetas + k] += r * (double)h->shapedirs[(size_t)k * C + v * 3 + c];
+        }
+      }
+    std::vector<float> jtf(jt.begin(), jt.end()), jdf(jd.begin(), jd.end());
+    CU_TRY(upload(&m->Jt, jtf));
+    CU_TRY(upload(&m->Jd, jdf));
+  }
+  // LBS weights -> ELL (idx,w) of width KW = max non-zeros per row
+  {
+    int kw = 1;
+    for (int v = 0; v < V; ++v) {
+      int n = 0;
+      for (int j = 0; j < kJ; ++j) n += h->lbs_weights[(size_t)v * kJ + j] != 0.f;
+      kw = std::max(kw, n);
+    }
+    kw = (kw <= 4) ? 4 : (kw <= 8 ? 8 : kJ);
+    m->KW = kw;
+    std::vector<uint8_t> idx((size_t)V * kw, 0);
+    std::vector<float> w((size_t)V * kw, 0.f);
+    for (int v = 0; v < V; ++v) {
+      int n = 0;
+      for (int j = 0; j < kJ; ++j) {
+        float x = h->lbs_weights[(size_t)v * kJ + j];
+        if (x != 0.f) { idx[(size_t)v * kw + n] = (uint8_t)j; w[(size_t)v * kw + n] = x; ++n; }
+      }
+    }
+    CU_TRY(upload(&m->lbs_idx, idx));
+    CU_TRY(upload(&m->lbs_w, w));
+  }
+  // sparse keypoint regressor (CSR by keypoint)
+  {
+    std::vector<int> ptr(m->R + 1, 0), vert;
+    std::vector<float> w;
+    for (int r = 0; r < m->R; ++r) {
+      for (int v = 0; v < V; ++v) {
+        float x = h->joint_regressor[(size_t)v * h->num_reg_joints + r];
+        if (x != 0.f) { vert.push_back(v); w.push_back(x); }
+      }
+      ptr[r + 1] = (int)vert.size();
+    }
+    CU_TRY(upload(&m->jr_ptr, ptr));
+    CU_TRY(upload(&m->jr_vert, vert));
+    CU_TRY(upload(&m->jr_w, w));
+  }
+  // the reference's three sampling modes are built eagerly so hot calls never allocate
+  const int eager[3] = {1, 2, 5};
+  for (int i = 0; i < 3; ++i) {
+    int rc = build_vs_tables(m, eager[i], &m->vst[i]);
+    if (rc != 0) { cudaSetDevice(prev); return rc; }
+  }
+  CU_TRY(cudaDeviceSynchronize());
+  cudaSetDevice(prev);
+  *out = m;
+  return SMPL_B200_OK;
+}
+
+void smpl_b200_model_destroy(SmplB200Model* m) {
+  if (!m) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(m->device);
+  cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
+  cudaFree(m->jr_ptr); cudaFree(m->jr_vert); cudaFree(m->jr_w);
+  for (int i = 0; i < kMaxVsCache; ++i) {
+    cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w);
+  }
+  free(m->h_Bm); free(m->h_W);
+  cudaSetDevice(prev);
+  delete m;
+}
+
+int smpl_b200_model_num_verts(const SmplB200Model* m) { return m ? m->V : 0; }
+int smpl_b200_model_lbs_width(const SmplB200Model* m) { return m ? m->KW : 0; }
+
+int smpl_b200_parts_create(int device, int num_parts, const int32_t* part_ptr, const int32_t* part_idx,
+                           int num_sampled_verts, SmplB200Parts** out) {
+  if (!part_ptr || !out || num_parts < 1 || num_sampled_verts < 1) {
+    set_error("parts_create: bad argument"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  if (num_parts > 31) { set_error("parts_create: at most 31 parts supported (got %d)", num_parts); return SMPL_B200_ERR_UNSUPPORTED; }
+  const int E = part_ptr[num_parts];
+  if (part_ptr[0] != 0 || E < 0 || (E > 0 && !part_idx)) { set_error("parts_create: bad CSR"); return SMPL_B200_ERR_BAD_ARG; }
+  std::vector<int> ptr(part_ptr, part_ptr + num_parts + 1), idx(part_idx, part_idx + E);
+  std::vector<uint8_t> po(E);
+  int max_part = 0;
+  for (int k = 0; k < num_parts; ++k) {
+    if (ptr[k + 1] < ptr[k]) { set_error("parts_create: part_ptr not monotone"); return SMPL_B200_ERR_BAD_ARG; }
+    max_part = std::max(max_part, ptr[k + 1] - ptr[k]);
+    for (int e = ptr[k]; e < ptr[k + 1]; ++e) {
+      if (idx[e] < 0 || idx[e] >= num_sampled_verts) {
+        set_error("parts_create: vertex index %d out of range [0,%d)", idx[e], num_sampled_verts);
+        return SMPL_B200_ERR_BAD_ARG;
+      }
+      po[e] = (uint8_t)k;
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("parts_create: no usable CUDA device %d", device); return SMPL_B200_ERR_NO_DEVICE;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU_TRY(cudaSetDevice(device));
+  SmplB200Parts* p = new SmplB200Parts();
+  p->device = device; p->P = num_parts; p->E = E; p->Vs = num_sampled_verts; p->max_part = max_part;
+  CU_TRY(upload(&p->ptr, ptr));
+  CU_TRY(upload(&p->idx, idx));
+  CU_TRY(upload(&p->part_of, po));
+  CU_TRY(cudaDeviceSynchronize());
+  cudaSetDevice(prev);
+  *out = p;
+  return SMPL_B200_OK;
+}
+
+void smpl_b200_parts_destroy(SmplB200Parts* p) {
+  if (!p) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);
+  cudaFree(p->ptr); cudaFree(p->idx); cudaFree(p->part_of);
+  cudaSetDevice(prev);
+  delete p;
+}
+
+// ---- workspace layout ------------------------------------------------------------------------------------
+static size_t ru(size_t x, size_t a) { return (x + a - 1) / a * a; }
+struct DecodeWs {
+  float *X, *A, *Jtr, *gA, *gX, *gcam, *gvp;
+  size_t gvp_ld;
+  size_t bytes;
+};
+static DecodeWs decode_ws(const SmplB200Model* m, int N, bool bwd, bool full_grad, int vs, void* base) {
+  DecodeWs w{};
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) { float* r = (float*)(p + off); off += ru(nfloat * sizeof(float), 256); return r; };
+  w.X = take((size_t)N * kKPad);
+  w.A = take((size_t)N * kJ * 12);
+  w.Jtr = take((size_t)N * kJ * 3);
+  if (bwd) {
+    w.gA = take((size_t)N * kJ * 12);
+    w.gX = take((size_t)N * kKPad);
+    w.gcam = take((size_t)N * 4);
+    const int Vs = (m->V + vs - 1) / vs;
+    w.gvp_ld = full_grad ? (size_t)m->LD : ru((size_t)Vs * 3, 4);
+    w.gvp = take((size_t)N * w.gvp_ld);
+  }
+  w.bytes = off;
+  return w;
+}
+
+size_t smpl_b200_workspace_bytes(const SmplB200Model* m, int op, int N, int img_wh, int vertex_sampling) {
+  if (!m || N < 0) return 0;
+  const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
+  (void)img_wh;
+  switch (op) {
+    case SMPL_B200_OP_DECODE_FWD: return decode_ws(m, N, false, false, 1, nullptr).bytes;
+    case SMPL_B200_OP_DECODE_BWD: return decode_ws(m, N, true, vs == 1, vs, nullptr).bytes;
+    case SMPL_B200_OP_SILHOUETTE_FWD:
+    case SMPL_B200_OP_SILHOUETTE_BWD: return 256;
+    default: return 0;
+  }
+}
+
+#define CHECK_LAUNCH(expr)                                                           \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      set_error("%s: %s", #expr, cudaGetErrorString(e__));                           \
+      return SMPL_B200_ERR_CUDA;                                                     \
+    }                                                                                \
+  } while (0)
+
+int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, float* verts, float* joints24,
+                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* projects,
+                         int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !params || N < 0 || (!verts && !projects)) { set_error("decode_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (N == 0) return SMPL_B200_OK;
+  const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
+  if (!aligned(params, 4) || (verts && !aligned(verts, 8)) || (v_posed_save && !aligned(v_posed_save, 16)) || !aligned(workspace, 16)) {
+    set_error("decode_fwd: misaligned buffer (verts 8B, v_posed_save/workspace 16B)"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (joints_reg && (num_reg_joints_used < 1 || num_reg_joints_used > m->R)) {
+    set_error("decode_fwd: joints_reg requested with %d keypoints, model has %d", num_reg_joints_used, m->R);
+    return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (joints_reg && !verts) { set_error("decode_fwd: joints_reg needs verts"); return SMPL_B200_ERR_BAD_ARG; }
+  // v_posed must live somewhere: the caller's save buffer, else the tail of the workspace
+  DecodeWs w = decode_ws(m, N, false, false, 1, workspace);
+  size_t need = w.bytes + (v_posed_save ? 0 : ru((size_t)N * m->LD * sizeof(float), 256));
+  if (!workspace || workspace_bytes < need) {
+    set_error("decode_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return SMPL_B200_ERR_WORKSPACE;
+  }
+  float* vp = v_posed_save ? v_posed_save : (float*)((char*)workspace + w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, w.A, joints24 ? joints24 : w.Jtr, st));
+  CHECK_LAUNCH(launch_blend_fwd(m, w.X, N, vp, st));
+  CHECK_LAUNCH(launch_lbs_fwd(m, vp, w.A, params, N, verts, projects, vs, st));
+  if (joints_reg) CHECK_LAUNCH(launch_joints_reg_fwd(m, verts, N, num_reg_joints_used, joints_reg, st));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, const float* v_posed_save,
+                         const float* g_verts, const float* g_projects, int vertex_sampling,
+                         const float* g_joints24, float* g_params, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (!m || !params || !v_posed_save || !g_params || N < 0) { set_error("decode_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (N == 0) return SMPL_B200_OK;
+  const int vs_in = vertex_sampling < 1 ? 1 : vertex_sampling;
+  const bool full = (g_verts != nullptr) || !g_projects;     // dense vertex gradient (or none at all)
+  const int vs_t = full ? 1 : vs_in;
+  const VsTables* t = get_vs_tables(m, vs_t);
+  if (!t) return SMPL_B200_ERR_CUDA;
+  DecodeWs w = decode_ws(m, N, true, full, vs_t, workspace);
+  if (!workspace || workspace_bytes < w.bytes || !aligned(workspace, 16)) {
+    set_error("decode_bwd: workspace too small or misaligned (%zu < %zu bytes)", workspace_bytes, w.bytes);
+    return SMPL_B200_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, w.A, w.Jtr, st));     // recompute A (cheap) instead of saving it
+  CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp, w.gvp_ld, w.gA,
+                              w.gcam, st));
+  CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
+  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, N, g_params, st));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_project_fwd(const float* verts, const float* params, int N, int V, int vertex_sampling, float* projects,
+                          void* stream) {
+  if (!verts || !params || !projects || N < 0 || V < 1) { set_error("project_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_project_fwd(verts, params, N, V, vertex_sampling < 1 ? 1 : vertex_sampling, projects, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V,
+                          int vertex_sampling, float* g_verts, float* g_params, void* stream) {
+  if (!verts || !params || !g_projects || !g_verts || !g_params || N < 0 || V < 1) {
+    set_error("project_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_project_bwd(verts, params, g_projects, N, V, vertex_sampling < 1 ? 1 : vertex_sampling, g_verts, g_params,
+                                  (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_mask_fwd(const float* projects, int N, int Vs, float* mask, void* stream) {
+  if (!projects || !mask || N < 0 || Vs < 1) { set_error("mask_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_mask_fwd(projects, N, Vs, mask, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+static int seg_check(const SmplB200Parts* p, const void* a, const void* b, const void* c, int N, int Vs, int wh, const char* who) {
+  if (!p || !a || !b || !c || N < 0) { set_error("%s: null/invalid argument", who); return SMPL_B200_ERR_BAD_ARG; }
+  if (Vs != p->Vs) { set_error("%s: Vs=%d does not match the part table (%d)", who, Vs, p->Vs); return SMPL_B200_ERR_BAD_ARG; }
+  if (wh < 1 || wh > 128) { set_error("%s: img_wh=%d unsupported (1..128)", who, wh); return SMPL_B200_ERR_UNSUPPORTED; }
+  if (!aligned(c, 16)) { set_error("%s: seg buffer must be 16-byte aligned", who); return SMPL_B200_ERR_BAD_ARG; }
+  return 0;
+}
+
+int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs, int img_wh,
+                      float* seg, void* stream) {
+  int rc = seg_check(parts, projects, mask, seg, N, Vs, img_wh, "seg_fwd");
+  if (rc) return rc;
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_seg_fwd(parts, projects, mask, N, Vs, img_wh, seg, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg, int N,
+                      int Vs, int img_wh, float* g_projects, void* stream) {
+  int rc = seg_check(parts, projects, mask, g_seg, N, Vs, img_wh, "seg_bwd");
+  if (rc) return rc;
+  if (!g_projects) { set_error("seg_bwd: null g_projects"); return SMPL_B200_ERR_BAD_ARG; }
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_seg_bwd(parts, projects, mask, g_seg, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!projects || !sil || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (img_wh > 4096) { set_error("silhouette_fwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_sil_fwd(projects, N, Vs, img_wh, sil, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, int Vs, int img_wh, float* g_projects,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!projects || !g_sil || !g_projects || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (img_wh > 4096) { set_error("silhouette_bwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
+  if (N == 0) return SMPL_B200_OK;
+  CHECK_LAUNCH(launch_sil_bwd(projects, g_sil, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+}  // extern "C"

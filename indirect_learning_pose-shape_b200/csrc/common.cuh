@@ -1,0 +1,124 @@
+// Shared declarations for the smpl_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/smpl_b200.h"
+
+#ifndef __CUDA_ARCH_LIST__
+#endif
+
+namespace smplb200 {
+
+constexpr int kJ = 24;            // joints
+constexpr int kBetas = 10;
+constexpr int kPoseBasis = 207;
+constexpr int kK = 217;           // blend rows actually used: 10 shape + 207 pose
+constexpr int kKPad = 224;        // padded blend depth (multiple of 16)
+constexpr int kParams = 86;
+constexpr int kMaskGrid = 64;     // compute_mask.py:44
+constexpr float kMaskInvisible = 500.0f;  // compute_mask.py:68
+constexpr int kMaxVsCache = 8;
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+struct VsTables {       // per vertex_sampling derived tables (device pointers)
+  int vs = 0;           // 0 = unused slot
+  int Vs = 0;           // sampled vertex count
+  int ncols = 0;        // Vs*3
+  float* BmT = nullptr;       // [ncols][kKPad] : BmT[c][k] = Bm[k][col(c)],  col(c) = 3*vs*(c/3) + c%3
+  int* csc_ptr = nullptr;     // [kJ+1]  joint -> entries (sampled vertices only)
+  int* csc_vert = nullptr;    // [nnz]   ORIGINAL vertex id
+  float* csc_w = nullptr;     // [nnz]
+};
+
+struct TreeInfo {       // passed by value to the pose kernels
+  int parent[kJ];
+  int depth[kJ];
+  int child[kJ][4];     // up to 4 children, -1 padded (general trees with more children are rejected)
+  int max_depth;
+};
+
+}  // namespace smplb200
+
+struct SmplB200Model {
+  int device = 0;
+  int V = 0;
+  int LD = 0;            // padded column count of the blend matrix / v_posed rows
+  int KW = 0;            // max non-zeros per LBS row
+  int R = 0;             // regressed joints
+  float* vt_pad = nullptr;   // [LD]
+  float* Bm = nullptr;       // [kKPad][LD]
+  float* Jt = nullptr;       // [kJ*3]
+  float* Jd = nullptr;       // [kJ*3][kBetas]
+  uint8_t* lbs_idx = nullptr;  // [V][KW]
+  float* lbs_w = nullptr;      // [V][KW]
+  int* jr_ptr = nullptr;       // [R+1]
+  int* jr_vert = nullptr;
+  float* jr_w = nullptr;
+  smplb200::TreeInfo tree;
+  smplb200::VsTables vst[smplb200::kMaxVsCache];
+  // host copies kept for lazily building VsTables
+  float* h_Bm = nullptr;     // [kK][3V] (host)
+  float* h_W = nullptr;      // [V][kJ]  (host)
+};
+
+struct SmplB200Parts {
+  int device = 0;
+  int P = 0;           // parts (31)
+  int E = 0;           // total entries
+  int Vs = 0;
+  int* ptr = nullptr;        // [P+1] device
+  int* idx = nullptr;        // [E]   device, sampled-space vertex index
+  uint8_t* part_of = nullptr;  // [E] device, part id of each entry
+  int max_part = 0;
+};
+
+namespace smplb200 {
+
+const VsTables* get_vs_tables(const SmplB200Model* m, int vs);
+
+// kernels launchers (implemented in the *_kernels.cu files). All return cudaError_t of the launch.
+cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* A, float* Jtr,
+                            cudaStream_t st);
+cudaError_t launch_blend_fwd(const SmplB200Model* m, const float* X, int N, float* v_posed, cudaStream_t st);
+cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
+                           float* verts, float* projects, int vs, cudaStream_t st);
+cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, int N, int R_used, float* joints,
+                                  cudaStream_t st);
+// t = tables of the PROCESSING stride (1 = every vertex, g_vp rows [LD]; >1 = sampled vertices only, g_vp rows
+// [gvp_ld] compact); vs_proj = sampling stride of g_projects.
+cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
+                           const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
+                           float* g_vp, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st);
+cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
+                             float* g_X, cudaStream_t st);
+cudaError_t launch_pose_bwd(const SmplB200Model* m, const float* params, const float* g_A, const float* g_X,
+                            const float* g_Jtr, const float* g_cam, int N, float* g_params, cudaStream_t st);
+cudaError_t launch_project_fwd(const float* verts, const float* params, int N, int V, int vs, float* projects,
+                               cudaStream_t st);
+cudaError_t launch_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V, int vs,
+                               float* g_verts, float* g_params, cudaStream_t st);
+cudaError_t launch_mask_fwd(const float* projects, int N, int Vs, float* mask, cudaStream_t st);
+cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
+                           float* seg, cudaStream_t st);
+cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg, int N,
+                           int Vs, int wh, float* g_projects, cudaStream_t st);
+cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, cudaStream_t st);
+cudaError_t launch_sil_bwd(const float* projects, const float* g_sil, int N, int Vs, int wh, float* g_projects,
+                           cudaStream_t st);
+
+// small device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace smplb200

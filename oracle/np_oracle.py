@@ -1,0 +1,296 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED.**
+
+NumPy restatement of the reference's keras_smpl decoder path, statement by statement, evaluated the
+way the reference evaluates it (dense matmuls, brute-force O(wh^2 * V) rasterisers, O(4096 * V) mask).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; the product (indirect_learning_pose-shape_b200/) never does and fails loudly without its CUDA
+library.
+
+Why "parity unpinned": the reference is python-2.7 / Keras 2.1 / TensorFlow 1.x code (README.md:20-28)
+with no tests, golden vectors or recorded outputs; TensorFlow, Keras, h5py, deepdish, chumpy and python2
+are absent from this image and the SMPL model file it needs (neutral_smpl_with_cocoplus_reg.pkl) is not
+shipped (/root/reference/.MISSING_LARGE_BLOBS).  The arithmetic lives in the third-party TensorFlow
+runtime (unpinned, ">= 1.6"); this file restates the published semantics of the TF ops at the reference's
+own call sites.  It is validated by (i) an fp64 twin of itself, (ii) finite differences of the torch twin
+(oracle/torch_oracle.py), (iii) closed-form properties (zero pose => verts == v_shaped, pure root rotation,
+translation equivariance of the rasterisers), and (iv) the committed vectors in tests/golden/, which were
+produced by THIS oracle (not by the reference) and only guard against drift.
+
+All file:line citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NUM_CAM = 4          # batch_smpl.py:90
+NUM_THETAS = 72      # batch_smpl.py:73
+MASK_GRID = 64       # compute_mask.py:44 (hard-coded, independent of img_wh)
+MASK_INVISIBLE = 500.0   # compute_mask.py:68
+
+
+# ------------------------------------------------------------------------------------------------
+# batch_smpl.py
+# ------------------------------------------------------------------------------------------------
+def batch_skew(vec):
+    """batch_smpl.py:230-253: scatter of [-z, y, z, -x, -y, x] into columns [1,2,3,5,6,7] of a 3x3."""
+    n = vec.shape[0]
+    res = np.zeros((n, 9), vec.dtype)
+    res[:, 1] = -vec[:, 2]
+    res[:, 2] = vec[:, 1]
+    res[:, 3] = vec[:, 2]
+    res[:, 5] = -vec[:, 0]
+    res[:, 6] = -vec[:, 1]
+    res[:, 7] = vec[:, 0]
+    return res.reshape(n, 3, 3)
+
+
+def batch_rodrigues(theta):
+    """batch_smpl.py:255-276.  theta: (N*24, 3)."""
+    dt = theta.dtype
+    tp = theta + dt.type(1e-8)                                                   # :265 (inside the norm only)
+    angle = np.sqrt(np.sum(tp * tp, axis=1, dtype=dt))[:, None]                  # tf.norm = sqrt(sum(x*x))
+    r = (theta / angle)[:, :, None]                                              # :266
+    angle = angle[:, :, None]                                                    # :268
+    cos = np.cos(angle)
+    sin = np.sin(angle)
+    outer = np.matmul(r, np.transpose(r, (0, 2, 1)))                             # :272
+    eyes = np.tile(np.eye(3, dtype=dt)[None], (theta.shape[0], 1, 1))            # :273
+    R = cos * eyes + (dt.type(1) - cos) * outer + sin * batch_skew(r[:, :, 0])   # :274-275
+    return R
+
+
+def batch_global_rigid_transformation(Rs, Js, parent):
+    """batch_smpl.py:168-228 with rotate_base=False.  Returns (new_J (N,24,3), A (N,24,4,4))."""
+    dt = Rs.dtype
+    N = Rs.shape[0]
+    root_rotation = Rs[:, 0, :, :]                                               # :192
+    Js = Js[..., None]                                                           # :195
+
+    def make_A(R, t):                                                            # :197-202
+        R_homo = np.pad(R, [[0, 0], [0, 1], [0, 0]])
+        t_homo = np.concatenate([t, np.ones((N, 1, 1), dt)], 1)
+        return np.concatenate([R_homo, t_homo], 2)
+
+    A0 = make_A(root_rotation, Js[:, 0])                                         # :204
+    results = [A0]
+    for i in range(1, parent.shape[0]):                                          # :206-211
+        j_here = Js[:, i] - Js[:, parent[i]]
+        A_here = make_A(Rs[:, i], j_here)
+        res_here = np.matmul(results[parent[i]], A_here)
+        results.append(res_here)
+    results = np.stack(results, axis=1)                                          # :214
+    new_J = results[:, :, :3, 3]                                                 # :216
+    Js_w0 = np.concatenate([Js, np.zeros((N, 24, 1, 1), dt)], 2)                 # :222
+    init_bone = np.matmul(results, Js_w0)                                        # :223
+    init_bone = np.pad(init_bone, [[0, 0], [0, 0], [0, 0], [3, 0]])              # :225
+    A = results - init_bone                                                      # :226
+    return new_J, A
+
+
+def smpl_layer_call(model, x, return_all=False, joint_type="lsp"):
+    """SMPLLayer.call (batch_smpl.py:96-153).  ``model`` is a SmplHostModel-like object whose arrays
+    already have the layouts ``build`` produces (:31-94); ``x`` is (N,86).  dtype follows ``x``."""
+    dt = x.dtype
+    c = lambda a: np.asarray(a, dt)  # noqa: E731
+    v_template, shapedirs, posedirs = c(model.v_template), c(model.shapedirs), c(model.posedirs)
+    J_regressor, lbs_weights = c(model.J_regressor), c(model.lbs_weights)
+    parents = np.asarray(model.parents)
+    N = x.shape[0]
+    V = v_template.shape[0]
+    thetas = x[:, NUM_CAM:NUM_THETAS + NUM_CAM]                                  # :98
+    betas = x[:, NUM_CAM + NUM_THETAS:]                                          # :99
+    v_shaped = np.reshape(betas @ shapedirs, [-1, V, 3]) + v_template            # :106-108
+    Jx = v_shaped[:, :, 0] @ J_regressor                                         # :112-115
+    Jy = v_shaped[:, :, 1] @ J_regressor
+    Jz = v_shaped[:, :, 2] @ J_regressor
+    J = np.stack([Jx, Jy, Jz], axis=2)
+    Rs = np.reshape(batch_rodrigues(np.reshape(thetas, [-1, 3])), [-1, 24, 3, 3])  # :119-120
+    pose_feature = np.reshape(Rs[:, 1:, :, :] - np.eye(3, dtype=dt), [-1, 207])  # :122
+    v_posed = np.reshape(pose_feature @ posedirs, [-1, V, 3]) + v_shaped         # :126-128
+    J_transformed, A = batch_global_rigid_transformation(Rs, J, parents)         # :131
+    W = np.reshape(np.tile(lbs_weights, [N, 1]), [N, -1, 24])                    # :135-136
+    T = np.reshape(np.matmul(W, np.reshape(A, [N, 24, 16])), [N, -1, 4, 4])      # :138-140
+    v_posed_homo = np.concatenate([v_posed, np.ones([N, V, 1], dt)], 2)          # :141-142
+    v_homo = np.matmul(T, v_posed_homo[..., None])                               # :143
+    verts = v_homo[:, :, :3, 0]                                                  # :145
+    if not return_all:
+        return verts
+    joint_regressor = c(model.joint_regressor)
+    if joint_type == "lsp":                                                      # :86-87
+        joint_regressor = joint_regressor[:, :14]
+    joints = np.stack([verts[:, :, k] @ joint_regressor for k in range(3)], axis=2)  # :147-151 (commented out upstream)
+    return dict(verts=verts, J_transformed=J_transformed, A=A, Rs=Rs, J=J, v_shaped=v_shaped, v_posed=v_posed,
+                pose_feature=pose_feature, joints=joints)
+
+
+# ------------------------------------------------------------------------------------------------
+# projection.py
+# ------------------------------------------------------------------------------------------------
+def orthographic_project(inputs, vertex_sampling):
+    """projection.py:54-81."""
+    verts, smpl = inputs
+    k_u, k_v, u0, v0 = smpl[:, 0:1], smpl[:, 1:2], smpl[:, 2:3], smpl[:, 3:4]
+    if vertex_sampling is not None:
+        verts = verts[:, ::vertex_sampling, :]                                   # :67-68
+    u = u0 + verts[:, :, 0] * k_u                                                # :77 (mul then add: two ops)
+    v = v0 + verts[:, :, 1] * k_v                                                # :78
+    return np.stack([u, v, verts[:, :, 2]], axis=2)                              # :79
+
+
+# ------------------------------------------------------------------------------------------------
+# compute_mask.py
+# ------------------------------------------------------------------------------------------------
+def compute_mask_one(pixels_with_depth):
+    """compute_mask_map_over_batch + get_min_depth_vert_index_at_pixel (compute_mask.py:35-108), literal:
+    one pass per pixel of the hard-coded 64x64 grid, argmax of z among the vertices that round onto it
+    (first index on ties), index 1 for an empty pixel, unique, scatter 1 into a 500-filled vector."""
+    img_wh = MASK_GRID
+    nv = pixels_with_depth.shape[0]
+    pu, pv, z = pixels_with_depth[:, 0], pixels_with_depth[:, 1], pixels_with_depth[:, 2]
+    winners = []
+    for r in range(img_wh):              # meshgrid 'xy': pixel_coord = (column, row), :49-54
+        row_sel = pv == np.float32(r)
+        for c in range(img_wh):
+            at = np.nonzero(row_sel & (pu == np.float32(c)))[0]                  # :90-92
+            if at.size == 0:
+                winners.append(1)                                                # tf.ones([1,1,4]) -> index 1, :98-99
+            else:
+                winners.append(int(at[np.argmax(z[at])]))                        # :100-102 (argmax, first on ties)
+    mask = np.ones(nv, np.float32) * np.float32(MASK_INVISIBLE)                  # :68
+    mask[np.unique(np.asarray(winners, np.int64))] = 1.0                         # :66,:69-70
+    return mask
+
+
+def compute_mask_one_fast(pixels_with_depth):
+    """Same result as compute_mask_one via a lexsort (used for larger oracle batches; equality is tested)."""
+    img_wh = MASK_GRID
+    nv = pixels_with_depth.shape[0]
+    pu, pv, z = pixels_with_depth[:, 0], pixels_with_depth[:, 1], pixels_with_depth[:, 2]
+    inside = (pu >= 0) & (pu <= img_wh - 1) & (pv >= 0) & (pv <= img_wh - 1)
+    idx = np.nonzero(inside)[0]
+    cell = (pv[idx].astype(np.int64) * img_wh + pu[idx].astype(np.int64))
+    zz = z[idx] + np.float32(0.0)
+    order = np.lexsort((idx, -zz.astype(np.float64), cell))      # by cell, then z descending, then index ascending
+    cs = cell[order]
+    first = np.ones(cs.shape[0], bool)
+    first[1:] = cs[1:] != cs[:-1]
+    win = idx[order][first]
+    mask = np.full(nv, MASK_INVISIBLE, np.float32)
+    mask[win] = 1.0
+    if np.unique(cs).size < img_wh * img_wh and nv > 1:
+        mask[1] = 1.0
+    return mask
+
+
+def compute_mask(batch_projects_with_depth, fast=True):
+    """compute_mask.py:12-32.  tf.round is round-half-to-even, as is np.round (np.rint)."""
+    p = np.asarray(batch_projects_with_depth, np.float32)
+    batch_pixels = np.rint(p[:, :, :2])                                          # :22
+    pwd = np.concatenate([batch_pixels, p[:, :, 2:3]], axis=2)                   # :23-25
+    f = compute_mask_one_fast if fast else compute_mask_one
+    return np.stack([f(pwd[n]) for n in range(pwd.shape[0])], 0)                 # :27-30 (map_fn, stateless intent)
+
+
+# ------------------------------------------------------------------------------------------------
+# projects_to_seg.py / projects_to_silhouette.py
+# ------------------------------------------------------------------------------------------------
+def _grid(img_wh, dt):
+    t1, t2 = np.meshgrid(np.arange(img_wh), np.arange(img_wh))                   # 'xy': t1 = column, t2 = row
+    return np.stack([t1, t2], axis=2).astype(dt).reshape(-1, 2)                  # projects_to_seg.py:26-31
+
+
+def projects_to_seg(inputs, img_wh, vertex_sampling, part_indices, pixel_chunk=None):
+    """projects_to_seg.py:9-69.  ``part_indices`` is the unpickled list of 31 lists of ORIGINAL vertex ids
+    (the reference reads it from disk at :18-24)."""
+    projects_with_depth, mask_vals = inputs
+    dt = projects_with_depth.dtype
+    projects = projects_with_depth[:, :, :2]
+    N = projects.shape[0]
+    reshaped_grid = _grid(img_wh, dt)                                            # (wh^2, 2)
+    segs = []
+    for part in range(len(part_indices)):
+        indices = part_indices[part]
+        if vertex_sampling is not None:
+            indices = [index // vertex_sampling for index in indices]            # :36-37
+        indices = np.asarray(indices, np.int64)
+        part_projects = projects[:, indices, :]                                  # (N, n, 2)   :41
+        part_mask_vals = mask_vals[:, indices]                                   # (N, n)      :45
+        diff = part_projects[:, None, :, :] - reshaped_grid[None, :, None, :]    # (N, wh^2, n, 2) :52
+        norm = np.sqrt(diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1])  # tf.norm: sqrt(sum(x*x))  :53
+        norm = norm * part_mask_vals[:, None, :]                                 # :54
+        exp = np.exp(-norm)                                                      # :55
+        scores = exp.max(axis=2) if indices.size else np.zeros((N, img_wh * img_wh), dt)  # :56
+        segs.append(scores.reshape(-1, img_wh, img_wh))                          # :57
+    stacked = np.stack(segs, axis=3)                                             # :60
+    sil = dt.type(1.0) - np.clip(np.sum(stacked, axis=3, dtype=dt), 0, 1)        # :61-64
+    out = np.concatenate([sil[..., None], stacked], axis=3)                      # :66-67
+    return out[:, ::-1].copy()                                                   # :68 flip rows
+
+
+def projects_to_silhouette(projects_with_depth, img_wh, row_chunk=8):
+    """projects_to_silhouette.py:14-44 (evaluated in row chunks only to bound memory; same arithmetic)."""
+    dt = projects_with_depth.dtype
+    projects = projects_with_depth[:, :, :2]
+    N = projects.shape[0]
+    grid = _grid(img_wh, dt)
+    scores = np.empty((N, img_wh * img_wh), dt)
+    step = row_chunk * img_wh
+    for s in range(0, img_wh * img_wh, step):
+        g = grid[s:s + step]
+        diff = projects[:, None, :, :] - g[None, :, None, :]                     # :35
+        norm = np.sqrt(diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1])  # :36
+        exp = np.exp(-norm / dt.type(1.2))                                       # :37
+        scores[:, s:s + step] = exp.max(axis=2)                                  # :38
+    sil = scores.reshape(-1, img_wh, img_wh)                                     # :39
+    out = np.stack([dt.type(1.0) - sil, sil], axis=3)                            # :40-41
+    return out[:, ::-1].copy()                                                   # :42
+
+
+# ------------------------------------------------------------------------------------------------
+# concat_mean_param.py / set_cam_params.py
+# ------------------------------------------------------------------------------------------------
+def _mean86(img_wh, mean_vals, with_smpl=True):
+    mean = np.zeros((1, 86))
+    if with_smpl:
+        mean_pose = np.array(mean_vals["pose"], np.float64)
+        mean_pose[:3] = 0.0                                                      # concat_mean_param.py:14
+        mean[0, 4:] = np.hstack((mean_pose, np.asarray(mean_vals["shape"], np.float64)))
+    mean[0, 0] = img_wh / 2.0
+    mean[0, 1] = img_wh / 2.0
+    mean[0, 2] = img_wh / 2.0
+    mean[0, 3] = img_wh / 1.6
+    return mean.astype(np.float32)                                               # tf.constant(..., float32)
+
+
+def concat_mean_param(img_features, img_wh, mean_vals):
+    """concat_mean_param.py:8-31."""
+    mean = np.tile(_mean86(img_wh, mean_vals), [img_features.shape[0], 1])
+    return np.concatenate([img_features, mean], axis=1)
+
+
+def set_cam_params(smpl, img_wh):
+    """set_cam_params.py:13-26."""
+    return smpl + np.tile(_mean86(img_wh, None, with_smpl=False), [smpl.shape[0], 1])
+
+
+def load_mean_set_cam_params(smpl, img_wh, mean_vals):
+    """set_cam_params.py:29-52."""
+    return smpl + np.tile(_mean86(img_wh, mean_vals), [smpl.shape[0], 1])
+
+
+# ------------------------------------------------------------------------------------------------
+# whole path
+# ------------------------------------------------------------------------------------------------
+def decode(model, params, img_wh, vertex_sampling, part_indices, silhouette_wh=None):
+    """model.py:108-118 tail: SMPLLayer -> orthographic_project -> compute_mask -> projects_to_seg
+    (+ train_stage2_silhouette.py:84 silhouette branch if ``silhouette_wh``)."""
+    params = np.asarray(params, np.float32)
+    allv = smpl_layer_call(model, params, return_all=True)
+    pwd = orthographic_project([allv["verts"], params], vertex_sampling)
+    mask = compute_mask(pwd)
+    seg = projects_to_seg([pwd, mask], img_wh, vertex_sampling, part_indices)
+    out = dict(allv, projects=pwd, mask=mask, seg=seg)
+    if silhouette_wh:
+        out["silhouette"] = projects_to_silhouette(pwd, silhouette_wh)
+    return out
