@@ -47,7 +47,8 @@ static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
   const int V = m->V;
   const int Vs = (V + vs - 1) / vs;
   const int ncols = Vs * 3;
-  std::vector<float> bt((size_t)ncols * kKPad, 0.f);
+  const int Kp = (ncols + 15) / 16 * 16;
+  std::vector<float> bt((size_t)Kp * kKPad, 0.f);
   for (int c = 0; c < ncols; ++c) {
     const int col = 3 * vs * (c / 3) + (c % 3);
     for (int k = 0; k < kK; ++k) bt[(size_t)c * kKPad + k] = m->h_Bm[(size_t)k * (3 * V) + col];
@@ -67,6 +68,7 @@ static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
   CU_TRY(upload(&t->csc_w, w));
   t->Vs = Vs;
   t->ncols = ncols;
+  t->Kp = Kp;
   t->vs = vs;  // publish last
   return 0;
 }
@@ -308,6 +310,7 @@ static size_t ru(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct DecodeWs {
   float *X, *A, *Jtr, *gA, *gX, *gcam, *gvp;
   size_t gvp_ld;
+  int cam_chunks;
   size_t bytes;
 };
 static DecodeWs decode_ws(const SmplB200Model* m, int N, bool bwd, bool full_grad, int vs, void* base) {
@@ -321,9 +324,10 @@ static DecodeWs decode_ws(const SmplB200Model* m, int N, bool bwd, bool full_gra
   if (bwd) {
     w.gA = take((size_t)N * kJ * 12);
     w.gX = take((size_t)N * kKPad);
-    w.gcam = take((size_t)N * 4);
     const int Vs = (m->V + vs - 1) / vs;
-    w.gvp_ld = full_grad ? (size_t)m->LD : ru((size_t)Vs * 3, 4);
+    w.cam_chunks = lbs_bwd_cam_chunks(Vs);
+    w.gcam = take((size_t)N * 4 * w.cam_chunks);
+    w.gvp_ld = full_grad ? (size_t)m->LD : ru((size_t)Vs * 3, 16);   // >= VsTables::Kp, rows stay 16-byte aligned
     w.gvp = take((size_t)N * w.gvp_ld);
   }
   w.bytes = off;
@@ -355,8 +359,8 @@ size_t smpl_b200_workspace_bytes(const SmplB200Model* m, int op, int N, int img_
 int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, float* verts, float* joints24,
                          float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* projects,
                          int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!m || !params || N < 0 || (!verts && !projects)) { set_error("decode_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
-  if (N == 0) return SMPL_B200_OK;
   const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
   if (!aligned(params, 4) || (verts && !aligned(verts, 8)) || (v_posed_save && !aligned(v_posed_save, 16)) || !aligned(workspace, 16)) {
     set_error("decode_fwd: misaligned buffer (verts 8B, v_posed_save/workspace 16B)"); return SMPL_B200_ERR_BAD_ARG;
@@ -385,8 +389,8 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
                          const float* g_verts, const float* g_projects, int vertex_sampling,
                          const float* g_joints24, float* g_params, void* workspace, size_t workspace_bytes,
                          void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!m || !params || !v_posed_save || !g_params || N < 0) { set_error("decode_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
-  if (N == 0) return SMPL_B200_OK;
   const int vs_in = vertex_sampling < 1 ? 1 : vertex_sampling;
   const bool full = (g_verts != nullptr) || !g_projects;     // dense vertex gradient (or none at all)
   const int vs_t = full ? 1 : vs_in;
@@ -402,32 +406,32 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp, w.gvp_ld, w.gA,
                               w.gcam, st));
   CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
-  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, N, g_params, st));
+  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, w.cam_chunks, N, g_params, st));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_project_fwd(const float* verts, const float* params, int N, int V, int vertex_sampling, float* projects,
                           void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!verts || !params || !projects || N < 0 || V < 1) { set_error("project_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_project_fwd(verts, params, N, V, vertex_sampling < 1 ? 1 : vertex_sampling, projects, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V,
                           int vertex_sampling, float* g_verts, float* g_params, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!verts || !params || !g_projects || !g_verts || !g_params || N < 0 || V < 1) {
     set_error("project_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG;
   }
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_project_bwd(verts, params, g_projects, N, V, vertex_sampling < 1 ? 1 : vertex_sampling, g_verts, g_params,
                                   (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_mask_fwd(const float* projects, int N, int Vs, float* mask, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!projects || !mask || N < 0 || Vs < 1) { set_error("mask_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_mask_fwd(projects, N, Vs, mask, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
@@ -442,39 +446,39 @@ static int seg_check(const SmplB200Parts* p, const void* a, const void* b, const
 
 int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs, int img_wh,
                       float* seg, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   int rc = seg_check(parts, projects, mask, seg, N, Vs, img_wh, "seg_fwd");
   if (rc) return rc;
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_seg_fwd(parts, projects, mask, N, Vs, img_wh, seg, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg, int N,
                       int Vs, int img_wh, float* g_projects, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   int rc = seg_check(parts, projects, mask, g_seg, N, Vs, img_wh, "seg_bwd");
   if (rc) return rc;
   if (!g_projects) { set_error("seg_bwd: null g_projects"); return SMPL_B200_ERR_BAD_ARG; }
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_seg_bwd(parts, projects, mask, g_seg, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,
                              size_t workspace_bytes, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   (void)workspace; (void)workspace_bytes;
   if (!projects || !sil || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   if (img_wh > 4096) { set_error("silhouette_fwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_sil_fwd(projects, N, Vs, img_wh, sil, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, int Vs, int img_wh, float* g_projects,
                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   (void)workspace; (void)workspace_bytes;
   if (!projects || !g_sil || !g_projects || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   if (img_wh > 4096) { set_error("silhouette_bwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
-  if (N == 0) return SMPL_B200_OK;
   CHECK_LAUNCH(launch_sil_bwd(projects, g_sil, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }

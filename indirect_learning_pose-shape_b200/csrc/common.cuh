@@ -5,9 +5,6 @@
 #include <stddef.h>
 #include "../../include/smpl_b200.h"
 
-#ifndef __CUDA_ARCH_LIST__
-#endif
-
 namespace smplb200 {
 
 constexpr int kJ = 24;            // joints
@@ -27,7 +24,8 @@ struct VsTables {       // per vertex_sampling derived tables (device pointers)
   int vs = 0;           // 0 = unused slot
   int Vs = 0;           // sampled vertex count
   int ncols = 0;        // Vs*3
-  float* BmT = nullptr;       // [ncols][kKPad] : BmT[c][k] = Bm[k][col(c)],  col(c) = 3*vs*(c/3) + c%3
+  int Kp = 0;           // ncols rounded up to a multiple of 16: depth of the backward blend product
+  float* BmT = nullptr;       // [Kp][kKPad] : BmT[c][k] = Bm[k][col(c)],  col(c) = 3*vs*(c/3) + c%3 ; zero rows past ncols
   int* csc_ptr = nullptr;     // [kJ+1]  joint -> entries (sampled vertices only)
   int* csc_vert = nullptr;    // [nnz]   ORIGINAL vertex id
   float* csc_w = nullptr;     // [nnz]
@@ -94,8 +92,11 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
                            float* g_vp, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st);
 cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
                              float* g_X, cudaStream_t st);
+// g_cam = [cam_chunks][N][4] partial camera-gradient sums from launch_lbs_bwd (or null)
 cudaError_t launch_pose_bwd(const SmplB200Model* m, const float* params, const float* g_A, const float* g_X,
-                            const float* g_Jtr, const float* g_cam, int N, float* g_params, cudaStream_t st);
+                            const float* g_Jtr, const float* g_cam, int cam_chunks, int N, float* g_params,
+                            cudaStream_t st);
+int lbs_bwd_cam_chunks(int num_processed_verts);
 cudaError_t launch_project_fwd(const float* verts, const float* params, int N, int V, int vs, float* projects,
                                cudaStream_t st);
 cudaError_t launch_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V, int vs,

@@ -1,0 +1,379 @@
+// K3: linear-blend skinning fused with the weak-perspective projection, forward and backward, plus the
+// stand-alone projection kernels and the optional keypoint regression.
+//
+// Reference arithmetic (file:line relative to the reference tree):
+//   skinning  T = W*A, verts = T*[v_posed;1] ... keras_smpl/batch_smpl.py:135-145
+//   orthographic_project ....................... keras_smpl/projection.py:54-81
+//   (commented) keypoint regression ............ keras_smpl/batch_smpl.py:147-151
+//
+// Layout: one block owns a chunk of 256 vertices and a group of kGroup samples.  Skin weights (ELL, <= KW
+// non-zeros per vertex) stay in registers for the whole group, the group's 24 bone transforms sit in shared
+// memory, and each sample's 768-float slice of v_posed / verts moves through a shared staging tile with
+// 16-byte coalesced loads and 8-byte coalesced stores (verts rows are only 8-byte aligned: 3*6890*4 % 16 == 8).
+#include "common.cuh"
+
+namespace smplb200 {
+
+namespace {
+
+constexpr int kChunk = 256;     // vertices per block
+constexpr int kGroup = 8;       // samples per block
+constexpr int kARow = kJ * 12;  // floats of bone transforms per sample
+
+template <int KW>
+struct Skin {
+  float w[KW];
+  int j[KW];
+};
+
+template <int KW>
+__device__ __forceinline__ Skin<KW> load_skin(const uint8_t* __restrict__ idx, const float* __restrict__ w, int v) {
+  Skin<KW> s;
+#pragma unroll
+  for (int k = 0; k < KW; k += 4) {
+    const uchar4 i4 = *reinterpret_cast<const uchar4*>(idx + (size_t)v * KW + k);
+    const float4 w4 = *reinterpret_cast<const float4*>(w + (size_t)v * KW + k);
+    s.j[k] = i4.x; s.j[k + 1] = i4.y; s.j[k + 2] = i4.z; s.j[k + 3] = i4.w;
+    s.w[k] = w4.x; s.w[k + 1] = w4.y; s.w[k + 2] = w4.z; s.w[k + 3] = w4.w;
+  }
+  return s;
+}
+
+// T (3x4, row-major) = sum_k w_k * A[j_k]   (batch_smpl.py:138-140; zero-weight joints contribute exact zeros)
+template <int KW>
+__device__ __forceinline__ void blend_T(const Skin<KW>& s, const float* __restrict__ As, float T[12]) {
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KW; ++k) {
+    const float4* a = reinterpret_cast<const float4*>(As + s.j[k] * 12);
+    const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+    const float w = s.w[k];
+    T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+    T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+    T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+  }
+}
+
+__device__ __forceinline__ void load_group_A(float* As, float* cam, const float* __restrict__ A,
+                                             const float* __restrict__ params, int n0, int rows) {
+  const float4* src = reinterpret_cast<const float4*>(A + (size_t)n0 * kARow);
+  float4* dst = reinterpret_cast<float4*>(As);
+  for (int i = threadIdx.x; i < rows * (kARow / 4); i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x < rows * 4) cam[threadIdx.x] = params[(size_t)(n0 + (threadIdx.x >> 2)) * kParams + (threadIdx.x & 3)];
+}
+
+template <int KW>
+__global__ void __launch_bounds__(kChunk)
+lbs_fwd_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A, const float* __restrict__ params,
+               int N, int V, const uint8_t* __restrict__ lbs_idx, const float* __restrict__ lbs_w,
+               float* __restrict__ verts, float* __restrict__ projects, int vs, int Vs) {
+  __shared__ __align__(16) float As[kGroup * kARow];
+  __shared__ float cam[kGroup * 4];
+  __shared__ __align__(16) float stage[2][kChunk * 3];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * kGroup;
+  const int rows = min(kGroup, N - n0);
+  const int v = blockIdx.x * kChunk + tid;
+  const bool valid = v < V;
+  const int col0 = blockIdx.x * kChunk * 3;
+  load_group_A(As, cam, A, params, n0, rows);
+  const Skin<KW> skin = load_skin<KW>(lbs_idx, lbs_w, valid ? v : 0);
+  const bool sampled = valid && projects && (v % vs == 0);
+  const bool need = valid && (verts || sampled);
+  const int q = v / vs;
+  if (tid < kChunk * 3 / 4)
+    reinterpret_cast<float4*>(stage[0])[tid] = *reinterpret_cast<const float4*>(vp + (size_t)n0 * LD + col0 + tid * 4);
+  __syncthreads();
+  for (int s = 0; s < rows; ++s) {
+    const int n = n0 + s;
+    float* st = stage[s & 1];
+    if (s + 1 < rows && tid < kChunk * 3 / 4)     // prefetch the next sample's slice into the other buffer
+      reinterpret_cast<float4*>(stage[(s + 1) & 1])[tid] =
+          *reinterpret_cast<const float4*>(vp + (size_t)(n + 1) * LD + col0 + tid * 4);
+    if (need) {
+      const float x = st[tid * 3], y = st[tid * 3 + 1], z = st[tid * 3 + 2];
+      float T[12];
+      blend_T<KW>(skin, As + s * kARow, T);
+      const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+      const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+      const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+      st[tid * 3] = ox; st[tid * 3 + 1] = oy; st[tid * 3 + 2] = oz;
+      if (sampled) {                               // projection.py:77-79: multiply, then add (two roundings)
+        float* p = projects + ((size_t)n * Vs + q) * 3;
+        p[0] = __fadd_rn(cam[s * 4 + 2], __fmul_rn(ox, cam[s * 4 + 0]));
+        p[1] = __fadd_rn(cam[s * 4 + 3], __fmul_rn(oy, cam[s * 4 + 1]));
+        p[2] = oz;
+      }
+    }
+    __syncthreads();
+    if (verts) {
+      float2* dst = reinterpret_cast<float2*>(verts + (size_t)n * V * 3 + col0);
+      const int lim = (V * 3 - col0) / 2;          // V*3 and col0 are even
+      for (int i = tid; i < kChunk * 3 / 2; i += kChunk)
+        if (i < lim) dst[i] = reinterpret_cast<const float2*>(st)[i];
+    }
+    __syncthreads();
+  }
+}
+
+// Gradient arriving at vertex v of sample n: dense g_verts plus the projection's adjoint at sampled vertices.
+__device__ __forceinline__ void vertex_grad(const float* __restrict__ g_verts, const float* __restrict__ g_projects,
+                                            int n, int v, int V, int vs_proj, int Vs_proj, float ku, float kv,
+                                            float& gx, float& gy, float& gz, float& gu, float& gv) {
+  gx = gy = gz = gu = gv = 0.f;
+  if (g_verts) {
+    const float* g = g_verts + ((size_t)n * V + v) * 3;
+    gx = g[0]; gy = g[1]; gz = g[2];
+  }
+  if (g_projects && v % vs_proj == 0) {
+    const float* g = g_projects + ((size_t)n * Vs_proj + v / vs_proj) * 3;
+    gu = g[0]; gv = g[1];
+    gx = fmaf(gu, ku, gx); gy = fmaf(gv, kv, gy); gz += g[2];
+  }
+}
+
+// Vertex-parallel half of the backward: g_vp = R_T^T g_vert (compact rows of gvp_ld floats, processed vertices only)
+// and per-chunk partial sums of the camera gradient.
+template <int KW>
+__global__ void __launch_bounds__(kChunk)
+lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A,
+                      const float* __restrict__ params, int N, int V, const uint8_t* __restrict__ lbs_idx,
+                      const float* __restrict__ lbs_w, const float* __restrict__ g_verts,
+                      const float* __restrict__ g_projects, int vs_proc, int Vp, int vs_proj, int Vs_proj,
+                      float* __restrict__ g_vp, int gvp_ld, int Kp, float* __restrict__ g_cam) {
+  __shared__ __align__(16) float As[kGroup * kARow];
+  __shared__ float cam[kGroup * 4];
+  __shared__ float red[kChunk / 32][4];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * kGroup;
+  const int rows = min(kGroup, N - n0);
+  const int q = blockIdx.x * kChunk + tid;          // processed-vertex index
+  const bool valid = q < Vp;
+  const int v = valid ? q * vs_proc : 0;
+  load_group_A(As, cam, A, params, n0, rows);
+  const Skin<KW> skin = load_skin<KW>(lbs_idx, lbs_w, v);
+  __syncthreads();
+  for (int s = 0; s < rows; ++s) {
+    const int n = n0 + s;
+    float c4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float ku = cam[s * 4], kv = cam[s * 4 + 1];
+      float gx, gy, gz, gu, gv;
+      vertex_grad(g_verts, g_projects, n, v, V, vs_proj, Vs_proj, ku, kv, gx, gy, gz, gu, gv);
+      float T[12];
+      blend_T<KW>(skin, As + s * kARow, T);
+      float* o = g_vp + (size_t)n * gvp_ld + (size_t)q * 3;
+      o[0] = fmaf(T[0], gx, fmaf(T[4], gy, T[8] * gz));
+      o[1] = fmaf(T[1], gx, fmaf(T[5], gy, T[9] * gz));
+      o[2] = fmaf(T[2], gx, fmaf(T[6], gy, T[10] * gz));
+      if (g_projects) {
+        const float* p = vp + (size_t)n * LD + (size_t)v * 3;
+        const float x = p[0], y = p[1], z = p[2];
+        const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+        const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+        c4[0] = gu * ox; c4[1] = gv * oy; c4[2] = gu; c4[3] = gv;   // u = u0 + x*k_u, v = v0 + y*k_v
+      }
+    }
+    if (blockIdx.x == gridDim.x - 1) {              // zero the K padding the blend backward reads
+      const int c = Vp * 3 + tid;
+      if (c < Kp) g_vp[(size_t)n * gvp_ld + c] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c4[k] = warp_sum(c4[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[tid >> 5][k] = c4[k];
+    }
+    __syncthreads();
+    if (tid < 4) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kChunk / 32; ++w) t += red[w][tid];
+      g_cam[((size_t)blockIdx.x * N + n) * 4 + tid] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// Joint-parallel half: one warp per (sample, joint) walks the joint's vertex list (CSC of the skin weights) and
+// reduces g_A[j] = sum_v w_vj * g_vert_v (x) [v_posed_v ; 1].  No atomics: the result is order-deterministic.
+__global__ void __launch_bounds__(256)
+lbs_bwd_joint_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ params, int N, int V,
+                     const int* __restrict__ csc_ptr, const int* __restrict__ csc_vert,
+                     const float* __restrict__ csc_w, const float* __restrict__ g_verts,
+                     const float* __restrict__ g_projects, int vs_proj, int Vs_proj, float* __restrict__ g_A) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)N * kJ) return;
+  const int n = (int)(wid / kJ), j = (int)(wid % kJ);
+  const float ku = params[(size_t)n * kParams], kv = params[(size_t)n * kParams + 1];
+  float acc[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+  const int e1 = csc_ptr[j + 1];
+  for (int e = csc_ptr[j] + lane; e < e1; e += 32) {
+    const int v = csc_vert[e];
+    const float w = csc_w[e];
+    float gx, gy, gz, gu, gv;
+    vertex_grad(g_verts, g_projects, n, v, V, vs_proj, Vs_proj, ku, kv, gx, gy, gz, gu, gv);
+    const float* p = vp + (size_t)n * LD + (size_t)v * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    gx *= w; gy *= w; gz *= w;
+    acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
+    acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
+    acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
+  }
+#pragma unroll
+  for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
+  if (lane < 3) {
+    float4 r;
+    if (lane == 0) r = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else if (lane == 1) r = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    else r = make_float4(acc[8], acc[9], acc[10], acc[11]);
+    reinterpret_cast<float4*>(g_A + ((size_t)n * kJ + j) * 12)[lane] = r;
+  }
+}
+
+// ---- stand-alone projection (projection.py:54-81) ---------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+project_fwd_kernel(const float* __restrict__ verts, const float* __restrict__ params, int N, int V, int vs, int Vs,
+                   float* __restrict__ projects) {
+  const int n = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Vs) return;
+  const float* prm = params + (size_t)n * kParams;
+  const float* p = verts + ((size_t)n * V + (size_t)q * vs) * 3;
+  float* o = projects + ((size_t)n * Vs + q) * 3;
+  o[0] = __fadd_rn(prm[2], __fmul_rn(p[0], prm[0]));
+  o[1] = __fadd_rn(prm[3], __fmul_rn(p[1], prm[1]));
+  o[2] = p[2];
+}
+
+// One block per sample: writes the whole g_verts row (zeros at unsampled vertices) and the whole g_params row.
+__global__ void __launch_bounds__(256)
+project_bwd_kernel(const float* __restrict__ verts, const float* __restrict__ params,
+                   const float* __restrict__ g_projects, int N, int V, int vs, int Vs, float* __restrict__ g_verts,
+                   float* __restrict__ g_params) {
+  __shared__ float red[8][4];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float ku = params[(size_t)n * kParams], kv = params[(size_t)n * kParams + 1];
+  float c4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int v = tid; v < V; v += blockDim.x) {
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (v % vs == 0) {
+      const float* g = g_projects + ((size_t)n * Vs + v / vs) * 3;
+      const float* p = verts + ((size_t)n * V + v) * 3;
+      gx = g[0] * ku; gy = g[1] * kv; gz = g[2];
+      c4[0] = fmaf(g[0], p[0], c4[0]); c4[1] = fmaf(g[1], p[1], c4[1]); c4[2] += g[0]; c4[3] += g[1];
+    }
+    float* o = g_verts + ((size_t)n * V + v) * 3;
+    o[0] = gx; o[1] = gy; o[2] = gz;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c4[k] = warp_sum(c4[k]);
+  if ((tid & 31) == 0)
+    for (int k = 0; k < 4; ++k) red[tid >> 5][k] = c4[k];
+  __syncthreads();
+  if (tid < kParams) {
+    float t = 0.f;
+    if (tid < 4)
+      for (int w = 0; w < 8; ++w) t += red[w][tid];
+    g_params[(size_t)n * kParams + tid] = t;
+  }
+}
+
+// ---- optional keypoint regression (the commented lines batch_smpl.py:147-151) -----------------------------------
+__global__ void __launch_bounds__(256)
+joints_reg_kernel(const float* __restrict__ verts, int N, int V, int R_used, const int* __restrict__ ptr,
+                  const int* __restrict__ vert, const float* __restrict__ w, float* __restrict__ joints) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)N * R_used) return;
+  const int n = (int)(wid / R_used), r = (int)(wid % R_used);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int e = ptr[r] + lane; e < ptr[r + 1]; e += 32) {
+    const float* p = verts + ((size_t)n * V + vert[e]) * 3;
+    const float ww = w[e];
+    a0 = fmaf(ww, p[0], a0); a1 = fmaf(ww, p[1], a1); a2 = fmaf(ww, p[2], a2);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) {
+    float* o = joints + ((size_t)n * R_used + r) * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
+  }
+}
+
+}  // namespace
+
+int lbs_bwd_cam_chunks(int Vp) { return (Vp + kChunk - 1) / kChunk; }
+
+cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
+                           float* verts, float* projects, int vs, cudaStream_t st) {
+  const int V = m->V, Vs = (V + vs - 1) / vs;
+  dim3 grid((V + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
+#define SMPL_LBS_FWD(KW)                                                                                          \
+  lbs_fwd_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, verts, projects, \
+                                              vs, Vs)
+  if (m->KW == 4) SMPL_LBS_FWD(4);
+  else if (m->KW == 8) SMPL_LBS_FWD(8);
+  else SMPL_LBS_FWD(24);
+#undef SMPL_LBS_FWD
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
+                           const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
+                           float* g_vp, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st) {
+  const int V = m->V, Vp = t->Vs, Vs_proj = (V + vs_proj - 1) / vs_proj;
+  dim3 grid((Vp + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
+#define SMPL_LBS_BWD(KW)                                                                                           \
+  lbs_bwd_vertex_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, g_verts,   \
+                                                     g_projects, t->vs, Vp, vs_proj, Vs_proj, g_vp, (int)gvp_ld, t->Kp, \
+                                                     g_cam)
+  if (m->KW == 4) SMPL_LBS_BWD(4);
+  else if (m->KW == 8) SMPL_LBS_BWD(8);
+  else SMPL_LBS_BWD(24);
+#undef SMPL_LBS_BWD
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const long long warps = (long long)N * kJ;
+  lbs_bwd_joint_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(v_posed, m->LD, params, N, V, t->csc_ptr, t->csc_vert,
+                                                                   t->csc_w, g_verts, g_projects, vs_proj, Vs_proj, g_A);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_project_fwd(const float* verts, const float* params, int N, int V, int vs, float* projects,
+                               cudaStream_t st) {
+  const int Vs = (V + vs - 1) / vs;
+  for (int n0 = 0; n0 < N; n0 += 65535) {     // gridDim.y limit
+    const int nn = min(65535, N - n0);
+    dim3 grid((Vs + 255) / 256, nn);
+    project_fwd_kernel<<<grid, 256, 0, st>>>(verts + (size_t)n0 * V * 3, params + (size_t)n0 * kParams, nn, V, vs, Vs,
+                                            projects + (size_t)n0 * Vs * 3);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V, int vs,
+                               float* g_verts, float* g_params, cudaStream_t st) {
+  const int Vs = (V + vs - 1) / vs;
+  project_bwd_kernel<<<N, 256, 0, st>>>(verts, params, g_projects, N, V, vs, Vs, g_verts, g_params);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, int N, int R_used, float* joints,
+                                  cudaStream_t st) {
+  const long long warps = (long long)N * R_used;
+  joints_reg_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(verts, N, m->V, R_used, m->jr_ptr, m->jr_vert, m->jr_w,
+                                                                joints);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace smplb200

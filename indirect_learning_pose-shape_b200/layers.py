@@ -1,0 +1,482 @@
+"""Host-side mirror of the reference's keras_smpl interface, backed by the sm_100a library.
+
+Names, argument order, list-style inputs and output layouts follow the reference (file:line relative to it):
+
+  SMPLLayer(pkl_path, batch_size=8, dtype='float32', joint_type='lsp')   keras_smpl/batch_smpl.py:23-166
+  orthographic_project([verts, smpl], vertex_sampling)                    keras_smpl/projection.py:54-81
+  compute_mask(batch_projects_with_depth)                                 keras_smpl/compute_mask.py:12-32
+  projects_to_seg([projects_with_depth, mask_vals], img_wh, vertex_sampling)   keras_smpl/projects_to_seg.py:9-69
+  projects_to_silhouette(projects_with_depth, img_wh)                     keras_smpl/projects_to_silhouette.py:14-44
+  concat_mean_param(img_features, img_wh)                                 keras_smpl/concat_mean_param.py:8-31
+  set_cam_params(smpl, img_wh) / load_mean_set_cam_params(smpl, img_wh)   keras_smpl/set_cam_params.py:13-52
+
+Tensors are torch CUDA float32; every op is a torch.autograd.Function whose forward and backward call the C ABI
+(include/smpl_b200.h) on torch's current stream.  There is no CPU or eager-PyTorch fallback: a CPU tensor, a missing
+library or a missing GPU raises.
+
+Documented deviations from the reference:
+  * `batch_size` is accepted but not required to match the runtime batch (the reference bakes it into the graph,
+    batch_smpl.py:120,135-142).
+  * compute_mask is stateless per sample (the docstring's intent, compute_mask.py:14-18), not the accidental
+    cross-call K.variable state of :68-70.
+  * gradients at a vertex that sits exactly on a pixel centre are 0 (TF's norm gradient gives NaN there); exact
+    ties in the max take the first arg-max (TF splits evenly).  Both are measure-zero events.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import weakref
+from typing import List, Optional, Sequence
+
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib, smpl_io
+
+NUM_PARAMS = 86
+NUM_JOINTS = 24
+
+
+def _vs(vertex_sampling) -> int:
+    return 1 if vertex_sampling is None else int(vertex_sampling)
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.SmplB200Error("%s is on %s: this package runs on CUDA only (no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# device handles
+# ------------------------------------------------------------------------------------------------------------
+class DeviceModel:
+    """Immutable device copy of the SMPL constants (SMPLLayer.build, batch_smpl.py:31-94)."""
+
+    def __init__(self, host_model: smpl_io.SmplHostModel, device):
+        lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SmplB200Error("SMPL model must live on a CUDA device (no CPU path)")
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        self.host = host_model
+        struct, keep = _lib.make_host_model(host_model)
+        handle = C.c_void_p()
+        _lib.check(lib.smpl_b200_model_create(C.byref(struct), index, C.byref(handle)), "smpl_b200_model_create")
+        del keep
+        self.handle = handle
+        self.V = int(lib.smpl_b200_model_num_verts(handle))
+        self.lbs_width = int(lib.smpl_b200_model_lbs_width(handle))
+        self.LD = (self.V * 3 + 127) // 128 * 128
+        self.R = int(host_model.joint_regressor.shape[1])
+        self._finalizer = weakref.finalize(self, lib.smpl_b200_model_destroy, handle)
+
+    def workspace_bytes(self, op: int, N: int, img_wh: int = 0, vs: int = 1) -> int:
+        return int(_lib.load().smpl_b200_workspace_bytes(self.handle, op, N, img_wh, vs))
+
+
+class PartTable:
+    """Device copy of a part->vertex list with indices divided by vertex_sampling (projects_to_seg.py:18-24,36-37)."""
+
+    def __init__(self, parts: Sequence[Sequence[int]], vertex_sampling, num_sampled_verts: int, device):
+        lib = _lib.load()
+        self.device = torch.device(device)
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        ptr, idx = smpl_io.sampled_part_table(parts, vertex_sampling)
+        self.P = len(parts)
+        self.Vs = int(num_sampled_verts)
+        handle = C.c_void_p()
+        i32p = C.POINTER(C.c_int32)
+        _lib.check(lib.smpl_b200_parts_create(index, self.P, ptr.ctypes.data_as(i32p), idx.ctypes.data_as(i32p), self.Vs,
+                                              C.byref(handle)), "smpl_b200_parts_create")
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, lib.smpl_b200_parts_destroy, handle)
+
+
+_cache_lock = threading.Lock()
+_model_cache = {}
+_parts_cache = {}
+
+
+def get_device_model(pkl_path_or_model, device) -> DeviceModel:
+    """One DeviceModel per (model, device); accepts a pickle path (the reference's argument) or a SmplHostModel."""
+    device = torch.device(device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (pkl_path_or_model if isinstance(pkl_path_or_model, str) else id(pkl_path_or_model), index)
+    with _cache_lock:
+        dm = _model_cache.get(key)
+        if dm is None:
+            host = smpl_io.load_smpl_pkl(pkl_path_or_model) if isinstance(pkl_path_or_model, str) else pkl_path_or_model
+            dm = DeviceModel(host, torch.device("cuda", index))
+            _model_cache[key] = dm
+        return dm
+
+
+def get_part_table(vertex_sampling, num_sampled_verts: int, device, part_indices_path: Optional[str] = None,
+                   parts: Optional[Sequence[Sequence[int]]] = None) -> PartTable:
+    """Part table for `vertex_sampling`.  Lookup order: explicit `parts`, explicit path, the reference's CWD-relative
+    literal (projects_to_seg.py:18-21), the copy of the same files shipped in this package's data/."""
+    device = torch.device(device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (id(parts) if parts is not None else (part_indices_path or ""), _vs(vertex_sampling), int(num_sampled_verts), index)
+    with _cache_lock:
+        pt = _parts_cache.get(key)
+        if pt is None:
+            if parts is None:
+                path = part_indices_path or smpl_io.part_vertices_filename(vertex_sampling)
+                if os.path.exists(path):
+                    parts = smpl_io.load_part_vertices(path)
+                elif part_indices_path is not None:
+                    raise IOError("part table %r not found" % part_indices_path)
+                else:
+                    parts = smpl_io.golden_part_vertices(vertex_sampling)
+            pt = PartTable(parts, vertex_sampling, num_sampled_verts, torch.device("cuda", index))
+            pt._parts_ref = parts
+            _parts_cache[key] = pt
+        return pt
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------------------
+class _DecodeFn(torch.autograd.Function):
+    """params (N,86) -> (verts, J_transformed, keypoints, projects); batch_smpl.py:96-153 (+ projection.py:54-81 fused)."""
+
+    @staticmethod
+    def forward(ctx, params, dm: DeviceModel, need_verts: bool, num_keypoints: int, project_vs: int):
+        lib = _lib.load()
+        params = _check_cuda_f32(params, "params")
+        if params.dim() != 2 or params.shape[1] != NUM_PARAMS:
+            raise ValueError("params must be (N,86), got %s" % (tuple(params.shape),))
+        if params.device != dm.device:
+            raise _lib.SmplB200Error("params on %s but the SMPL model is on %s" % (params.device, dm.device))
+        N = params.shape[0]
+        dev = params.device
+        with torch.cuda.device(dev):
+            verts = torch.empty((N, dm.V, 3), dtype=torch.float32, device=dev) if need_verts else None
+            joints = torch.empty((N, NUM_JOINTS, 3), dtype=torch.float32, device=dev)
+            keyp = torch.empty((N, num_keypoints, 3), dtype=torch.float32, device=dev) if num_keypoints else None
+            Vs = (dm.V + project_vs - 1) // project_vs if project_vs else 0
+            proj = torch.empty((N, Vs, 3), dtype=torch.float32, device=dev) if project_vs else None
+            vp = torch.empty((N, dm.LD), dtype=torch.float32, device=dev)
+            ws = _workspace(dm.workspace_bytes(_lib.OP_DECODE_FWD, N), dev)
+            _lib.check(lib.smpl_b200_decode_fwd(dm.handle, _ptr(params), N, _ptr(verts), _ptr(joints), _ptr(keyp),
+                                                num_keypoints, _ptr(vp), _ptr(proj), max(project_vs, 1), _ptr(ws),
+                                                ws.numel(), _stream()), "smpl_b200_decode_fwd")
+        ctx.dm, ctx.project_vs = dm, project_vs
+        ctx.save_for_backward(params, vp)
+        if keyp is not None:
+            ctx.mark_non_differentiable(keyp)     # dead code in the reference (batch_smpl.py:147-151): forward only
+        return verts, joints, keyp, proj
+
+    @staticmethod
+    def backward(ctx, g_verts, g_joints, g_keyp, g_proj):
+        lib = _lib.load()
+        params, vp = ctx.saved_tensors
+        dm = ctx.dm
+        N = params.shape[0]
+        dev = params.device
+        g_verts = None if g_verts is None else _check_cuda_f32(g_verts, "grad verts")
+        g_joints = None if g_joints is None else _check_cuda_f32(g_joints, "grad joints")
+        g_proj = None if g_proj is None else _check_cuda_f32(g_proj, "grad projects")
+        vs = max(ctx.project_vs, 1)
+        with torch.cuda.device(dev):
+            g_params = torch.empty_like(params)
+            ws_vs = 1 if (g_verts is not None or g_proj is None) else vs
+            ws = _workspace(dm.workspace_bytes(_lib.OP_DECODE_BWD, N, 0, ws_vs), dev)
+            _lib.check(lib.smpl_b200_decode_bwd(dm.handle, _ptr(params), N, _ptr(vp), _ptr(g_verts), _ptr(g_proj), vs,
+                                                _ptr(g_joints), _ptr(g_params), _ptr(ws), ws.numel(), _stream()),
+                       "smpl_b200_decode_bwd")
+        return g_params, None, None, None, None
+
+
+class _ProjectFn(torch.autograd.Function):
+    """projection.py:54-81, stand-alone."""
+
+    @staticmethod
+    def forward(ctx, verts, smpl, vs: int):
+        lib = _lib.load()
+        verts = _check_cuda_f32(verts, "verts")
+        smpl = _check_cuda_f32(smpl, "smpl")
+        N, V = verts.shape[0], verts.shape[1]
+        if smpl.shape[0] != N or smpl.shape[1] < 4:
+            raise ValueError("smpl must be (N, >=4) with the camera in columns 0..3")
+        if smpl.shape[1] != NUM_PARAMS:
+            raise ValueError("smpl must be (N,86) (model.py:33-35), got %s" % (tuple(smpl.shape),))
+        Vs = (V + vs - 1) // vs
+        with torch.cuda.device(verts.device):
+            proj = torch.empty((N, Vs, 3), dtype=torch.float32, device=verts.device)
+            _lib.check(lib.smpl_b200_project_fwd(_ptr(verts), _ptr(smpl), N, V, vs, _ptr(proj), _stream()),
+                       "smpl_b200_project_fwd")
+        ctx.vs = vs
+        ctx.save_for_backward(verts, smpl)
+        return proj
+
+    @staticmethod
+    def backward(ctx, g_proj):
+        lib = _lib.load()
+        verts, smpl = ctx.saved_tensors
+        g_proj = _check_cuda_f32(g_proj, "grad projects")
+        N, V = verts.shape[0], verts.shape[1]
+        with torch.cuda.device(verts.device):
+            g_verts = torch.empty_like(verts)
+            g_smpl = torch.empty_like(smpl)
+            _lib.check(lib.smpl_b200_project_bwd(_ptr(verts), _ptr(smpl), _ptr(g_proj), N, V, ctx.vs, _ptr(g_verts),
+                                                 _ptr(g_smpl), _stream()), "smpl_b200_project_bwd")
+        return g_verts, g_smpl, None
+
+
+class _SegFn(torch.autograd.Function):
+    """projects_to_seg.py:9-69."""
+
+    @staticmethod
+    def forward(ctx, pwd, mask, table: PartTable, img_wh: int):
+        lib = _lib.load()
+        pwd = _check_cuda_f32(pwd, "projects_with_depth")
+        mask = _check_cuda_f32(mask, "mask_vals")
+        N, Vs = pwd.shape[0], pwd.shape[1]
+        if pwd.dim() != 3 or pwd.shape[2] != 3 or tuple(mask.shape) != (N, Vs):
+            raise ValueError("expected projects (N,Vs,3) and mask (N,Vs), got %s and %s" %
+                             (tuple(pwd.shape), tuple(mask.shape)))
+        with torch.cuda.device(pwd.device):
+            seg = torch.empty((N, img_wh, img_wh, table.P + 1), dtype=torch.float32, device=pwd.device)
+            _lib.check(lib.smpl_b200_seg_fwd(table.handle, _ptr(pwd), _ptr(mask), N, Vs, img_wh, _ptr(seg), _stream()),
+                       "smpl_b200_seg_fwd")
+        ctx.table, ctx.img_wh = table, img_wh
+        ctx.save_for_backward(pwd, mask)
+        return seg
+
+    @staticmethod
+    def backward(ctx, g_seg):
+        lib = _lib.load()
+        pwd, mask = ctx.saved_tensors
+        g_seg = _check_cuda_f32(g_seg, "grad seg")
+        N, Vs = pwd.shape[0], pwd.shape[1]
+        with torch.cuda.device(pwd.device):
+            g_pwd = torch.empty_like(pwd)
+            _lib.check(lib.smpl_b200_seg_bwd(ctx.table.handle, _ptr(pwd), _ptr(mask), _ptr(g_seg), N, Vs, ctx.img_wh,
+                                             _ptr(g_pwd), _stream()), "smpl_b200_seg_bwd")
+        return g_pwd, None, None, None       # the mask is a constant (compute_mask.py:30, back_prop=False)
+
+
+class _SilFn(torch.autograd.Function):
+    """projects_to_silhouette.py:14-44."""
+
+    @staticmethod
+    def forward(ctx, pwd, img_wh: int):
+        lib = _lib.load()
+        pwd = _check_cuda_f32(pwd, "projects_with_depth")
+        N, Vs = pwd.shape[0], pwd.shape[1]
+        with torch.cuda.device(pwd.device):
+            sil = torch.empty((N, img_wh, img_wh, 2), dtype=torch.float32, device=pwd.device)
+            _lib.check(lib.smpl_b200_silhouette_fwd(_ptr(pwd), N, Vs, img_wh, _ptr(sil), None, 0, _stream()),
+                       "smpl_b200_silhouette_fwd")
+        ctx.img_wh = img_wh
+        ctx.save_for_backward(pwd)
+        return sil
+
+    @staticmethod
+    def backward(ctx, g_sil):
+        lib = _lib.load()
+        (pwd,) = ctx.saved_tensors
+        g_sil = _check_cuda_f32(g_sil, "grad silhouette")
+        N, Vs = pwd.shape[0], pwd.shape[1]
+        with torch.cuda.device(pwd.device):
+            g_pwd = torch.empty_like(pwd)
+            _lib.check(lib.smpl_b200_silhouette_bwd(_ptr(pwd), _ptr(g_sil), N, Vs, ctx.img_wh, _ptr(g_pwd), None, 0,
+                                                    _stream()), "smpl_b200_silhouette_bwd")
+        return g_pwd, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's public names
+# ------------------------------------------------------------------------------------------------------------
+class SMPLLayer(torch.nn.Module):
+    """Drop-in for keras_smpl.batch_smpl.SMPLLayer (batch_smpl.py:23-166).
+
+    `pkl_path` may also be a smpl_io.SmplHostModel (the real pickle is a licensed download).  `call(x)` maps
+    (N,86) params to (N,6890,3) vertices and leaves the posed joints in `self.J_transformed` (batch_smpl.py:131).
+    `joints(x)` additionally evaluates the cocoplus/LSP keypoint regression the reference keeps commented out
+    (batch_smpl.py:147-151).
+    """
+
+    def __init__(self, pkl_path, batch_size=8, dtype="float32", joint_type="lsp", device=None, **kwargs):
+        super().__init__()
+        if str(dtype) not in ("float32", "torch.float32"):
+            raise TypeError("only float32 is supported (reference default, batch_smpl.py:24)")
+        if joint_type not in ("lsp", "cocoplus"):
+            raise ValueError("joint_type must be 'lsp' or 'cocoplus'")
+        self.pkl_path = pkl_path
+        self.dtype_name = "float32"
+        self.joint_type = joint_type
+        self.batch_size = batch_size
+        self.num_cam = 4                                    # batch_smpl.py:90
+        self._device = None if device is None else torch.device(device)
+        self._dm: Optional[DeviceModel] = None
+        self.J_transformed = None
+        self.trainable = False                              # batch_smpl.py:92-94: no trainable weights
+
+    def build(self, input_shape=None, device=None):
+        """batch_smpl.py:31-94.  Raises IOError (FileNotFoundError) if the pickle is missing, like the reference."""
+        dev = torch.device(device) if device is not None else self._device
+        if dev is None or dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if self._dm is None or self._dm.device != dev:
+            self._dm = get_device_model(self.pkl_path, dev)
+        self.size = [self._dm.V, 3]
+        self.num_betas = 10
+        self.num_joints = NUM_JOINTS
+        self.num_thetas = NUM_JOINTS * 3
+        return self._dm
+
+    @property
+    def num_keypoints(self) -> int:
+        return 14 if self.joint_type == "lsp" else 19       # batch_smpl.py:86-87
+
+    def _model_for(self, x: torch.Tensor) -> DeviceModel:
+        if not x.is_cuda:
+            raise _lib.SmplB200Error("SMPLLayer input is on %s: CUDA only, no CPU fallback" % x.device)
+        if self._dm is None or self._dm.device != x.device:
+            self.build(device=x.device)
+        return self._dm
+
+    def call(self, x: torch.Tensor) -> torch.Tensor:
+        dm = self._model_for(x)
+        verts, joints, _, _ = _DecodeFn.apply(x, dm, True, 0, 0)
+        self.J_transformed = joints
+        return verts
+
+    forward = call
+
+    def joints(self, x: torch.Tensor):
+        """(verts, keypoints (N,14|19,3)): the commented-out regression of batch_smpl.py:147-151 (forward only)."""
+        dm = self._model_for(x)
+        verts, joints, keyp, _ = _DecodeFn.apply(x, dm, True, min(self.num_keypoints, dm.R), 0)
+        self.J_transformed = joints
+        return verts, keyp
+
+    def compute_output_shape(self, input_shape):
+        V = self._dm.V if self._dm is not None else smpl_io.NUM_VERTS
+        return (input_shape[0], V, 3)                       # batch_smpl.py:155-159
+
+    def get_config(self):
+        return {"pkl_path": self.pkl_path, "batch_size": self.batch_size, "dtype": self.dtype_name}   # :161-166
+
+
+def orthographic_project(inputs, vertex_sampling):
+    """projection.py:54-81: (verts (N,V,3), smpl (N,86)) -> (N, ceil(V/vs), 3) = (u, v, z)."""
+    verts, smpl = inputs
+    return _ProjectFn.apply(verts, smpl, _vs(vertex_sampling))
+
+
+def compute_mask(batch_projects_with_depth: torch.Tensor) -> torch.Tensor:
+    """compute_mask.py:12-32: (N,Vs,3) -> (N,Vs) in {1,500}; no gradient (back_prop=False)."""
+    lib = _lib.load()
+    pwd = _check_cuda_f32(batch_projects_with_depth.detach(), "batch_projects_with_depth")
+    if pwd.dim() != 3 or pwd.shape[2] != 3:
+        raise ValueError("expected (N,Vs,3), got %s" % (tuple(pwd.shape),))
+    N, Vs = pwd.shape[0], pwd.shape[1]
+    with torch.cuda.device(pwd.device):
+        mask = torch.empty((N, Vs), dtype=torch.float32, device=pwd.device)
+        _lib.check(lib.smpl_b200_mask_fwd(_ptr(pwd), N, Vs, _ptr(mask), _stream()), "smpl_b200_mask_fwd")
+    return mask
+
+
+def projects_to_seg(input, img_wh, vertex_sampling, part_indices_path: Optional[str] = None, parts=None):
+    """projects_to_seg.py:9-69: ([projects (N,Vs,3), mask (N,Vs)]) -> (N, wh, wh, 32), channel 0 = background,
+    rows flipped.  The part table is read from the reference's CWD-relative file unless given explicitly."""
+    projects_with_depth, mask_vals = input
+    table = get_part_table(vertex_sampling, projects_with_depth.shape[1], projects_with_depth.device,
+                           part_indices_path, parts)
+    return _SegFn.apply(projects_with_depth, mask_vals, table, int(img_wh))
+
+
+def projects_to_silhouette(projects_with_depth, img_wh):
+    """projects_to_silhouette.py:14-44: (N,Vs,3) -> (N, wh, wh, 2) = [1-s, s], rows flipped."""
+    return _SilFn.apply(projects_with_depth, int(img_wh))
+
+
+_mean_cache = {}
+
+
+def _mean_tensor(img_wh, device, with_smpl: bool, mean_params_path: Optional[str] = None) -> torch.Tensor:
+    key = (float(img_wh), str(device), with_smpl, mean_params_path)
+    t = _mean_cache.get(key)
+    if t is None:
+        if with_smpl:
+            m = smpl_io.mean_param_vector(img_wh, smpl_io.load_mean_params(mean_params_path))
+        else:
+            m = np.zeros((1, NUM_PARAMS))
+            m[0, :4] = [img_wh / 2.0, img_wh / 2.0, img_wh / 2.0, img_wh / 1.6]
+        t = torch.as_tensor(m.astype(np.float32), device=device)       # tf.constant(..., dtype='float32')
+        _mean_cache[key] = t
+    return t
+
+
+def concat_mean_param(img_features, img_wh, mean_params_path: Optional[str] = None):
+    """concat_mean_param.py:8-31: (N,F) -> (N,F+86) = [features | mean params]."""
+    mean = _mean_tensor(img_wh, img_features.device, True, mean_params_path)
+    return torch.cat([img_features, mean.expand(img_features.shape[0], -1)], dim=1)
+
+
+def set_cam_params(smpl, img_wh):
+    """set_cam_params.py:13-26: adds the camera initialisation [wh/2, wh/2, wh/2, wh/1.6] to columns 0..3."""
+    return smpl + _mean_tensor(img_wh, smpl.device, False)
+
+
+def load_mean_set_cam_params(smpl, img_wh, mean_params_path: Optional[str] = None):
+    """set_cam_params.py:29-52: adds the mean pose (global rotation zeroed), mean shape and camera initialisation."""
+    return smpl + _mean_tensor(img_wh, smpl.device, True, mean_params_path)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the whole path as one module (model.py:108-118 tail; + train_stage2_silhouette.py:84 silhouette branch)
+# ------------------------------------------------------------------------------------------------------------
+class SmplDecoder(torch.nn.Module):
+    """params (N,86) -> dict(seg, [silhouette], projects, mask, [verts], joints): the decoder tail of
+    model.py:108-118 with the projection fused into the skinning kernel."""
+
+    def __init__(self, pkl_path, img_wh: int, vertex_sampling=None, silhouette_wh: Optional[int] = None,
+                 need_verts: bool = True, parts=None, part_indices_path: Optional[str] = None, device=None):
+        super().__init__()
+        self.smpl = SMPLLayer(pkl_path, device=device)
+        self.img_wh = int(img_wh)
+        self.vertex_sampling = vertex_sampling
+        self.silhouette_wh = silhouette_wh
+        self.need_verts = need_verts
+        self._parts, self._parts_path = parts, part_indices_path
+
+    def forward(self, params: torch.Tensor, seg: bool = True):
+        dm = self.smpl._model_for(params)
+        vs = _vs(self.vertex_sampling)
+        verts, joints, _, proj = _DecodeFn.apply(params, dm, self.need_verts, 0, vs)
+        self.smpl.J_transformed = joints
+        out = {"verts": verts, "joints": joints, "projects": proj}
+        if seg:
+            mask = compute_mask(proj)
+            table = get_part_table(self.vertex_sampling, proj.shape[1], proj.device, self._parts_path, self._parts)
+            out["mask"] = mask
+            out["seg"] = _SegFn.apply(proj, mask, table, self.img_wh)
+        if self.silhouette_wh:
+            out["silhouette"] = _SilFn.apply(proj, int(self.silhouette_wh))
+        return out

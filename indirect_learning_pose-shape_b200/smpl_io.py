@@ -30,7 +30,9 @@ NUM_PARTS = 31
 # (batch_smpl.py:71, :206-211).
 SMPL_PARENTS = np.array([-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21], np.int32)
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_fixtures.npz")
+# The reference's own data files (part tables, mean-parameter h5 bytes, template geometry of the PLY), extracted by
+# tools/make_golden_fixtures.py; used when the CWD-relative files the reference opens are not present.
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ref_fixtures.npz")
 
 
 @dataclass

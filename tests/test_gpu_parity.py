@@ -1,0 +1,370 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the oracle restatement on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): vertices, joints, projections <= 1e-5 absolute in fp32; segmentation labels
+identical except float-rounding boundary pixels (<= 0.1 %).  Soft scores are compared at 2e-6 absolute (exp differs by
+1-2 ulp between libm/SIMD and CUDA).  Integer-valued outputs (the visibility mask) must be bit-exact on identical
+inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle, torch_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_GEOM = 1e-5
+TOL_SCORE = 2e-6
+LABEL_MISMATCH_MAX = 1e-3
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev())
+
+
+@pytest.fixture(scope="module")
+def layer(pkg, host_model):
+    return pkg.SMPLLayer(host_model, device=dev())
+
+
+@pytest.fixture(scope="module")
+def tconst(host_model):
+    return torch_oracle.TorchSmplConstants(host_model, torch.float32)
+
+
+@pytest.fixture(scope="module")
+def tconst64(host_model):
+    return torch_oracle.TorchSmplConstants(host_model, torch.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SMPL decode
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 70])
+def test_decode_forward(pkg, host_model, layer, make_params, n):
+    p = make_params(n, 48, seed=n)
+    ref = np_oracle.smpl_layer_call(host_model, p, return_all=True)
+    verts = layer(t(p))
+    torch.cuda.synchronize()
+    assert verts.shape == (n, 6890, 3)
+    assert np.abs(verts.cpu().numpy() - ref["verts"]).max() <= TOL_GEOM
+    assert np.abs(layer.J_transformed.cpu().numpy() - ref["J_transformed"]).max() <= TOL_GEOM
+
+
+def test_decode_forward_vs_fp64(pkg, host_model, layer, make_params):
+    """Error attribution: both the kernel and the fp32 oracle sit within 1e-5 of the fp64 oracle."""
+    p = make_params(6, 48, seed=3)
+    ref64 = np_oracle.smpl_layer_call(host_model, p.astype(np.float64), return_all=True)["verts"]
+    ref32 = np_oracle.smpl_layer_call(host_model, p, return_all=True)["verts"]
+    got = layer(t(p)).cpu().numpy()
+    assert np.abs(got - ref64).max() <= TOL_GEOM
+    assert np.abs(ref32 - ref64).max() <= TOL_GEOM
+
+
+def test_decode_mean_params_config1(pkg, host_model, layer):
+    """BASELINE config 1: batch 1, neutral mean parameters (concat_mean_param.py:12-25)."""
+    p = pkg.smpl_io.mean_param_vector(48).astype(np.float32)
+    ref = np_oracle.smpl_layer_call(host_model, p, return_all=True)
+    got = layer(t(p)).cpu().numpy()
+    assert np.abs(got - ref["verts"]).max() <= TOL_GEOM
+
+
+def test_zero_pose_is_shape_blend(pkg, host_model, layer):
+    p = np.zeros((3, 86), np.float32)
+    p[:, 76:] = np.random.default_rng(0).standard_normal((3, 10)).astype(np.float32)
+    got = layer(t(p)).cpu().numpy()
+    v_shaped = (p[:, 76:] @ host_model.shapedirs).reshape(3, -1, 3) + host_model.v_template
+    assert np.abs(got - v_shaped).max() <= 2e-6
+
+
+def test_keypoints(pkg, host_model, make_params):
+    p = make_params(4, 48, seed=9)
+    for jt, k in (("lsp", 14), ("cocoplus", 19)):
+        layer = pkg.SMPLLayer(host_model, joint_type=jt, device=dev())
+        ref = np_oracle.smpl_layer_call(host_model, p, return_all=True, joint_type=jt)
+        verts, keyp = layer.joints(t(p))
+        assert keyp.shape == (4, k, 3)
+        assert np.abs(keyp.cpu().numpy() - ref["joints"]).max() <= TOL_GEOM
+
+
+@pytest.mark.parametrize("vs", [None, 2, 5])
+def test_projection(pkg, host_model, layer, make_params, vs):
+    p = make_params(5, 48, seed=11)
+    ref = np_oracle.smpl_layer_call(host_model, p)
+    ref_p = np_oracle.orthographic_project([ref, p], vs)
+    # stand-alone op on the oracle's vertices: bit-exact (one multiply, one add, no contraction)
+    got = pkg.orthographic_project([t(ref), t(p)], vs).cpu().numpy()
+    assert got.shape == ref_p.shape
+    assert np.array_equal(got, ref_p)
+    # fused decode + projection.  |u| ~ 24..48 here, so 1e-5 is 2.6 ulp: the fp32 oracle itself sits a few ulp from
+    # the exact value.  Bound the kernel by 1e-5 against the fp64 oracle, and against the fp32 oracle by 1e-5 plus
+    # the fp32 oracle's own distance from fp64 (triangle inequality), both measured here.
+    p64 = p.astype(np.float64)
+    ref_p64 = np_oracle.orthographic_project([np_oracle.smpl_layer_call(host_model, p64), p64], vs)
+    oracle_noise = np.abs(ref_p - ref_p64).max()
+    dec = pkg.SmplDecoder(host_model, 48, vs, device=dev())
+    out = dec(t(p), seg=False)
+    got_p = out["projects"].cpu().numpy()
+    assert np.abs(got_p - ref_p64).max() <= TOL_GEOM
+    assert np.abs(got_p - ref_p).max() <= TOL_GEOM + oracle_noise
+    assert np.abs(out["verts"].cpu().numpy() - ref).max() <= TOL_GEOM
+
+
+def _decode_loss_torch(C, x, vs, w_v, w_j, w_p):
+    o = torch_oracle.smpl_layer_call(C, x, return_all=True)
+    pr = torch_oracle.orthographic_project([o["verts"], x], vs)
+    return (o["verts"] * w_v).sum() + (o["J_transformed"] * w_j).sum() + (pr * w_p).sum()
+
+
+@pytest.mark.parametrize("n,vs,use_verts", [(3, None, True), (5, 5, False), (5, 5, True), (70, 5, False), (66, 2, True)])
+def test_decode_backward(pkg, host_model, tconst, tconst64, make_params, n, vs, use_verts):
+    """d(loss)/d(params) through decode (+ fused projection) against torch autograd of the oracle twin."""
+    rng = np.random.default_rng(n)
+    p = make_params(n, 48, seed=20 + n)
+    Vs = -(-6890 // (vs or 1))
+    w_v = rng.standard_normal((n, 6890, 3)).astype(np.float32) * (1.0 if use_verts else 0.0)
+    w_j = rng.standard_normal((n, 24, 3)).astype(np.float32)
+    w_p = rng.standard_normal((n, Vs, 3)).astype(np.float32)
+    # oracle, fp64 (reference value) and fp32 (the parity target's own rounding noise)
+    grads = {}
+    for name, C, dt in (("f64", tconst64, torch.float64), ("f32", tconst, torch.float32)):
+        x = torch.tensor(p, dtype=dt, requires_grad=True)
+        _decode_loss_torch(C, x, vs, torch.tensor(w_v, dtype=dt), torch.tensor(w_j, dtype=dt),
+                           torch.tensor(w_p, dtype=dt)).backward()
+        grads[name] = x.grad.numpy().astype(np.float64)
+    dec = pkg.SmplDecoder(host_model, 48, vs, need_verts=True, device=dev())
+    x = t(p).requires_grad_(True)
+    out = dec(x, seg=False)
+    loss = (out["joints"] * t(w_j)).sum() + (out["projects"] * t(w_p)).sum()
+    if use_verts:
+        loss = loss + (out["verts"] * t(w_v)).sum()
+    loss.backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    scale = np.abs(grads["f64"]).max(axis=0, keepdims=True) + 1e-6
+    err = np.abs(got - grads["f64"]) / scale
+    noise = np.abs(grads["f32"] - grads["f64"]) / scale
+    assert err.max() <= max(5e-5, 4 * noise.max()), (err.max(), noise.max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# visibility mask
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vs", [None, 5])
+def test_mask_bit_exact(pkg, host_model, make_params, vs):
+    p = make_params(6, 48, seed=5)
+    pr = np_oracle.orthographic_project([np_oracle.smpl_layer_call(host_model, p), p], vs)
+    ref = np_oracle.compute_mask(pr)
+    got = pkg.compute_mask(t(pr)).cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert set(np.unique(got)) <= {1.0, 500.0}
+
+
+def test_mask_edge_cases(pkg):
+    """ties in z (lowest index wins), half-to-even rounding, out-of-grid vertices, the 'index 1' quirk, -0.0."""
+    rng = np.random.default_rng(1)
+    pr = (rng.random((4, 300, 3)) * 70 - 3).astype(np.float32)
+    pr[0, :40, 2] = 0.5                       # many equal depths
+    pr[0, :20, :2] = [10.2, 11.4]             # ... on the same pixel
+    pr[1, :8, 0] = [0.5, 1.5, 2.5, 3.5, -0.5, 63.5, 62.5, 64.49]   # half-way cases
+    pr[1, :8, 1] = 7.0
+    pr[2, :6, :2] = [-0.2, 0.3]
+    pr[2, :6, 2] = [0.0, -0.0, 0.0, -0.0, -1.0, -0.0]
+    pr[3, :, :2] = 200.0                      # nothing lands on the grid: only vertex 1 is "visible"
+    ref_lit = np.stack([np_oracle.compute_mask_one(np.concatenate([np.rint(pr[i, :, :2]), pr[i, :, 2:]], 1))
+                        for i in range(4)])
+    got = pkg.compute_mask(t(pr)).cpu().numpy()
+    assert np.array_equal(got, ref_lit)
+    assert got[3, 1] == 1.0 and (got[3] == 1.0).sum() == 1
+
+
+def test_mask_full_grid_no_vertex1_quirk(pkg):
+    """When all 4096 pixels are occupied nothing votes for index 1."""
+    c, r = np.meshgrid(np.arange(64), np.arange(64))
+    pr = np.stack([c.ravel(), r.ravel(), np.ones(4096)], 1).astype(np.float32)
+    pr = np.concatenate([pr, pr + np.array([0.1, 0.1, -0.5], np.float32)], 0)[None]     # occluded duplicates
+    got = pkg.compute_mask(t(pr)).cpu().numpy()
+    assert np.array_equal(got, np_oracle.compute_mask(pr))
+    assert (got[0, :4096] == 1).all() and (got[0, 4096:] == 500).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# part segmentation
+# ---------------------------------------------------------------------------------------------------------------
+def _labels(seg):
+    return seg.argmax(-1)
+
+
+def _oracle_inputs(host_model, make_params, n, wh, vs, seed):
+    p = make_params(n, wh, seed=seed)
+    pr = np_oracle.orthographic_project([np_oracle.smpl_layer_call(host_model, p), p], vs)
+    return p, pr, np_oracle.compute_mask(pr)
+
+
+@pytest.mark.parametrize("n,wh,vs", [(3, 48, 5), (2, 48, None), (2, 64, 2), (1, 33, 5)])
+def test_seg_forward(pkg, host_model, parts_by_vs, make_params, n, wh, vs):
+    p, pr, mask = _oracle_inputs(host_model, make_params, n, wh, vs, seed=31)
+    ref = np_oracle.projects_to_seg([pr, mask], wh, vs, parts_by_vs[vs])
+    got = pkg.projects_to_seg([t(pr), t(mask)], wh, vs, parts=parts_by_vs[vs]).cpu().numpy()
+    assert got.shape == (n, wh, wh, 32)
+    assert np.abs(got - ref).max() <= TOL_SCORE
+    assert (_labels(got) != _labels(ref)).mean() <= LABEL_MISMATCH_MAX
+
+
+def test_seg_arbitrary_weights(pkg, parts_by_vs):
+    """Drop-in inputs: any positive weights, not only compute_mask's {1,500} (generic and heavy classes), vertices
+    on pixel centres, vertices outside the image, an all-invisible sample."""
+    rng = np.random.default_rng(7)
+    n, Vs, wh = 4, 1378, 48
+    pr = np.concatenate([rng.random((n, Vs, 2)) * 60 - 6, rng.standard_normal((n, Vs, 1))], 2).astype(np.float32)
+    mask = rng.choice(np.array([1.0, 500.0, 2.5, 0.3, 300.0, 1000.0], np.float32), size=(n, Vs))
+    pr[0, :200, :2] = np.rint(pr[0, :200, :2]) + rng.choice([0.0, 1e-3, -2e-4, 0.05], size=(200, 1)).astype(np.float32)
+    mask[1] = 500.0
+    pr[1, :300, :2] = np.rint(pr[1, :300, :2]) + (rng.random((300, 2)).astype(np.float32) - 0.5) * 0.3
+    mask[2] = 1.0
+    ref = np_oracle.projects_to_seg([pr, mask], wh, 5, parts_by_vs[5])
+    got = pkg.projects_to_seg([t(pr), t(mask)], wh, 5, parts=parts_by_vs[5]).cpu().numpy()
+    assert np.abs(got - ref).max() <= TOL_SCORE
+    assert (_labels(got) != _labels(ref)).mean() <= LABEL_MISMATCH_MAX
+
+
+def _seg_grad_oracle(pr, mask, wh, vs, parts, g, dt):
+    x = torch.tensor(pr, dtype=dt, requires_grad=True)
+    out = torch_oracle.projects_to_seg([x, torch.tensor(mask, dtype=dt)], wh, vs, parts)
+    (out * torch.tensor(g, dtype=dt)).sum().backward()
+    return x.grad.numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("n,wh,vs", [(3, 48, 5), (1, 48, None), (2, 64, 2)])
+def test_seg_backward(pkg, host_model, parts_by_vs, make_params, n, wh, vs):
+    p, pr, mask = _oracle_inputs(host_model, make_params, n, wh, vs, seed=41)
+    g = np.random.default_rng(2).standard_normal((n, wh, wh, 32)).astype(np.float32)
+    ref64 = _seg_grad_oracle(pr, mask, wh, vs, parts_by_vs[vs], g, torch.float64)
+    x = t(pr).requires_grad_(True)
+    out = pkg.projects_to_seg([x, t(mask)], wh, vs, parts=parts_by_vs[vs])
+    (out * t(g)).sum().backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    assert np.all(got[..., 2] == 0)
+    scale = np.abs(ref64).max() + 1e-9
+    # a handful of (pixel, part) arg-min decisions may flip at float-rounding ties between fp32 and fp64
+    bad = np.abs(got - ref64) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(got - ref64).max(), scale)
+
+
+def test_seg_backward_weighted_and_gate(pkg, parts_by_vs):
+    """Gradient with heavy winners, generic weights, and pixels whose part sum exceeds 1 (clip gate closed)."""
+    rng = np.random.default_rng(17)
+    n, Vs, wh = 2, 1378, 48
+    pr = np.concatenate([rng.random((n, Vs, 2)) * 50 - 1, rng.standard_normal((n, Vs, 1))], 2).astype(np.float32)
+    mask = rng.choice(np.array([1.0, 500.0, 500.0, 2.0], np.float32), size=(n, Vs))
+    pr[0, :400, :2] = np.rint(pr[0, :400, :2]) + (rng.random((400, 2)).astype(np.float32) - 0.5) * 0.01
+    g = rng.standard_normal((n, wh, wh, 32)).astype(np.float32)
+    ref64 = _seg_grad_oracle(pr, mask, wh, 5, parts_by_vs[5], g, torch.float64)
+    x = t(pr).requires_grad_(True)
+    (pkg.projects_to_seg([x, t(mask)], wh, 5, parts=parts_by_vs[5]) * t(g)).sum().backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    scale = np.abs(ref64).max() + 1e-9
+    bad = np.abs(got - ref64) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(got - ref64).max(), scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# silhouette
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,wh,vs", [(2, 48, None), (2, 64, 5), (1, 256, None), (1, 100, 2)])
+def test_silhouette_forward(pkg, host_model, make_params, n, wh, vs):
+    p, pr, _ = _oracle_inputs(host_model, make_params, n, wh, vs, seed=51)
+    ref = np_oracle.projects_to_silhouette(pr, wh)
+    got = pkg.projects_to_silhouette(t(pr), wh).cpu().numpy()
+    assert got.shape == (n, wh, wh, 2)
+    assert np.abs(got - ref).max() <= TOL_SCORE
+    assert (_labels(got) != _labels(ref)).mean() <= LABEL_MISMATCH_MAX
+
+
+def test_silhouette_scattered_points(pkg):
+    """Sparse, clustered and out-of-image vertices: exercises long ring searches and clamped border cells."""
+    rng = np.random.default_rng(3)
+    wh = 96
+    pr = np.zeros((3, 500, 3), np.float32)
+    pr[0, :, :2] = rng.random((500, 2)) * 8 + 70                      # one tight cluster in a corner
+    pr[1, :, :2] = rng.random((500, 2)) * 400 - 150                    # mostly outside the image
+    pr[2, :, :2] = np.rint(rng.random((500, 2)) * 95)                  # on pixel centres (d == 0)
+    ref = np_oracle.projects_to_silhouette(pr, wh)
+    got = pkg.projects_to_silhouette(t(pr), wh).cpu().numpy()
+    assert np.abs(got - ref).max() <= TOL_SCORE
+
+
+@pytest.mark.parametrize("n,wh,vs", [(2, 48, None), (1, 128, 5)])
+def test_silhouette_backward(pkg, host_model, make_params, n, wh, vs):
+    p, pr, _ = _oracle_inputs(host_model, make_params, n, wh, vs, seed=61)
+    g = np.random.default_rng(4).standard_normal((n, wh, wh, 2)).astype(np.float32)
+    x64 = torch.tensor(pr, dtype=torch.float64, requires_grad=True)
+    (torch_oracle.projects_to_silhouette(x64, wh) * torch.tensor(g, dtype=torch.float64)).sum().backward()
+    ref64 = x64.grad.numpy()
+    x = t(pr).requires_grad_(True)
+    (pkg.projects_to_silhouette(x, wh) * t(g)).sum().backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    assert np.all(got[..., 2] == 0)
+    scale = np.abs(ref64).max() + 1e-9
+    bad = np.abs(got - ref64) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(got - ref64).max(), scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole path
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,vs", [(4, 5), (2, None)])
+def test_full_path_forward(pkg, host_model, parts_by_vs, make_params, n, vs):
+    wh = 48
+    p = make_params(n, wh, seed=71)
+    ref = np_oracle.decode(host_model, p, wh, vs, parts_by_vs[vs])
+    dec = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev())
+    out = dec(t(p))
+    assert np.abs(out["verts"].cpu().numpy() - ref["verts"]).max() <= TOL_GEOM
+    assert np.abs(out["projects"].cpu().numpy() - ref["projects"]).max() <= 2.5 * TOL_GEOM   # see test_projection
+    # projections differ by ~1e-6, so a vertex within that of a .5 boundary may change pixel: allow a tiny mismatch
+    assert (out["mask"].cpu().numpy() != ref["mask"]).mean() <= 2e-3
+    seg = out["seg"].cpu().numpy()
+    assert (_labels(seg) != _labels(ref["seg"])).mean() <= 5e-3
+    same = (out["mask"].cpu().numpy() == ref["mask"]).all(axis=1)
+    if same.any():
+        assert np.abs(seg[same] - ref["seg"][same]).max() <= 1e-4      # |ds| <= |dd| ~ 1e-5 * few
+
+
+def test_full_path_backward_runs_and_matches(pkg, host_model, parts_by_vs, tconst64, make_params):
+    """End-to-end d(loss)/d(params) for the training configuration (vs=5, 48x48), vs the fp64 torch oracle."""
+    n, wh, vs = 3, 48, 5
+    p = make_params(n, wh, seed=81)
+    g = np.random.default_rng(5).standard_normal((n, wh, wh, 32))
+    x64 = torch.tensor(p, dtype=torch.float64, requires_grad=True)
+    o = torch_oracle.decode(tconst64, x64, wh, vs, parts_by_vs[vs])
+    (o["seg"] * torch.tensor(g)).sum().backward()
+    ref = x64.grad.numpy()
+    dec = pkg.SmplDecoder(host_model, wh, vs, need_verts=False, parts=parts_by_vs[vs], device=dev())
+    x = t(p).requires_grad_(True)
+    out = dec(x)
+    assert out["verts"] is None
+    (out["seg"] * t(g.astype(np.float32))).sum().backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    same_mask = (out["mask"].cpu().numpy() == o["mask"].numpy()).all(axis=1)
+    assert same_mask.any()
+    scale = np.abs(ref).max(axis=0, keepdims=True) + 1e-6
+    err = (np.abs(got - ref) / scale)[same_mask]
+    assert err.max() <= 2e-2, err.max()       # thousands of arg-min terms per parameter; a few flip at fp32 ties
+    assert np.median(err) <= 1e-4
+
+
+def test_errors(pkg, host_model):
+    layer = pkg.SMPLLayer(host_model, device=dev())
+    with pytest.raises(pkg.SmplB200Error):
+        layer(torch.zeros(2, 86))                         # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        layer(torch.zeros(2, 85, device=dev()))
+    with pytest.raises(TypeError):
+        layer(torch.zeros(2, 86, device=dev(), dtype=torch.float64))
+    with pytest.raises((IOError, OSError)):
+        pkg.SMPLLayer("./does_not_exist.pkl", device=dev()).build()
+    assert layer(torch.zeros(0, 86, device=dev())).shape == (0, 6890, 3)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Extract the reference's *data* fixtures into tests/golden/ref_fixtures.npz.
+"""Extract the reference's *data* fixtures into indirect_learning_pose-shape_b200/data/ref_fixtures.npz.
 
 Run once in the build container (needs /root/reference, which does not exist on
 the GPU box).  Only data is extracted, never source:
@@ -24,7 +24,8 @@ import sys
 import numpy as np
 
 REF = os.environ.get("SMPL_REF_DIR", "/root/reference")
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_fixtures.npz")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "indirect_learning_pose-shape_b200", "data",
+                   "ref_fixtures.npz")
 
 
 def read_ply_vertices(path):
