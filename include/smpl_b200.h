@@ -68,6 +68,18 @@ const char* smpl_b200_last_error(void);
 /* number of kernel launches issued through this library by the calling process since load (all threads) */
 uint64_t smpl_b200_launch_count(void);
 
+/* ---- built-in profiler ------------------------------------------------------------------------------ */
+/* While enabled, every kernel launch of the library is bracketed by a cudaEvent pair recorded on the launching
+ * stream (the reference's counterpart is the TF FULL_TRACE timeline of profiling_renderer.py:39-50).
+ * collect() synchronises the recorded events, returns per-kernel launch counts and summed durations, and resets. */
+typedef struct SmplB200KernelStat {
+  const char* name;   /* static string, e.g. "seg_fwd" */
+  long long launches;
+  double total_ms;
+} SmplB200KernelStat;
+int smpl_b200_profile_enable(int on);
+int smpl_b200_profile_collect(SmplB200KernelStat* out, int max_stats, int* num_stats);
+
 /* ---- handles ---------------------------------------------------------------------------------------- */
 /* SMPLLayer.__init__/build (batch_smpl.py:24-94): uploads and repacks the constants on `device`. */
 int smpl_b200_model_create(const SmplB200HostModel* host, int device, SmplB200Model** out);

@@ -6,7 +6,7 @@ interface and include/smpl_b200.h for the C ABI underneath.  The directory name 
     import importlib; smpl = importlib.import_module("indirect_learning_pose-shape_b200")
 """
 from . import smpl_io  # noqa: F401  (numpy only; safe without the CUDA library)
-from ._lib import SmplB200Error, launch_count, load as load_library  # noqa: F401
+from ._lib import SmplB200Error, launch_count, load as load_library, profile_collect, profile_enable  # noqa: F401
 from .layers import (  # noqa: F401
     DeviceModel,
     PartTable,
@@ -27,4 +27,4 @@ from .sharding import all_gather_outputs, shard_bounds, shard_slice  # noqa: F40
 __all__ = ["SMPLLayer", "SmplDecoder", "orthographic_project", "compute_mask", "projects_to_seg",
            "projects_to_silhouette", "concat_mean_param", "set_cam_params", "load_mean_set_cam_params",
            "DeviceModel", "PartTable", "get_device_model", "get_part_table", "smpl_io", "SmplB200Error",
-           "launch_count", "load_library", "shard_bounds", "shard_slice", "all_gather_outputs"]
+           "launch_count", "load_library", "profile_enable", "profile_collect", "shard_bounds", "shard_slice", "all_gather_outputs"]

@@ -28,11 +28,18 @@ class HostModel(C.Structure):
                 ("lbs_weights", _f32p), ("parents", _i32p), ("joint_regressor", _f32p)]
 
 
+class KernelStat(C.Structure):
+    """struct SmplB200KernelStat"""
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_longlong), ("total_ms", C.c_double)]
+
+
 # name -> (restype, argtypes): exactly the symbols include/smpl_b200.h declares
 SIGNATURES = {
     "smpl_b200_abi_version": (C.c_int, []),
     "smpl_b200_last_error": (C.c_char_p, []),
     "smpl_b200_launch_count": (C.c_uint64, []),
+    "smpl_b200_profile_enable": (C.c_int, [C.c_int]),
+    "smpl_b200_profile_collect": (C.c_int, [C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]),
     "smpl_b200_model_create": (C.c_int, [C.POINTER(HostModel), C.c_int, C.POINTER(C.c_void_p)]),
     "smpl_b200_model_destroy": (None, [C.c_void_p]),
     "smpl_b200_model_num_verts": (C.c_int, [C.c_void_p]),
@@ -100,6 +107,19 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(load().smpl_b200_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    """Bracket every kernel launch of the library with CUDA events on its stream (see smpl_b200_profile_enable)."""
+    check(load().smpl_b200_profile_enable(1 if on else 0), "smpl_b200_profile_enable")
+
+
+def profile_collect() -> dict:
+    """{kernel name: (launches, total_ms)} since the last collect; synchronises the recorded events."""
+    stats = (KernelStat * 32)()
+    n = C.c_int(0)
+    check(load().smpl_b200_profile_collect(stats, 32, C.byref(n)), "smpl_b200_profile_collect")
+    return {stats[i].name.decode(): (int(stats[i].launches), float(stats[i].total_ms)) for i in range(min(n.value, 32))}
 
 
 def _fp(a: np.ndarray):

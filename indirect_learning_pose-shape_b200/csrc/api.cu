@@ -25,6 +25,39 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- built-in profiler: CUDA-event pairs around every launch, on the launching stream ---------------------------
+static const char* const kKernelNames[KID_COUNT] = {
+    "pose_fwd", "blend_fwd", "lbs_fwd", "joints_reg", "lbs_bwd_vertex", "lbs_bwd_joint", "blend_bwd", "pose_bwd",
+    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd"};
+struct ProfRecord { int kid; cudaEvent_t a, b; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mutex;
+static std::vector<ProfRecord> g_prof_records;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+LaunchScope::LaunchScope(int kid, cudaStream_t s) : slot(-1), st(s) {
+  count_launch();
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  ProfRecord r{kid, prof_event(), prof_event()};
+  if (!r.a || !r.b) return;
+  cudaEventRecord(r.a, st);
+  slot = (int)g_prof_records.size();
+  g_prof_records.push_back(r);
+}
+LaunchScope::~LaunchScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  cudaEventRecord(g_prof_records[slot].b, st);
+}
+
 #define CU_TRY(expr)                                                                         \
   do {                                                                                       \
     cudaError_t e__ = (expr);                                                                \
@@ -105,6 +138,35 @@ extern "C" {
 int smpl_b200_abi_version(void) { return SMPL_B200_ABI_VERSION; }
 const char* smpl_b200_last_error(void) { return g_err; }
 uint64_t smpl_b200_launch_count(void) { return g_launches.load(); }
+
+int smpl_b200_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_profile_collect(SmplB200KernelStat* out, int max_stats, int* num_stats) {
+  if (!num_stats || (max_stats > 0 && !out) || max_stats < 0) { set_error("profile_collect: bad argument"); return SMPL_B200_ERR_BAD_ARG; }
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  double ms[KID_COUNT] = {0};
+  long long cnt[KID_COUNT] = {0};
+  for (ProfRecord& r : g_prof_records) {
+    float t = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("profile_collect: %s", cudaGetErrorString(e)); g_prof_records.clear(); return SMPL_B200_ERR_CUDA; }
+    ms[r.kid] += t; cnt[r.kid] += 1;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_records.clear();
+  int n = 0;
+  for (int k = 0; k < KID_COUNT; ++k) {
+    if (!cnt[k]) continue;
+    if (n < max_stats) { out[n].name = kKernelNames[k]; out[n].launches = cnt[k]; out[n].total_ms = ms[k]; }
+    ++n;
+  }
+  *num_stats = n;
+  return SMPL_B200_OK;
+}
 
 int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model** out) {
   if (!h || !out) { set_error("model_create: null argument"); return SMPL_B200_ERR_BAD_ARG; }

@@ -183,6 +183,7 @@ blend_bwd_skinny_kernel(const float* __restrict__ gvp, int gvp_ld, const float* 
 constexpr int kDenseBatch = 64;   // below this the blend is a bandwidth-bound skinny product
 
 cudaError_t launch_blend_fwd(const SmplB200Model* m, const float* X, int N, float* v_posed, cudaStream_t st) {
+  LaunchScope scope(KID_BLEND_FWD, st);
   if (N < kDenseBatch) {
     dim3 grid(m->LD / 128, (N + kSkinnyRows - 1) / kSkinnyRows);
     blend_fwd_skinny_kernel<<<grid, 256, 0, st>>>(X, m->Bm, m->vt_pad, v_posed, N, m->LD);
@@ -191,13 +192,13 @@ cudaError_t launch_blend_fwd(const SmplB200Model* m, const float* X, int N, floa
     sgemm_128x128_kernel<true><<<grid, kThreads, 0, st>>>(X, kKPad, m->Bm, m->LD, v_posed, m->LD, m->vt_pad, N, m->LD,
                                                          kKPad);
   }
-  count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
                              float* g_X, cudaStream_t st) {
   (void)m;
+  LaunchScope scope(KID_BLEND_BWD, st);
   if (N < kDenseBatch) {
     cudaError_t e = cudaMemsetAsync(g_X, 0, sizeof(float) * (size_t)N * kKPad, st);
     if (e != cudaSuccess) return e;
@@ -208,7 +209,6 @@ cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const fl
     sgemm_128x128_kernel<false><<<grid, kThreads, 0, st>>>(g_vp, (int)gvp_ld, t->BmT, kKPad, g_X, kKPad, nullptr, N, kKPad,
                                                           t->Kp);
   }
-  count_launch();
   return cudaGetLastError();
 }
 

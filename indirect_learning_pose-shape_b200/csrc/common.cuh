@@ -20,6 +20,21 @@ constexpr int kMaxVsCache = 8;
 void set_error(const char* fmt, ...);
 void count_launch();
 
+// Kernel ids for the built-in profiler (smpl_b200_profile_*): one per __global__ function of the library.
+enum KernelId {
+  KID_POSE_FWD = 0, KID_BLEND_FWD, KID_LBS_FWD, KID_JOINTS_REG, KID_LBS_BWD_VERTEX, KID_LBS_BWD_JOINT, KID_BLEND_BWD,
+  KID_POSE_BWD, KID_PROJECT_FWD, KID_PROJECT_BWD, KID_MASK, KID_SEG_FWD, KID_SEG_BWD, KID_SIL_FWD, KID_SIL_BWD,
+  KID_COUNT
+};
+// RAII scope around one kernel launch: counts it and, while profiling is enabled, brackets it with CUDA events
+// recorded on the launching stream.
+struct LaunchScope {
+  LaunchScope(int kid, cudaStream_t st);
+  ~LaunchScope();
+  int slot;
+  cudaStream_t st;
+};
+
 struct VsTables {       // per vertex_sampling derived tables (device pointers)
   int vs = 0;           // 0 = unused slot
   int Vs = 0;           // sampled vertex count

@@ -312,6 +312,7 @@ cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const f
                            float* verts, float* projects, int vs, cudaStream_t st) {
   const int V = m->V, Vs = (V + vs - 1) / vs;
   dim3 grid((V + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
+  LaunchScope scope(KID_LBS_FWD, st);
 #define SMPL_LBS_FWD(KW)                                                                                          \
   lbs_fwd_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, verts, projects, \
                                               vs, Vs)
@@ -319,7 +320,6 @@ cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const f
   else if (m->KW == 8) SMPL_LBS_FWD(8);
   else SMPL_LBS_FWD(24);
 #undef SMPL_LBS_FWD
-  count_launch();
   return cudaGetLastError();
 }
 
@@ -328,6 +328,9 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
                            float* g_vp, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st) {
   const int V = m->V, Vp = t->Vs, Vs_proj = (V + vs_proj - 1) / vs_proj;
   dim3 grid((Vp + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
+  cudaError_t e;
+  {
+    LaunchScope scope(KID_LBS_BWD_VERTEX, st);
 #define SMPL_LBS_BWD(KW)                                                                                           \
   lbs_bwd_vertex_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, g_verts,   \
                                                      g_projects, t->vs, Vp, vs_proj, Vs_proj, g_vp, (int)gvp_ld, t->Kp, \
@@ -336,13 +339,13 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
   else if (m->KW == 8) SMPL_LBS_BWD(8);
   else SMPL_LBS_BWD(24);
 #undef SMPL_LBS_BWD
-  count_launch();
-  cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) return e;
   const long long warps = (long long)N * kJ;
+  LaunchScope scope(KID_LBS_BWD_JOINT, st);
   lbs_bwd_joint_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(v_posed, m->LD, params, N, V, t->csc_ptr, t->csc_vert,
                                                                    t->csc_w, g_verts, g_projects, vs_proj, Vs_proj, g_A);
-  count_launch();
   return cudaGetLastError();
 }
 
@@ -352,9 +355,9 @@ cudaError_t launch_project_fwd(const float* verts, const float* params, int N, i
   for (int n0 = 0; n0 < N; n0 += 65535) {     // gridDim.y limit
     const int nn = min(65535, N - n0);
     dim3 grid((Vs + 255) / 256, nn);
+    LaunchScope scope(KID_PROJECT_FWD, st);
     project_fwd_kernel<<<grid, 256, 0, st>>>(verts + (size_t)n0 * V * 3, params + (size_t)n0 * kParams, nn, V, vs, Vs,
                                             projects + (size_t)n0 * Vs * 3);
-    count_launch();
   }
   return cudaGetLastError();
 }
@@ -362,17 +365,17 @@ cudaError_t launch_project_fwd(const float* verts, const float* params, int N, i
 cudaError_t launch_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V, int vs,
                                float* g_verts, float* g_params, cudaStream_t st) {
   const int Vs = (V + vs - 1) / vs;
+  LaunchScope scope(KID_PROJECT_BWD, st);
   project_bwd_kernel<<<N, 256, 0, st>>>(verts, params, g_projects, N, V, vs, Vs, g_verts, g_params);
-  count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, int N, int R_used, float* joints,
                                   cudaStream_t st) {
   const long long warps = (long long)N * R_used;
+  LaunchScope scope(KID_JOINTS_REG, st);
   joints_reg_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(verts, N, m->V, R_used, m->jr_ptr, m->jr_vert, m->jr_w,
                                                                 joints);
-  count_launch();
   return cudaGetLastError();
 }
 

@@ -68,8 +68,8 @@ mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict
 }  // namespace
 
 cudaError_t launch_mask_fwd(const float* projects, int N, int Vs, float* mask, cudaStream_t st) {
+  LaunchScope scope(KID_MASK, st);
   mask_kernel<<<N, 256, 0, st>>>(projects, N, Vs, mask);
-  count_launch();
   return cudaGetLastError();
 }
 

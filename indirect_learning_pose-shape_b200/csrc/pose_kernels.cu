@@ -310,8 +310,8 @@ pose_bwd_kernel(const float* __restrict__ params, int N, const float* __restrict
 cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* A, float* Jtr,
                             cudaStream_t st) {
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  LaunchScope scope(KID_POSE_FWD, st);
   pose_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, X, A, Jtr);
-  count_launch();
   return cudaGetLastError();
 }
 
@@ -319,9 +319,9 @@ cudaError_t launch_pose_bwd(const SmplB200Model* m, const float* params, const f
                             const float* g_Jtr, const float* g_cam, int cam_chunks, int N, float* g_params,
                             cudaStream_t st) {
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  LaunchScope scope(KID_POSE_BWD, st);
   pose_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, g_A, g_X, g_Jtr, g_cam,
                                                          cam_chunks, g_params);
-  count_launch();
   return cudaGetLastError();
 }
 

@@ -289,8 +289,8 @@ cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const 
   int split = 1;
   if (N < 2 * 148) split = max(1, min(ngroups / warps, (2 * 148 + N - 1) / N));
   dim3 grid(N, split);
+  LaunchScope scope(KID_SEG_FWD, st);
   seg_fwd_kernel<<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg);
-  count_launch();
   return cudaGetLastError();
 }
 
@@ -302,8 +302,8 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  LaunchScope scope(KID_SEG_BWD, st);
   seg_bwd_kernel<<<N, warps * 32, smem, st>>>(projects, mask, g_seg, N, Vs, p->ptr, p->idx, p->P, p->E, wh, g_projects);
-  count_launch();
   return cudaGetLastError();
 }
 

@@ -220,8 +220,8 @@ cudaError_t launch_sil(const float* projects, const float* g_sil, int N, int Vs,
     if (e != cudaSuccess) return e;
   }
   dim3 grid(N, split);
+  LaunchScope scope(BWD ? KID_SIL_BWD : KID_SIL_FWD, st);
   sil_kernel<BWD><<<grid, 256, smem, st>>>(projects, g_sil, N, Vs, wh, B, G, out);
-  count_launch();
   return cudaGetLastError();
 }
 
