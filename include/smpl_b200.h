@@ -139,12 +139,18 @@ int smpl_b200_project_bwd(const float* verts, const float* params, const float* 
 int smpl_b200_mask_fwd(const float* projects, int N, int Vs, float* mask, void* stream);
 
 /* ---- projects_to_seg (projects_to_seg.py:9-69) -------------------------------------------------------- */
-/* projects (N,Vs,3), mask (N,Vs) -> seg (N,wh,wh,num_parts+1): channel 0 background, rows flipped. */
+/* projects (N,Vs,3), mask (N,Vs) -> seg (N,wh,wh,num_parts+1): channel 0 background, rows flipped.
+ * `saved` (nullable) receives what the backward needs instead of a second search: 32 bytes per pixel -- the clip
+ * gate (0 <= sum_k s_k <= 1) and the arg-min of every part (index into the part's visible-vertex list; 0xff none,
+ * 0xfe re-query) -- in an opaque, kernel-tile order.  Size: smpl_b200_seg_saved_bytes(); 16-byte aligned.
+ * `seg` may be NULL when only `saved` is wanted. */
+size_t smpl_b200_seg_saved_bytes(int N, int img_wh);
 int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs,
-                      int img_wh, float* seg, void* stream);
-/* g_seg (N,wh,wh,P+1) -> g_projects (N,Vs,3), fully written (z column and untouched vertices are 0). */
+                      int img_wh, float* seg, void* saved, void* stream);
+/* g_seg (N,wh,wh,P+1) + the forward's `saved` -> g_projects (N,Vs,3), fully written (z column and untouched
+ * vertices are 0).  projects and mask must be the forward's inputs. */
 int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg,
-                      int N, int Vs, int img_wh, float* g_projects, void* stream);
+                      const void* saved, int N, int Vs, int img_wh, float* g_projects, void* stream);
 
 /* ---- projects_to_silhouette (projects_to_silhouette.py:14-44) ------------------------------------------ */
 /* projects (N,Vs,3) -> sil (N,wh,wh,2): channel 0 = 1-s, channel 1 = s, rows flipped. */

@@ -498,30 +498,53 @@ int smpl_b200_mask_fwd(const float* projects, int N, int Vs, float* mask, void* 
   return SMPL_B200_OK;
 }
 
-static int seg_check(const SmplB200Parts* p, const void* a, const void* b, const void* c, int N, int Vs, int wh, const char* who) {
-  if (!p || !a || !b || !c || N < 0) { set_error("%s: null/invalid argument", who); return SMPL_B200_ERR_BAD_ARG; }
+static int seg_check(const SmplB200Parts* p, const void* a, const void* b, int N, int Vs, int wh, const char* who) {
+  if (!p || !a || !b || N < 0) { set_error("%s: null/invalid argument", who); return SMPL_B200_ERR_BAD_ARG; }
   if (Vs != p->Vs) { set_error("%s: Vs=%d does not match the part table (%d)", who, Vs, p->Vs); return SMPL_B200_ERR_BAD_ARG; }
   if (wh < 1 || wh > 128) { set_error("%s: img_wh=%d unsupported (1..128)", who, wh); return SMPL_B200_ERR_UNSUPPORTED; }
-  if (!aligned(c, 16)) { set_error("%s: seg buffer must be 16-byte aligned", who); return SMPL_B200_ERR_BAD_ARG; }
+  if (p->E > 65534) { set_error("%s: part table too large (%d entries, max 65534)", who, p->E); return SMPL_B200_ERR_UNSUPPORTED; }
   return 0;
 }
 
+size_t smpl_b200_seg_saved_bytes(int N, int img_wh) {
+  if (N < 0 || img_wh < 0) return 0;
+  return seg_saved_bytes(N, img_wh);
+}
+
 int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs, int img_wh,
-                      float* seg, void* stream) {
+                      float* seg, void* saved, void* stream) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
-  int rc = seg_check(parts, projects, mask, seg, N, Vs, img_wh, "seg_fwd");
+  int rc = seg_check(parts, projects, mask, N, Vs, img_wh, "seg_fwd");
   if (rc) return rc;
-  CHECK_LAUNCH(launch_seg_fwd(parts, projects, mask, N, Vs, img_wh, seg, (cudaStream_t)stream));
+  if (!seg && !saved) { set_error("seg_fwd: both outputs are null"); return SMPL_B200_ERR_BAD_ARG; }
+  if ((seg && !aligned(seg, 16)) || (saved && !aligned(saved, 16))) {
+    set_error("seg_fwd: seg/saved must be 16-byte aligned"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  cudaError_t e = launch_seg_fwd(parts, projects, mask, N, Vs, img_wh, seg, (unsigned char*)saved, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) {
+    set_error("seg_fwd: part table (%d entries) and img_wh=%d need more than 227 KB of shared memory", parts->E, img_wh);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  CHECK_LAUNCH(e);
   return SMPL_B200_OK;
 }
 
-int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg, int N,
-                      int Vs, int img_wh, float* g_projects, void* stream) {
+int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg,
+                      const void* saved, int N, int Vs, int img_wh, float* g_projects, void* stream) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
-  int rc = seg_check(parts, projects, mask, g_seg, N, Vs, img_wh, "seg_bwd");
+  int rc = seg_check(parts, projects, mask, N, Vs, img_wh, "seg_bwd");
   if (rc) return rc;
-  if (!g_projects) { set_error("seg_bwd: null g_projects"); return SMPL_B200_ERR_BAD_ARG; }
-  CHECK_LAUNCH(launch_seg_bwd(parts, projects, mask, g_seg, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
+  if (!g_seg || !saved || !g_projects) {
+    set_error("seg_bwd: null g_seg / saved / g_projects (run seg_fwd with a `saved` buffer first)");
+    return SMPL_B200_ERR_BAD_ARG;
+  }
+  cudaError_t e = launch_seg_bwd(parts, projects, mask, g_seg, (const unsigned char*)saved, N, Vs, img_wh, g_projects,
+                                 (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) {
+    set_error("seg_bwd: part table (%d entries), Vs=%d and img_wh=%d need more than 227 KB of shared memory", parts->E, Vs, img_wh);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  CHECK_LAUNCH(e);
   return SMPL_B200_OK;
 }
 

@@ -117,10 +117,11 @@ cudaError_t launch_project_fwd(const float* verts, const float* params, int N, i
 cudaError_t launch_project_bwd(const float* verts, const float* params, const float* g_projects, int N, int V, int vs,
                                float* g_verts, float* g_params, cudaStream_t st);
 cudaError_t launch_mask_fwd(const float* projects, int N, int Vs, float* mask, cudaStream_t st);
+size_t seg_saved_bytes(int N, int wh);
 cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
-                           float* seg, cudaStream_t st);
-cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg, int N,
-                           int Vs, int wh, float* g_projects, cudaStream_t st);
+                           float* seg, unsigned char* saved, cudaStream_t st);
+cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
+                           const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st);
 cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, cudaStream_t st);
 cudaError_t launch_sil_bwd(const float* projects, const float* g_sil, int N, int Vs, int wh, float* g_projects,
                            cudaStream_t st);

@@ -1,22 +1,34 @@
 // K5: 31-part soft segmentation from projected vertices and the visibility weights, forward and backward.
 //
 // Reference arithmetic (keras_smpl/projects_to_seg.py:9-69), per part k and pixel g = (column c, row r):
-//   s_k[g] = max_i exp(-(||p_i - g||_2 * w_i))        :52-56   (tf.norm = sqrt(du*du + dv*dv), no FMA)
+//   s_k[g] = max_i exp(-(||p_i - g||_2 * w_i))        :52-56
 //   bg[g]  = 1 - clip(sum_k s_k[g], 0, 1)             :61-64
 //   out[n, wh-1-r, c, :] = [bg, s_0 .. s_30]          :66-68   (rows flipped)
 //
-// exp, sqrt and the multiply by w are monotone, so  max_i exp(-(d_i w_i)) = exp(-min_i (d_i w_i))  bit for bit: both
-// directions are an exact weighted-nearest-vertex query.  Vertices are split by weight once per sample:
-//   light    w == 1        one per occupied z-buffer cell after compute_mask; min over SQUARED distances in the hot
-//                           loop, a single sqrt at the end (sqrt is monotone and correctly rounded)
+// exp, sqrt and the multiply by w are monotone, so  max_i exp(-(d_i w_i)) = exp(-min_i (d_i w_i)): both directions are
+// an exact weighted-nearest-vertex query (arg-min over squared distances computed as fl(fl(du^2)+fl(dv^2)), the same
+// roundings as tf.norm).  Vertices are split by weight once per sample:
+//   light    w == 1        one per occupied z-buffer cell after compute_mask; min over SQUARED distances in the hot loop
 //   heavy    w >= 256      d*w > 128 unless d < 0.5, and exp(-128) is exactly 0 in fp32, so a heavy vertex can only
 //                           reach the one pixel it rounds to: chained per pixel, visited by that pixel alone
 //   generic  anything else evaluated against every pixel (never produced by compute_mask; kept for drop-in inputs)
-// The backward keeps (argmin slot, distance*weight) per (pixel, part) in a shared tile, then transposes the work:
-// lane k owns part k and walks the 32 pixels of the group, merging runs of equal arg-min vertices in registers, so
-// a run costs one shared-memory atomicAdd pair instead of one per pixel (run-length warp aggregation).
-// Gradient conventions (TF autodiff): first arg-min takes the whole gradient on exact ties (TF splits
-// evenly; ties have measure zero); d == 0 yields 0 where TF yields NaN; the clip gate is inclusive (0 <= sum <= 1).
+//
+// Forward: a warp owns a tile of (LX*BW) x (LY*BH) pixels, a lane a BW x BH block of it, so the per-axis squared
+// offsets du^2 (BW values) and dv^2 (BH values) are shared by the block's pixels.  Eight channels of each pixel are
+// kept in registers and leave as ONE 32-byte store (st.global.v8.f32 = a full DRAM sector; partial-sector stores cost
+// a read-fill).  The score epilogue is d = d2*rsqrt(d2), s = ex2(-d*log2 e): <= 3e-7 absolute from exp(-sqrt(d2)),
+// an order of magnitude inside the 1e-5 geometry tolerance that bounds the inputs.
+// When a backward will follow, the forward also records per pixel the clip gate and the arg-min of every part as one
+// byte (`saved`, 32 B per pixel, laid out in the forward's own (tile, block, lane) order), so the backward never
+// searches.
+//
+// Backward: lane = channel.  Records are read back in the forward's order (no index arithmetic beyond shifts), the
+// upstream gradient row of the pixel is one coalesced 128-byte load, s is recomputed at the recorded arg-min, and the
+// per-vertex sums accumulate in per-warp PRIVATE shared-memory slots indexed by the part's light slot: lane k is the
+// only writer of part k's slots, so plain load/add/store replaces atomics (shared fp32 atomicAdd is a CAS loop on
+// sm_100).  Runs of equal arg-min vertices along a row are merged in registers first.
+// Gradient conventions (TF autodiff): the first arg-min takes the whole gradient on exact ties (TF splits
+// evenly; measure zero); d == 0 yields 0 where TF yields NaN; the clip gate is inclusive (0 <= sum <= 1).
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -26,14 +38,20 @@ namespace {
 
 constexpr float kHeavyMin = 256.0f;
 constexpr float kDropX = 110.0f;      // exp(-x) == 0 in fp32 (denormals included) for x > 103.98
-constexpr int kNone16 = 0xffff;
+constexpr unsigned kNone16 = 0xffffu;
+constexpr int kArgNone = 0xff;        // saved byte: the part has no vertex that reaches this pixel (zero gradient)
+constexpr int kArgSlow = 0xfe;        // saved byte: winner is a heavy/generic vertex or index >= 254: re-query
+constexpr float kLog2e = 1.4426950408889634f;
 
 struct SegSmem {
   float4* ent;     // [E]  light: {u, v, 1, vid}   heavy/generic: {u, v, w, entry | next << 16}
   int* head;       // [wh*wh] first heavy slot of each pixel, -1 none
   int* lcount;     // [32] light entries per part (packed at the front of the part's CSR segment)
+  int* lbase;      // [32] exclusive prefix sum of lcount
+  int* pptr;       // [36] the part table's CSR pointers (P+1 used)
   int* ghead;      // [1]  chain of generic slots, -1 none
-  float* tiles;    // per-warp staging
+  int* nheavy;     // [1]  number of chained heavy entries
+  unsigned char* rest;
 };
 
 __device__ __forceinline__ float dist2(float u, float v, float gx, float gy) {
@@ -41,12 +59,37 @@ __device__ __forceinline__ float dist2(float u, float v, float gx, float gy) {
   return __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
 }
 
+// exp(-sqrt(d2)) for the light class, fast path (see header).  d2 = +inf (empty part) -> 0.
+__device__ __forceinline__ float score_from_d2(float d2) {
+  const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));            // d2 == 0 -> 0 ; inf*0 is NaN, handled below
+  return (d2 < CUDART_INF_F) ? exp2f(-d * kLog2e) : 0.f;     // exp2f lowers to ex2.approx with a range fix-up
+}
+
+__device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
+  SegSmem sm;
+  size_t off = 0;
+  sm.ent = reinterpret_cast<float4*>(raw + off); off += (size_t)((E + 1) & ~1) * 16;
+  sm.head = reinterpret_cast<int*>(raw + off); off += ((size_t)wh * wh * 4 + 15) & ~(size_t)15;
+  sm.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
+  sm.lbase = reinterpret_cast<int*>(raw + off); off += 32 * 4;
+  sm.pptr = reinterpret_cast<int*>(raw + off); off += 36 * 4;
+  sm.ghead = reinterpret_cast<int*>(raw + off);
+  sm.nheavy = sm.ghead + 1; off += 16;
+  sm.rest = raw + off;
+  return sm;
+}
+size_t seg_base_smem(int E, int wh) {
+  return (size_t)((E + 1) & ~1) * 16 + (((size_t)wh * wh * 4 + 15) & ~(size_t)15) + 2 * 32 * 4 + 36 * 4 + 16;
+}
+
 // Split the sample's part vertices into weight classes (one warp per part, ballot compaction).
 __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, const float* __restrict__ mask,
                          const int* __restrict__ ptr, const int* __restrict__ idx, int P, int wh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < wh * wh; i += blockDim.x) sm.head[i] = -1;
-  if (threadIdx.x == 0) *sm.ghead = -1;
+  if (threadIdx.x == 0) { *sm.ghead = -1; *sm.nheavy = 0; }
+  if (threadIdx.x < 32) sm.lcount[threadIdx.x] = 0;
+  if (threadIdx.x < 36) sm.pptr[threadIdx.x] = ptr[min((int)threadIdx.x, P)];
   __syncthreads();
   for (int k = warp; k < P; k += nwarps) {
     const int p0 = ptr[k], p1 = ptr[k + 1];
@@ -67,19 +110,19 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
       if (light) sm.ent[p0 + nl + __popc(bl & lt)] = make_float4(u, v, 1.0f, __int_as_float(vid));
       if (other) {
         const int slot = p1 - 1 - (no + __popc(bo & lt));
-        int next = kNone16;
-        bool keep = true;
+        unsigned next = kNone16;
         if (w >= kHeavyMin) {
           const float pu = rintf(u), pv = rintf(v);
-          keep = pu >= 0.f && pu <= (float)(wh - 1) && pv >= 0.f && pv <= (float)(wh - 1);
+          bool keep = pu >= 0.f && pu <= (float)(wh - 1) && pv >= 0.f && pv <= (float)(wh - 1);
           if (keep) keep = __fmul_rn(sqrtf(dist2(u, v, pu, pv)), w) <= kDropX;
-          if (keep) next = atomicExch(&sm.head[(int)pv * wh + (int)pu], slot) & 0xffff;
+          if (keep) {                                   // dropped heavy entries keep their slot but are never linked
+            next = (unsigned)atomicExch(&sm.head[(int)pv * wh + (int)pu], slot) & 0xffffu;
+            atomicAdd(sm.nheavy, 1);
+          }
         } else {
-          next = atomicExch(sm.ghead, slot) & 0xffff;
+          next = (unsigned)atomicExch(sm.ghead, slot) & 0xffffu;
         }
-        // dropped heavy entries keep their slot but are never linked
-        sm.ent[slot] = make_float4(u, v, w, __int_as_float((e & 0xffff) | (next << 16)));
-        (void)keep;
+        sm.ent[slot] = make_float4(u, v, w, __uint_as_float(((unsigned)e & 0xffffu) | (next << 16)));
       }
       nl += __popc(bl);
       no += __popc(bo);
@@ -87,223 +130,448 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
     if (lane == 0) sm.lcount[k] = nl;
   }
   __syncthreads();
+  if (threadIdx.x < 32) {                               // exclusive scan of the light counts
+    const int c = sm.lcount[threadIdx.x];
+    int s = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if ((int)threadIdx.x >= o) s += t;
+    }
+    sm.lbase[threadIdx.x] = s - c;
+  }
+  __syncthreads();
 }
 
-// x = min_i d_i*w_i over the chained (heavy or generic) entries of part k; returns the best slot through `arg`.
-__device__ __forceinline__ void walk_chain(const SegSmem& sm, int first, int k, const int* __restrict__ ptr, float gx,
-                                           float gy, float& x, int& arg) {
+// x = min_i d_i*w_i over the chained (heavy or generic) entries of part [p0,p1); returns the best slot through `arg`.
+__device__ __forceinline__ void walk_chain(const SegSmem& sm, int first, int p0, int p1, float gx, float gy, float& x,
+                                           int& arg) {
   int slot = first;
   while (slot >= 0) {
     const float4 e = sm.ent[slot];
-    const int meta = __float_as_int(e.w);
-    if (slot >= ptr[k] && slot < ptr[k + 1]) {           // slots never leave their part's CSR segment
+    if (slot >= p0 && slot < p1) {                       // slots never leave their part's CSR segment
       const float xe = __fmul_rn(sqrtf(dist2(e.x, e.y, gx, gy)), e.z);
       if (xe < x) { x = xe; arg = slot; }
     }
-    const int nx = (meta >> 16) & 0xffff;
-    slot = (nx == kNone16) ? -1 : nx;
+    const unsigned nx = (__float_as_uint(e.w) >> 16) & 0xffffu;
+    slot = (nx == kNone16) ? -1 : (int)nx;
   }
 }
 
-// Weighted nearest vertex of part k for this lane's pixel.  TRACK also returns the winning slot.
-template <bool TRACK>
-__device__ __forceinline__ float part_query(const SegSmem& sm, const int* __restrict__ ptr, int k, float gx, float gy,
-                                            int myhead, int ghead, int& arg) {
-  const int p0 = ptr[k], nl = sm.lcount[k];
+// Out-of-line slow path of the forward: does a heavy/generic vertex beat the light minimum d2 at this pixel?
+// Returns the winning score (exact expf) or a negative value if the light minimum stands.
+__device__ __noinline__ float slow_pixel_score(const SegSmem& sm, int p0, int p1, float gx, float gy, int head, int ghead,
+                                               float d2_light) {
+  float x = sqrtf(d2_light);
+  int a = -1;
+  if (head >= 0) walk_chain(sm, head, p0, p1, gx, gy, x, a);
+  if (ghead >= 0) walk_chain(sm, ghead, p0, p1, gx, gy, x, a);
+  return (a >= 0) ? expf(-x) : -1.0f;
+}
+
+// Out-of-line slow path of the backward: full weighted nearest-vertex query of part [p0,p1) for one pixel.
+__device__ __noinline__ int slow_pixel_query(const SegSmem& sm, int p0, int p1, int nl, float gx, float gy, int head,
+                                             int ghead) {
   float best = CUDART_INF_F;
   int barg = -1;
-#pragma unroll 4
   for (int i = 0; i < nl; ++i) {
-    const float4 e = sm.ent[p0 + i];                      // same address on every lane: broadcast
+    const float4 e = sm.ent[p0 + i];
     const float d2 = dist2(e.x, e.y, gx, gy);
-    if (TRACK) {
-      if (d2 < best) { best = d2; barg = p0 + i; }
-    } else {
-      best = fminf(best, d2);
-    }
+    if (d2 < best) { best = d2; barg = p0 + i; }
   }
-  float x = sqrtf(best);                                  // w == 1: d*w == d
-  if (myhead >= 0) walk_chain(sm, myhead, k, ptr, gx, gy, x, barg);
-  if (ghead >= 0) walk_chain(sm, ghead, k, ptr, gx, gy, x, barg);
-  arg = barg;
-  return x;
+  float x = sqrtf(best);
+  if (head >= 0) walk_chain(sm, head, p0, p1, gx, gy, x, barg);
+  if (ghead >= 0) walk_chain(sm, ghead, p0, p1, gx, gy, x, barg);
+  return barg;
 }
 
-__device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh, int Vs_acc) {
-  SegSmem sm;
-  size_t off = 0;
-  sm.ent = reinterpret_cast<float4*>(raw + off); off += (size_t)((E + 1) & ~1) * 16;
-  sm.head = reinterpret_cast<int*>(raw + off); off += (size_t)wh * wh * 4;
-  sm.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
-  sm.ghead = reinterpret_cast<int*>(raw + off); off += 16;
-  off += (size_t)Vs_acc * 8;                              // backward accumulator sits here (see seg_bwd_kernel)
-  sm.tiles = reinterpret_cast<float*>(raw + off);
-  return sm;
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+// Tile geometry shared by forward and backward (the `saved` layout depends on it).
+struct SegGeom {
+  int BW, BH, LX, LY, TW, TH, NB, tiles_x, tiles_y, ntiles;
+};
+SegGeom seg_geom(int wh) {
+  SegGeom g;
+  if (wh % 48 == 0) { g.BW = 3; g.BH = 2; g.LX = 16; }        // 48 x 4 pixel tiles
+  else { g.BW = 4; g.BH = 2; g.LX = 16; }                     // 64 x 4 pixel tiles
+  g.LY = 32 / g.LX; g.TW = g.LX * g.BW; g.TH = g.LY * g.BH; g.NB = g.BW * g.BH;
+  g.tiles_x = (wh + g.TW - 1) / g.TW; g.tiles_y = (wh + g.TH - 1) / g.TH; g.ntiles = g.tiles_x * g.tiles_y;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float kBigD2 = 1e30f;      // "no vertex yet": rsqrt/ex2 map it to a score of exactly 0 without a branch
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// saved layout: 4 planes (channels 8q..8q+7); plane q holds, for record id = (tile*NB + b)*32 + lane, 8 bytes.
+// byte of channel 0: bit 0 = clip gate.  byte of channel 1+k: 0 none, 1..254 light index + 1, 255 re-query.
+template <int BW, int BH, int LX, bool TRACK>
+__global__ void __launch_bounds__(256, 3)
 seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, int N, int Vs,
                const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh,
-               float* __restrict__ seg) {
+               float* __restrict__ seg, unsigned char* __restrict__ saved) {
+  constexpr int LY = 32 / LX, TW = LX * BW, TH = LY * BH, NB = BW * BH;
   extern __shared__ __align__(16) unsigned char raw[];
-  const SegSmem sm = carve(raw, E, wh, 0);
+  const SegSmem sm = carve(raw, E, wh);
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
   const int ghead = *sm.ghead;
+  const bool any_heavy = *sm.nheavy > 0;
   const int C = P + 1;
-  float* tile = sm.tiles + warp * (32 * 33);
-  const int npix = wh * wh, ngroups = (npix + 31) / 32;
-  // this block's share of the pixel groups (gridDim.y splits a sample when the batch alone cannot fill the GPU)
-  const int g0 = (int)(((long long)ngroups * blockIdx.y) / gridDim.y);
-  const int g1 = (int)(((long long)ngroups * (blockIdx.y + 1)) / gridDim.y);
-  for (int grp = g0 + warp; grp < g1; grp += nwarps) {
-    const int pix = grp * 32 + lane;
-    const bool active = pix < npix;
-    const int r = pix / wh, c = pix - r * wh;
-    const float gx = (float)c, gy = (float)r;             // grid = (column, row) (:26-31)
-    const int myhead = active ? sm.head[pix] : -1;
-    float S = 0.f;
-    for (int k = 0; k < P; ++k) {
-      int arg;
-      const float x = part_query<false>(sm, ptr, k, gx, gy, myhead, ghead, arg);
-      const float s = expf(-x);
-      tile[lane * 33 + 1 + k] = s;
-      S += s;
-    }
-    tile[lane * 33] = 1.0f - fminf(fmaxf(S, 0.f), 1.f);
-    __syncwarp();
-    const int cnt = min(32, npix - grp * 32);
-    for (int j = 0; j < cnt; ++j) {
-      const int pj = grp * 32 + j;
-      const int rj = pj / wh, cj = pj - rj * wh;
-      if (lane < C) seg[(((size_t)n * wh + (wh - 1 - rj)) * wh + cj) * C + lane] = tile[j * 33 + lane];
-    }
-    __syncwarp();
-  }
-}
+  const int tiles_x = (wh + TW - 1) / TW, tiles_y = (wh + TH - 1) / TH, ntiles = tiles_x * tiles_y;
+  const int t0 = (int)(((long long)ntiles * blockIdx.y) / gridDim.y);
+  const int t1 = (int)(((long long)ntiles * (blockIdx.y + 1)) / gridDim.y);
+  const int lx = lane % LX, ly = lane / LX;
+  const size_t plane = (size_t)ntiles * NB * 32 * 8;               // bytes of one saved plane of one sample
+  unsigned char* sv = TRACK ? saved + (size_t)n * plane * 4 : nullptr;
+  float* seg_n = seg ? seg + (size_t)n * wh * wh * C : nullptr;
+  // per-lane staging of one chunk: stage[(sub*NB + q)*32 + lane]  (lane-contiguous: conflict-free, no sync needed)
+  float* stage = reinterpret_cast<float*>(sm.rest) + (size_t)warp * (8 * NB * 32) + lane;
 
-__global__ void __launch_bounds__(256)
-seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
-               int N, int Vs, const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh,
-               float* __restrict__ g_projects) {
-  extern __shared__ __align__(16) unsigned char raw[];
-  const SegSmem sm = carve(raw, E, wh, Vs);
-  float* gacc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sm.ghead) + 16);   // [Vs][2]
-  const int n = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < Vs * 2; i += blockDim.x) gacc[i] = 0.f;
-  classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
-  const int ghead = *sm.ghead;
-  const int C = P + 1;
-  float* tileX = sm.tiles + warp * (2 * 32 * 33 + 32);
-  int* tileI = reinterpret_cast<int*>(tileX + 32 * 33);
-  float* gate = tileX + 2 * 32 * 33;
-  const int npix = wh * wh, ngroups = (npix + 31) / 32;
-  for (int grp = warp; grp < ngroups; grp += nwarps) {
-    // ---- phase 1: lane = pixel; weighted nearest vertex of every part, and the clip gate ----------------------
-    {
-      const int pix = grp * 32 + lane;
-      const bool active = pix < npix;
-      const int r = pix / wh, c = pix - r * wh;
-      const float gx = (float)c, gy = (float)r;
-      const int myhead = active ? sm.head[pix] : -1;
-      float S = 0.f;
-      for (int k = 0; k < P; ++k) {
-        int arg;
-        const float x = part_query<true>(sm, ptr, k, gx, gy, myhead, ghead, arg);
-        tileX[lane * 33 + k] = x;
-        tileI[lane * 33 + k] = arg;
-        S += expf(-x);
-      }
-      gate[lane] = (S >= 0.f && S <= 1.f) ? 1.f : 0.f;    // clip_by_value passes gradient on the closed interval
+  for (int t = t0 + warp; t < t1; t += nwarps) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int c0 = tx * TW + lx * BW, r0 = ty * TH + ly * BH;      // this lane's block origin (grid = (column,row), :26-31)
+    float gxs[BW], gys[BH];
+#pragma unroll
+    for (int i = 0; i < BW; ++i) gxs[i] = (float)(c0 + i);
+#pragma unroll
+    for (int j = 0; j < BH; ++j) gys[j] = (float)(r0 + j);
+    bool blk_slow = ghead >= 0;                                    // any heavy vertex chained to one of my pixels?
+    if (any_heavy) {
+#pragma unroll
+      for (int j = 0; j < BH; ++j)
+#pragma unroll
+        for (int i = 0; i < BW; ++i)
+          if (c0 + i < wh && r0 + j < wh) blk_slow |= sm.head[(r0 + j) * wh + c0 + i] >= 0;
     }
-    __syncwarp();
-    // ---- phase 2: lane = part; walk the group's pixels, merge runs of equal arg-min vertices -------------------
-    {
-      const int cnt = min(32, npix - grp * 32);
-      int run_vid = -1;
-      float run_u = 0.f, run_v = 0.f;
-      for (int j = 0; j < cnt; ++j) {
-        const int pj = grp * 32 + j;
-        const int rj = pj / wh, cj = pj - rj * wh;
-        const float gch = (lane < C) ? g_seg[(((size_t)n * wh + (wh - 1 - rj)) * wh + cj) * C + lane] : 0.f;
-        const float g0 = __shfl_sync(0xffffffffu, gch, 0);
-        const float gk = __shfl_down_sync(0xffffffffu, gch, 1);     // lane k <- channel k+1
-        if (lane < P) {
-          const int arg = tileI[j * 33 + lane];
-          const float x = tileX[j * 33 + lane];
-          int vid = -1;
-          float cu = 0.f, cv = 0.f;
-          if (arg >= 0) {
-            const float4 e = sm.ent[arg];
-            const float s = expf(-x);
-            const float G = gk - gate[j] * g0;
-            const float du = __fsub_rn(e.x, (float)cj), dv = __fsub_rn(e.y, (float)rj);
-            const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
-            const float coef = (d > 0.f) ? (-e.z * s * G) / d : 0.f;  // d(exp(-d w))/dp = -w s (p - g)/d
-            cu = coef * du; cv = coef * dv;
-            const int meta = __float_as_int(e.w);
-            vid = (e.z == 1.0f) ? meta : idx[meta & 0xffff];
+    float S[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) S[q] = 0.f;
+
+    // channel chunks 1, 2, 3, then chunk 0 last: its channel 0 (background) needs the sum over all parts
+    for (int cc = 1; cc <= 4; ++cc) {
+      const int chunk = cc & 3;
+      if (chunk * 8 >= C) continue;
+      unsigned clo[NB], chi[NB];                                   // packed saved bytes, channels 0-3 / 4-7 of the chunk
+#pragma unroll
+      for (int q = 0; q < NB; ++q) { clo[q] = 0u; chi[q] = 0u; }
+#pragma unroll 1
+      for (int sub = 0; sub < 8; ++sub) {
+        const int ch = chunk * 8 + sub;
+        float sc[NB];
+        int code[NB];
+        if (ch == 0 || ch >= C) {                                  // background is filled in after the loop
+#pragma unroll
+          for (int q = 0; q < NB; ++q) stage[(sub * NB + q) * 32] = 0.f;
+          continue;
+        }
+        const int p0 = sm.pptr[ch - 1], p1 = sm.pptr[ch], nl = sm.lcount[ch - 1];
+        float best[NB];
+        int barg[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) { best[q] = kBigD2; barg[q] = -1; }
+#pragma unroll 2
+        for (int v = 0; v < nl; ++v) {
+          const float4 e = sm.ent[p0 + v];                         // same address on every lane: broadcast
+          float du2[BW], dv2[BH], d2[NB];
+#pragma unroll
+          for (int i = 0; i < BW; ++i) { const float d = __fsub_rn(e.x, gxs[i]); du2[i] = __fmul_rn(d, d); }
+#pragma unroll
+          for (int j = 0; j < BH; ++j) { const float d = __fsub_rn(e.y, gys[j]); dv2[j] = __fmul_rn(d, d); }
+#pragma unroll
+          for (int j = 0; j < BH; ++j)
+#pragma unroll
+            for (int i = 0; i < BW; ++i) d2[j * BW + i] = __fadd_rn(du2[i], dv2[j]);
+#pragma unroll
+          for (int q = 0; q < NB; ++q) {
+            if (TRACK) barg[q] = (d2[q] < best[q]) ? v : barg[q];
+            best[q] = fminf(best[q], d2[q]);
           }
-          if (vid != run_vid) {
-            if (run_vid >= 0) { atomicAdd(&gacc[run_vid * 2], run_u); atomicAdd(&gacc[run_vid * 2 + 1], run_v); }
-            run_vid = vid; run_u = cu; run_v = cv;
-          } else {
-            run_u += cu; run_v += cv;
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const float rs = rsqrt_approx(fmaxf(best[q], 1e-30f));
+          sc[q] = ex2_approx((best[q] * rs) * (-kLog2e));          // exp(-sqrt(d2)); kBigD2 -> 0, d2 == 0 -> 1
+          code[q] = min(barg[q] + 1, 255);                         // 0 none, 1..254 index+1, 255 re-query
+        }
+        if (blk_slow) {                                            // rare: heavy / generic vertices
+#pragma unroll
+          for (int q = 0; q < NB; ++q) {
+            const int i = q % BW, j = q / BW;
+            if (c0 + i < wh && r0 + j < wh) {
+              const int hd = any_heavy ? sm.head[(r0 + j) * wh + c0 + i] : -1;
+              if (hd >= 0 || ghead >= 0) {
+                const float ss = slow_pixel_score(sm, p0, p1, gxs[i], gys[j], hd, ghead, best[q]);
+                if (ss >= 0.f) { sc[q] = ss; code[q] = 255; }
+              }
+            }
+          }
+        }
+        const unsigned sh = 8u * (sub & 3);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          stage[(sub * NB + q) * 32] = sc[q];
+          S[q] += sc[q];
+          if (TRACK) {
+            if (sub < 4) clo[q] |= (unsigned)code[q] << sh;
+            else chi[q] |= (unsigned)code[q] << sh;
           }
         }
       }
-      if (run_vid >= 0) { atomicAdd(&gacc[run_vid * 2], run_u); atomicAdd(&gacc[run_vid * 2 + 1], run_v); }
+      if (chunk == 0) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          stage[q * 32] = 1.0f - fminf(fmaxf(S[q], 0.f), 1.f);     // :61-64
+          if (TRACK) clo[q] |= (S[q] >= 0.f && S[q] <= 1.f) ? 1u : 0u;   // clip gate (inclusive), for the backward
+        }
+      }
+      // one 32-byte sector per pixel; rows flipped (:68)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int r = r0 + q / BW, c = c0 + q % BW;
+        if (seg_n && r < wh && c < wh) {
+          float* o = seg_n + ((wh - 1 - r) * wh + c) * C + chunk * 8;
+          float v8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v8[e] = stage[(e * NB + q) * 32];
+          if (C == 32) {
+            st_global_v8(o, v8);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (chunk * 8 + e < C) o[e] = v8[e];
+          }
+        }
+        if (TRACK) {
+          uint2* so = reinterpret_cast<uint2*>(sv + (size_t)chunk * plane) + ((t * NB + q) * 32 + lane);
+          *so = make_uint2(clo[q], chi[q]);
+        }
+      }
     }
-    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBatch = 8;          // records whose loads are in flight together (consecutive lanes of one block row)
+constexpr int kAccSlots = 512;     // private accumulator slots per warp (light entries beyond this use atomics)
+
+// rare: winner is a heavy/generic vertex (or a light index that did not fit a byte): exact re-query, atomics
+__device__ __noinline__ void slow_pixel_grad(const SegSmem& sm, const int* __restrict__ idx, float* gacc, int p0, int p1,
+                                             int nl, float gx, float gy, int head, int ghead, float G) {
+  const int slot = slow_pixel_query(sm, p0, p1, nl, gx, gy, head, ghead);
+  if (slot < 0) return;
+  const float4 e = sm.ent[slot];
+  const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+  const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+  const float s = expf(-__fmul_rn(d, e.z));
+  const float coef = (d > 0.f) ? (-e.z * s * G) / d : 0.f;         // d(exp(-d w))/dp = -w s (p - g)/d
+  const int vid = (e.z == 1.0f) ? __float_as_int(e.w) : idx[__float_as_uint(e.w) & 0xffffu];
+  atomicAdd(&gacc[vid * 2], coef * du);
+  atomicAdd(&gacc[vid * 2 + 1], coef * dv);
+}
+
+template <int BW, int BH, int LX>
+__global__ void __launch_bounds__(256, 3)
+seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
+               const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
+               const int* __restrict__ idx, int P, int E, int wh, int tiles_x, int ntiles,
+               float* __restrict__ g_projects) {
+  constexpr int LY = 32 / LX, TW = LX * BW, TH = LY * BH, NB = BW * BH;
+  static_assert(LX % kBatch == 0, "a batch must stay inside one lane row");
+  extern __shared__ __align__(16) unsigned char raw[];
+  const SegSmem sm = carve(raw, E, wh);
+  float* gacc = reinterpret_cast<float*>(sm.rest);                  // [Vs][2]
+  float2* wacc_all = reinterpret_cast<float2*>(gacc + (size_t)((Vs * 2 + 3) & ~3));   // [nwarps][kAccSlots]
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < Vs * 2; i += blockDim.x) gacc[i] = 0.f;
+  for (int i = threadIdx.x; i < nwarps * kAccSlots; i += blockDim.x) wacc_all[i] = make_float2(0.f, 0.f);
+  classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
+  const int ghead = *sm.ghead;
+  const int C = P + 1;
+  const bool live = lane >= 1 && lane < C;                          // lane = channel; channel 0 carries the gate
+  const int k = live ? lane - 1 : 0;
+  const int p0 = sm.pptr[k], p1 = sm.pptr[k + 1], nl = sm.lcount[k];
+  float2* wacc = wacc_all + (size_t)warp * kAccSlots + sm.lbase[k]; // this lane's part, private to (warp, lane)
+  const int acc_cap = kAccSlots - sm.lbase[k];                      // light indices >= acc_cap overflow to atomics
+  const size_t plane = (size_t)ntiles * NB * 32 * 8;
+  const unsigned char* sv = saved + (size_t)n * plane * 4 + (size_t)(lane >> 3) * plane + (lane & 7);
+  const float* g_n = g_seg + (size_t)n * wh * wh * C + (lane < C ? lane : 0);
+  const int nrec = ntiles * NB * 32;
+
+  int run_li = -1;                                                  // current run: light index within this lane's part
+  float run_u = 0.f, run_v = 0.f;
+  // records in the forward's order: id = (tile*NB + b)*32 + l32 ; a batch = kBatch consecutive lanes of one block row
+  for (int base = warp * kBatch; base < nrec; base += nwarps * kBatch) {
+    const int l0 = base & 31, tb = base >> 5;
+    const int b = tb % NB, t = tb / NB;                             // compile-time divisors
+    const int ty = (tiles_x == 1) ? t : t / tiles_x, tx = t - ty * tiles_x;
+    const int r = ty * TH + (l0 / LX) * BH + b / BW;
+    const int cb = tx * TW + (l0 % LX) * BW + b % BW;               // column of the batch's first record; +BW per record
+    const bool row_in = r < wh;
+    const float* grow = g_n + ((wh - 1 - r) * wh + cb) * C;         // rows flipped (:68)
+    const unsigned char* srow = sv + (size_t)base * 8;
+    int code[kBatch];
+    float g[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {                              // issue the whole batch of loads first
+      const bool in = row_in && (cb + j * BW) < wh;
+      code[j] = in ? (int)srow[j * 8] : 0;
+      g[j] = (in && lane < C) ? grow[j * BW * C] : 0.f;
+    }
+    const float gy = (float)r;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int gate = __shfl_sync(0xffffffffu, code[j], 0);
+      const float g0 = __shfl_sync(0xffffffffu, g[j], 0);
+      const float G = g[j] - ((gate & 1) ? g0 : 0.f);               // d bg / d s_k = -gate
+      const float gx = (float)(cb + j * BW);
+      int li = -1;
+      float cu = 0.f, cv = 0.f;
+      if (live && code[j] != 0) {
+        if (code[j] == 255) {
+          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gx, gy, sm.head[r * wh + cb + j * BW], ghead, G);
+        } else {
+          li = code[j] - 1;
+          const float4 e = sm.ent[p0 + li];                         // light entry: w == 1
+          const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+          const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+          const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
+          const float s = ex2_approx((d2 * rs) * (-kLog2e));
+          const float coef = -(s * G) * rs;                         // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
+          cu = coef * du; cv = coef * dv;
+        }
+      }
+      if (li != run_li) {
+        if (run_li >= 0) {
+          if (run_li < acc_cap) {                                   // private slot: this lane is its only writer
+            float2 a = wacc[run_li];
+            a.x += run_u; a.y += run_v;
+            wacc[run_li] = a;
+          } else {
+            const int vid = __float_as_int(sm.ent[p0 + run_li].w);
+            atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
+          }
+        }
+        run_li = li; run_u = cu; run_v = cv;
+      } else {
+        run_u += cu; run_v += cv;
+      }
+    }
+  }
+  if (run_li >= 0) {
+    if (run_li < acc_cap) {
+      float2 a = wacc[run_li];
+      a.x += run_u; a.y += run_v;
+      wacc[run_li] = a;
+    } else {
+      const int vid = __float_as_int(sm.ent[p0 + run_li].w);
+      atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
+    }
+  }
+  __syncthreads();
+  // fold the warps' private slots into the per-vertex sums (a vertex may sit in more than one part)
+  const int nlight = min(sm.lbase[31] + sm.lcount[31], kAccSlots);
+  for (int li = threadIdx.x; li < nlight; li += blockDim.x) {
+    float su = 0.f, sv2 = 0.f;
+    for (int w = 0; w < nwarps; ++w) { const float2 a = wacc_all[(size_t)w * kAccSlots + li]; su += a.x; sv2 += a.y; }
+    int kk = 0;                                                     // part kk with lbase[kk] <= li < lbase[kk] + lcount[kk]
+    while (kk < 31 && li >= sm.lbase[kk + 1]) ++kk;
+    const int vid = __float_as_int(sm.ent[sm.pptr[kk] + (li - sm.lbase[kk])].w);
+    atomicAdd(&gacc[vid * 2], su); atomicAdd(&gacc[vid * 2 + 1], sv2);
   }
   __syncthreads();
   float* out = g_projects + (size_t)n * Vs * 3;
   for (int i = threadIdx.x; i < Vs * 3; i += blockDim.x) {
     const int v = i / 3, c = i - v * 3;
-    out[i] = (c < 2) ? gacc[v * 2 + c] : 0.f;             // z receives no gradient from the rasteriser
+    out[i] = (c < 2) ? gacc[v * 2 + c] : 0.f;                       // z receives no gradient from the rasteriser
   }
-}
-
-size_t seg_smem_bytes(int E, int wh, int Vs_acc, int warps, bool bwd) {
-  size_t b = (size_t)((E + 1) & ~1) * 16 + (size_t)wh * wh * 4 + 32 * 4 + 16 + (size_t)Vs_acc * 8;
-  b += (size_t)warps * (bwd ? (2 * 32 * 33 + 32) : (32 * 33)) * 4;
-  return b;
 }
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-}  // namespace
-
-cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
-                           float* seg, cudaStream_t st) {
-  int warps = 8;
-  while (warps > 1 && seg_smem_bytes(p->E, wh, 0, warps, false) > kMaxSmem) warps >>= 1;
-  const size_t smem = seg_smem_bytes(p->E, wh, 0, warps, false);
-  if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  // split a sample's pixel groups over gridDim.y when the batch alone leaves SMs idle
-  const int ngroups = (wh * wh + 31) / 32;
+template <int BW, int BH, int LX>
+cudaError_t launch_fwd_cfg(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
+                           float* seg, unsigned char* saved, cudaStream_t st) {
+  const SegGeom g = seg_geom(wh);
+  int warps = 1;
+  for (int w = 8; w >= 1; --w)                 // the largest warp count <= 8 that divides the tile count evenly
+    if (g.ntiles % w == 0) { warps = w; break; }
+  // split a sample's tiles over gridDim.y when the batch alone leaves SMs idle
   int split = 1;
-  if (N < 2 * 148) split = max(1, min(ngroups / warps, (2 * 148 + N - 1) / N));
+  if (N < 2 * 148) {
+    split = max(1, min(g.ntiles, (2 * 148 + N - 1) / N));
+    warps = max(1, min(warps, (g.ntiles + split - 1) / split));
+  }
+  const size_t smem = seg_base_smem(p->E, wh) + (size_t)warps * 8 * g.NB * 32 * 4;
+  if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   dim3 grid(N, split);
   LaunchScope scope(KID_SEG_FWD, st);
-  seg_fwd_kernel<<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg);
+  cudaError_t e;
+  if (saved) {
+    e = cudaFuncSetAttribute(seg_fwd_kernel<BW, BH, LX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    seg_fwd_kernel<BW, BH, LX, true><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh,
+                                                                    seg, saved);
+  } else {
+    e = cudaFuncSetAttribute(seg_fwd_kernel<BW, BH, LX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    seg_fwd_kernel<BW, BH, LX, false><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh,
+                                                                     seg, nullptr);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg, int N,
-                           int Vs, int wh, float* g_projects, cudaStream_t st) {
-  int warps = 8;
-  while (warps > 1 && seg_smem_bytes(p->E, wh, Vs, warps, true) > kMaxSmem) warps >>= 1;
-  const size_t smem = seg_smem_bytes(p->E, wh, Vs, warps, true);
+}  // namespace
+
+size_t seg_saved_bytes(int N, int wh) {
+  const SegGeom g = seg_geom(wh);
+  return (size_t)N * g.ntiles * g.NB * 32 * 8 * 4;
+}
+
+cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
+                           float* seg, unsigned char* saved, cudaStream_t st) {
+  if (wh % 48 == 0) return launch_fwd_cfg<3, 2, 16>(p, projects, mask, N, Vs, wh, seg, saved, st);
+  return launch_fwd_cfg<4, 2, 16>(p, projects, mask, N, Vs, wh, seg, saved, st);
+}
+
+cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
+                           const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st) {
+  const int warps = 8;
+  const size_t smem = seg_base_smem(p->E, wh) + (size_t)((Vs * 2 + 3) & ~3) * 4 + (size_t)warps * kAccSlots * 8;
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  const SegGeom g = seg_geom(wh);
   LaunchScope scope(KID_SEG_BWD, st);
-  seg_bwd_kernel<<<N, warps * 32, smem, st>>>(projects, mask, g_seg, N, Vs, p->ptr, p->idx, p->P, p->E, wh, g_projects);
+#define SMPL_SEG_BWD(BW, BH, LX)                                                                                       \
+  do {                                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<BW, BH, LX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                    \
+    seg_bwd_kernel<BW, BH, LX><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->P,  \
+                                                            p->E, wh, g.tiles_x, g.ntiles, g_projects);                \
+  } while (0)
+  if (wh % 48 == 0) SMPL_SEG_BWD(3, 2, 16);
+  else SMPL_SEG_BWD(4, 2, 16);
+#undef SMPL_SEG_BWD
   return cudaGetLastError();
 }
 

@@ -258,24 +258,28 @@ class _SegFn(torch.autograd.Function):
         if pwd.dim() != 3 or pwd.shape[2] != 3 or tuple(mask.shape) != (N, Vs):
             raise ValueError("expected projects (N,Vs,3) and mask (N,Vs), got %s and %s" %
                              (tuple(pwd.shape), tuple(mask.shape)))
+        need_grad = bool(ctx.needs_input_grad[0])
         with torch.cuda.device(pwd.device):
             seg = torch.empty((N, img_wh, img_wh, table.P + 1), dtype=torch.float32, device=pwd.device)
-            _lib.check(lib.smpl_b200_seg_fwd(table.handle, _ptr(pwd), _ptr(mask), N, Vs, img_wh, _ptr(seg), _stream()),
-                       "smpl_b200_seg_fwd")
+            # the backward's state: clip gate + arg-min byte per (pixel, part); only produced when a backward can follow
+            saved = _workspace(lib.smpl_b200_seg_saved_bytes(N, img_wh), pwd.device) if need_grad else None
+            _lib.check(lib.smpl_b200_seg_fwd(table.handle, _ptr(pwd), _ptr(mask), N, Vs, img_wh, _ptr(seg), _ptr(saved),
+                                             _stream()), "smpl_b200_seg_fwd")
         ctx.table, ctx.img_wh = table, img_wh
-        ctx.save_for_backward(pwd, mask)
+        if need_grad:
+            ctx.save_for_backward(pwd, mask, saved)
         return seg
 
     @staticmethod
     def backward(ctx, g_seg):
         lib = _lib.load()
-        pwd, mask = ctx.saved_tensors
+        pwd, mask, saved = ctx.saved_tensors
         g_seg = _check_cuda_f32(g_seg, "grad seg")
         N, Vs = pwd.shape[0], pwd.shape[1]
         with torch.cuda.device(pwd.device):
             g_pwd = torch.empty_like(pwd)
-            _lib.check(lib.smpl_b200_seg_bwd(ctx.table.handle, _ptr(pwd), _ptr(mask), _ptr(g_seg), N, Vs, ctx.img_wh,
-                                             _ptr(g_pwd), _stream()), "smpl_b200_seg_bwd")
+            _lib.check(lib.smpl_b200_seg_bwd(ctx.table.handle, _ptr(pwd), _ptr(mask), _ptr(g_seg), _ptr(saved), N, Vs,
+                                             ctx.img_wh, _ptr(g_pwd), _stream()), "smpl_b200_seg_bwd")
         return g_pwd, None, None, None       # the mask is a constant (compute_mask.py:30, back_prop=False)
 
 
