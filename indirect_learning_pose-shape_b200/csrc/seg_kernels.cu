@@ -111,23 +111,42 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
       if (other) {
         const int slot = p1 - 1 - (no + __popc(bo & lt));
         unsigned next = kNone16;
-        if (w >= kHeavyMin) {
-          const float pu = rintf(u), pv = rintf(v);
-          bool keep = pu >= 0.f && pu <= (float)(wh - 1) && pv >= 0.f && pv <= (float)(wh - 1);
-          if (keep) keep = __fmul_rn(sqrtf(dist2(u, v, pu, pv)), w) <= kDropX;
-          if (keep) {                                   // dropped heavy entries keep their slot but are never linked
-            next = (unsigned)atomicExch(&sm.head[(int)pv * wh + (int)pu], slot) & 0xffffu;
-            atomicAdd(sm.nheavy, 1);
-          }
-        } else {
-          next = (unsigned)atomicExch(sm.ghead, slot) & 0xffffu;
-        }
+        // heavy entries are linked in a second pass (below), once the part's light list is complete
+        if (!(w >= kHeavyMin)) next = (unsigned)atomicExch(sm.ghead, slot) & 0xffffu;
         sm.ent[slot] = make_float4(u, v, w, __uint_as_float(((unsigned)e & 0xffffu) | (next << 16)));
       }
       nl += __popc(bl);
       no += __popc(bo);
     }
     if (lane == 0) sm.lcount[k] = nl;
+    __syncwarp();
+    // Second pass over this part's heavy entries (they sit at the back of the segment): a heavy vertex reaches only
+    // the pixel it rounds to, and matters only if it BEATS the part's light minimum there -- the same comparison
+    // (x_heavy < sqrt(min d2_light)) the per-pixel path makes, so dropping the losers is exact.  Winners are chained.
+    for (int base = p1 - no; base < p1; base += 32) {
+      const int slot = base + lane;
+      if (slot < p1) {
+        const float4 h = sm.ent[slot];
+        if (h.z >= kHeavyMin) {
+          const float pu = rintf(h.x), pv = rintf(h.y);
+          if (pu >= 0.f && pu <= (float)(wh - 1) && pv >= 0.f && pv <= (float)(wh - 1)) {
+            const float xh = __fmul_rn(sqrtf(dist2(h.x, h.y, pu, pv)), h.z);
+            if (xh <= kDropX) {
+              float best = CUDART_INF_F;
+              for (int i = 0; i < nl; ++i) {
+                const float4 l = sm.ent[p0 + i];
+                best = fminf(best, dist2(l.x, l.y, pu, pv));
+              }
+              if (xh < sqrtf(best)) {
+                const unsigned next = (unsigned)atomicExch(&sm.head[(int)pv * wh + (int)pu], slot) & 0xffffu;
+                sm.ent[slot].w = __uint_as_float((__float_as_uint(h.w) & 0xffffu) | (next << 16));
+                atomicAdd(sm.nheavy, 1);
+              }
+            }
+          }
+        }
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x < 32) {                               // exclusive scan of the light counts
@@ -390,7 +409,7 @@ __device__ __noinline__ void slow_pixel_grad(const SegSmem& sm, const int* __res
   atomicAdd(&gacc[vid * 2 + 1], coef * dv);
 }
 
-template <int BW, int BH, int LX>
+template <int BW, int BH, int LX, bool C32>
 __global__ void __launch_bounds__(256, 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
@@ -408,19 +427,31 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   for (int i = threadIdx.x; i < nwarps * kAccSlots; i += blockDim.x) wacc_all[i] = make_float2(0.f, 0.f);
   classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
   const int ghead = *sm.ghead;
-  const int C = P + 1;
+  const int C = C32 ? 32 : P + 1;
   const bool live = lane >= 1 && lane < C;                          // lane = channel; channel 0 carries the gate
   const int k = live ? lane - 1 : 0;
   const int p0 = sm.pptr[k], p1 = sm.pptr[k + 1], nl = sm.lcount[k];
+  const float4* ent_k = sm.ent + p0;
   float2* wacc = wacc_all + (size_t)warp * kAccSlots + sm.lbase[k]; // this lane's part, private to (warp, lane)
   const int acc_cap = kAccSlots - sm.lbase[k];                      // light indices >= acc_cap overflow to atomics
   const size_t plane = (size_t)ntiles * NB * 32 * 8;
   const unsigned char* sv = saved + (size_t)n * plane * 4 + (size_t)(lane >> 3) * plane + (lane & 7);
   const float* g_n = g_seg + (size_t)n * wh * wh * C + (lane < C ? lane : 0);
   const int nrec = ntiles * NB * 32;
+  const bool all_in = (wh % TW == 0) && (wh % TH == 0);             // every record is a pixel of the image
 
   int run_li = -1;                                                  // current run: light index within this lane's part
   float run_u = 0.f, run_v = 0.f;
+  auto flush = [&]() {
+    if (run_li < acc_cap) {                                         // private slot: this lane is its only writer
+      float2 a = wacc[run_li];
+      a.x += run_u; a.y += run_v;
+      wacc[run_li] = a;
+    } else {
+      const int vid = __float_as_int(ent_k[run_li].w);
+      atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
+    }
+  };
   // records in the forward's order: id = (tile*NB + b)*32 + l32 ; a batch = kBatch consecutive lanes of one block row
   for (int base = warp * kBatch; base < nrec; base += nwarps * kBatch) {
     const int l0 = base & 31, tb = base >> 5;
@@ -428,67 +459,47 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     const int ty = (tiles_x == 1) ? t : t / tiles_x, tx = t - ty * tiles_x;
     const int r = ty * TH + (l0 / LX) * BH + b / BW;
     const int cb = tx * TW + (l0 % LX) * BW + b % BW;               // column of the batch's first record; +BW per record
-    const bool row_in = r < wh;
+    const bool row_in = all_in || r < wh;
     const float* grow = g_n + ((wh - 1 - r) * wh + cb) * C;         // rows flipped (:68)
     const unsigned char* srow = sv + (size_t)base * 8;
     int code[kBatch];
     float g[kBatch];
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {                              // issue the whole batch of loads first
-      const bool in = row_in && (cb + j * BW) < wh;
+      const bool in = row_in && (all_in || (cb + j * BW) < wh);
       code[j] = in ? (int)srow[j * 8] : 0;
-      g[j] = (in && lane < C) ? grow[j * BW * C] : 0.f;
+      g[j] = (in && (C32 || lane < C)) ? grow[j * BW * C] : 0.f;
     }
-    const float gy = (float)r;
+    const float gy = (float)r, gxb = (float)cb;
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {
       const int gate = __shfl_sync(0xffffffffu, code[j], 0);
       const float g0 = __shfl_sync(0xffffffffu, g[j], 0);
       const float G = g[j] - ((gate & 1) ? g0 : 0.f);               // d bg / d s_k = -gate
-      const float gx = (float)(cb + j * BW);
-      int li = -1;
+      const float gx = gxb + (float)(j * BW);
+      int li = live ? code[j] - 1 : -1;                             // 0 -> -1 none
       float cu = 0.f, cv = 0.f;
-      if (live && code[j] != 0) {
-        if (code[j] == 255) {
-          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gx, gy, sm.head[r * wh + cb + j * BW], ghead, G);
-        } else {
-          li = code[j] - 1;
-          const float4 e = sm.ent[p0 + li];                         // light entry: w == 1
-          const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
-          const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
-          const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
-          const float s = ex2_approx((d2 * rs) * (-kLog2e));
-          const float coef = -(s * G) * rs;                         // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
-          cu = coef * du; cv = coef * dv;
-        }
+      if (li == 254) {                                              // code 255: rare exact re-query, atomics
+        slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gx, gy, sm.head[r * wh + cb + j * BW], ghead, G);
+        li = -1;
+      } else if (li >= 0) {
+        const float4 e = ent_k[li];                                 // light entry: w == 1
+        const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+        const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+        const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
+        const float s = ex2_approx((d2 * rs) * (-kLog2e));
+        const float coef = -(s * G) * rs;                           // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
+        cu = coef * du; cv = coef * dv;
       }
       if (li != run_li) {
-        if (run_li >= 0) {
-          if (run_li < acc_cap) {                                   // private slot: this lane is its only writer
-            float2 a = wacc[run_li];
-            a.x += run_u; a.y += run_v;
-            wacc[run_li] = a;
-          } else {
-            const int vid = __float_as_int(sm.ent[p0 + run_li].w);
-            atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
-          }
-        }
+        if (run_li >= 0) flush();
         run_li = li; run_u = cu; run_v = cv;
       } else {
         run_u += cu; run_v += cv;
       }
     }
   }
-  if (run_li >= 0) {
-    if (run_li < acc_cap) {
-      float2 a = wacc[run_li];
-      a.x += run_u; a.y += run_v;
-      wacc[run_li] = a;
-    } else {
-      const int vid = __float_as_int(sm.ent[p0 + run_li].w);
-      atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
-    }
-  }
+  if (run_li >= 0) flush();
   __syncthreads();
   // fold the warps' private slots into the per-vertex sums (a vertex may sit in more than one part)
   const int nlight = min(sm.lbase[31] + sm.lcount[31], kAccSlots);
@@ -562,15 +573,16 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   const SegGeom g = seg_geom(wh);
   LaunchScope scope(KID_SEG_BWD, st);
-#define SMPL_SEG_BWD(BW, BH, LX)                                                                                       \
+#define SMPL_SEG_BWD(BW, BH, LX, C32)                                                                                  \
   do {                                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<BW, BH, LX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<BW, BH, LX, C32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    seg_bwd_kernel<BW, BH, LX><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->P,  \
-                                                            p->E, wh, g.tiles_x, g.ntiles, g_projects);                \
+    seg_bwd_kernel<BW, BH, LX, C32><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx,  \
+                                                                 p->P, p->E, wh, g.tiles_x, g.ntiles, g_projects);     \
   } while (0)
-  if (wh % 48 == 0) SMPL_SEG_BWD(3, 2, 16);
-  else SMPL_SEG_BWD(4, 2, 16);
+  const bool c32 = p->P == 31;
+  if (wh % 48 == 0) { if (c32) SMPL_SEG_BWD(3, 2, 16, true); else SMPL_SEG_BWD(3, 2, 16, false); }
+  else { if (c32) SMPL_SEG_BWD(4, 2, 16, true); else SMPL_SEG_BWD(4, 2, 16, false); }
 #undef SMPL_SEG_BWD
   return cudaGetLastError();
 }
