@@ -42,7 +42,7 @@ BYTES_FWD = 344 + V * 12 + VS_COUNT * 12 + VS_COUNT * 4 + IMG_WH * IMG_WH * 32 *
 BYTES_BWD = IMG_WH * IMG_WH * 32 * 4 + 344 + 344                                            # 295,600
 BYTES_STEP = BYTES_FWD + BYTES_BWD                                                          # 695,584
 SEG_BYTES = IMG_WH * IMG_WH * 32 * 4
-LD = (V * 3 + 127) // 128 * 128
+LD = (V + 255) // 256 * 768
 # per-kernel algorithmic bytes per sample: tensors the kernel must read + write once
 KERNEL_BYTES = {
     "pose_fwd": 344 + 224 * 4 + 24 * 12 * 4 + 24 * 3 * 4,

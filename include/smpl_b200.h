@@ -31,7 +31,7 @@ extern "C" {
 #define SMPL_B200_ABI_VERSION 1
 #define SMPL_B200_NUM_PARAMS 86
 #define SMPL_B200_NUM_JOINTS 24
-#define SMPL_B200_VPOSED_LD(num_verts) ((((num_verts) * 3 + 127) / 128) * 128) /* row stride (floats) of the saved v_posed */
+#define SMPL_B200_VPOSED_LD(num_verts) ((((num_verts) + 255) / 256) * 768) /* row stride (floats) of the saved v_posed: whole 256-vertex chunks */
 
 typedef enum SmplB200Status {
   SMPL_B200_OK = 0,

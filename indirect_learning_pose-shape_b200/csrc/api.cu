@@ -80,11 +80,17 @@ static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
   const int V = m->V;
   const int Vs = (V + vs - 1) / vs;
   const int ncols = Vs * 3;
-  const int Kp = (ncols + 15) / 16 * 16;
-  std::vector<float> bt((size_t)Kp * kKPad, 0.f);
+  const int Kp = (ncols + 31) / 32 * 32;
+  std::vector<float> bt((size_t)Kp * kKPad, 0.f), bsh((size_t)kKPad * Kp, 0.f), bsl((size_t)kKPad * Kp, 0.f);
   for (int c = 0; c < ncols; ++c) {
     const int col = 3 * vs * (c / 3) + (c % 3);
-    for (int k = 0; k < kK; ++k) bt[(size_t)c * kKPad + k] = m->h_Bm[(size_t)k * (3 * V) + col];
+    for (int k = 0; k < kK; ++k) {
+      const float x = m->h_Bm[(size_t)k * (3 * V) + col];
+      bt[(size_t)c * kKPad + k] = x;
+      const float h = tf32_hi(x);
+      bsh[(size_t)k * Kp + c] = h;
+      bsl[(size_t)k * Kp + c] = x - h;
+    }
   }
   std::vector<int> ptr(kJ + 1, 0), vert;
   std::vector<float> w;
@@ -96,6 +102,8 @@ static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
     ptr[j + 1] = (int)vert.size();
   }
   CU_TRY(upload(&t->BmT, bt));
+  CU_TRY(upload(&t->Bs_hi, bsh));
+  CU_TRY(upload(&t->Bs_lo, bsl));
   CU_TRY(upload(&t->csc_ptr, ptr));
   CU_TRY(upload(&t->csc_vert, vert));
   CU_TRY(upload(&t->csc_w, w));
@@ -230,6 +238,24 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
     memcpy(vt.data(), h->v_template, sizeof(float) * C);
     CU_TRY(upload(&m->Bm, bm));
     CU_TRY(upload(&m->vt_pad, vt));
+    // K-major copies for the tensor-core forward: BT[c][k] = Bm[k][c], split exactly into TF32 hi + remainder
+    std::vector<float> bth((size_t)m->LD * kKPad, 0.f), btl((size_t)m->LD * kKPad, 0.f);
+    for (int k = 0; k < kK; ++k)
+      for (size_t c = 0; c < C; ++c) {
+        const float x = m->h_Bm[(size_t)k * C + c];
+        const float h = tf32_hi(x);
+        bth[c * kKPad + k] = h;
+        btl[c * kKPad + k] = x - h;
+      }
+    CU_TRY(upload(&m->BT_hi, bth));
+    CU_TRY(upload(&m->BT_lo, btl));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    m->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+      set_error("model_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+      delete m; cudaSetDevice(prev); return SMPL_B200_ERR_NO_DEVICE;
+    }
   }
   // folded joint regression: J = Jt + Jd * beta   (exact algebra of batch_smpl.py:106-115, evaluated in fp64)
   {
@@ -302,10 +328,10 @@ void smpl_b200_model_destroy(SmplB200Model* m) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
-  cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
+  cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->BT_hi); cudaFree(m->BT_lo); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
   cudaFree(m->jr_ptr); cudaFree(m->jr_vert); cudaFree(m->jr_w);
   for (int i = 0; i < kMaxVsCache; ++i) {
-    cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w);
+    cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].Bs_hi); cudaFree(m->vst[i].Bs_lo); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w);
   }
   free(m->h_Bm); free(m->h_W);
   cudaSetDevice(prev);
@@ -370,7 +396,7 @@ void smpl_b200_parts_destroy(SmplB200Parts* p) {
 // ---- workspace layout ------------------------------------------------------------------------------------
 static size_t ru(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct DecodeWs {
-  float *X, *A, *Jtr, *gA, *gX, *gcam, *gvp;
+  float *X, *Xlo, *A, *Jtr, *gA, *gX, *gcam, *gvp, *gvplo;
   size_t gvp_ld;
   int cam_chunks;
   size_t bytes;
@@ -381,6 +407,7 @@ static DecodeWs decode_ws(const SmplB200Model* m, int N, bool bwd, bool full_gra
   size_t off = 0;
   auto take = [&](size_t nfloat) { float* r = (float*)(p + off); off += ru(nfloat * sizeof(float), 256); return r; };
   w.X = take((size_t)N * kKPad);
+  w.Xlo = take((size_t)N * kKPad);
   w.A = take((size_t)N * kJ * 12);
   w.Jtr = take((size_t)N * kJ * 3);
   if (bwd) {
@@ -389,8 +416,9 @@ static DecodeWs decode_ws(const SmplB200Model* m, int N, bool bwd, bool full_gra
     const int Vs = (m->V + vs - 1) / vs;
     w.cam_chunks = lbs_bwd_cam_chunks(Vs);
     w.gcam = take((size_t)N * 4 * w.cam_chunks);
-    w.gvp_ld = full_grad ? (size_t)m->LD : ru((size_t)Vs * 3, 16);   // >= VsTables::Kp, rows stay 16-byte aligned
+    w.gvp_ld = full_grad ? (size_t)m->LD : ru((size_t)Vs * 3, 32);   // >= VsTables::Kp, rows stay 16-byte aligned
     w.gvp = take((size_t)N * w.gvp_ld);
+    w.gvplo = take((size_t)N * w.gvp_ld);
   }
   w.bytes = off;
   return w;
@@ -440,8 +468,10 @@ int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, flo
   }
   float* vp = v_posed_save ? v_posed_save : (float*)((char*)workspace + w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, w.A, joints24 ? joints24 : w.Jtr, st));
-  CHECK_LAUNCH(launch_blend_fwd(m, w.X, N, vp, st));
+  const bool dense = N >= kDenseBatch;                                  // tensor cores only where the batch makes the GEMM dense
+  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, dense ? w.Xlo : nullptr, w.A, joints24 ? joints24 : w.Jtr, st));
+  if (dense) CHECK_LAUNCH(launch_blend_fwd_tc(m, w.X, w.Xlo, N, vp, st));
+  else CHECK_LAUNCH(launch_blend_fwd(m, w.X, N, vp, st));
   CHECK_LAUNCH(launch_lbs_fwd(m, vp, w.A, params, N, verts, projects, vs, st));
   if (joints_reg) CHECK_LAUNCH(launch_joints_reg_fwd(m, verts, N, num_reg_joints_used, joints_reg, st));
   return SMPL_B200_OK;
@@ -464,10 +494,12 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
     return SMPL_B200_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, w.A, w.Jtr, st));     // recompute A (cheap) instead of saving it
-  CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp, w.gvp_ld, w.gA,
-                              w.gcam, st));
-  CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
+  const bool dense = N >= kDenseBatch;
+  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, nullptr, w.A, w.Jtr, st));   // recompute A (cheap) instead of saving it
+  CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp,
+                              dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, st));
+  if (dense) CHECK_LAUNCH(launch_blend_bwd_tc(m, t, w.gvp, w.gvplo, w.gvp_ld, N, w.gX, st));
+  else CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
   CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, w.cam_chunks, N, g_params, st));
   return SMPL_B200_OK;
 }

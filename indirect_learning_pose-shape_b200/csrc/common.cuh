@@ -39,8 +39,10 @@ struct VsTables {       // per vertex_sampling derived tables (device pointers)
   int vs = 0;           // 0 = unused slot
   int Vs = 0;           // sampled vertex count
   int ncols = 0;        // Vs*3
-  int Kp = 0;           // ncols rounded up to a multiple of 16: depth of the backward blend product
+  int Kp = 0;           // ncols rounded up to a multiple of 32: depth of the backward blend product
   float* BmT = nullptr;       // [Kp][kKPad] : BmT[c][k] = Bm[k][col(c)],  col(c) = 3*vs*(c/3) + c%3 ; zero rows past ncols
+  float* Bs_hi = nullptr;     // [kKPad][Kp] : the same matrix K-major for the tensor-core backward, TF32 hi part
+  float* Bs_lo = nullptr;     // [kKPad][Kp] : ... and the exact remainder (x = hi + lo)
   int* csc_ptr = nullptr;     // [kJ+1]  joint -> entries (sampled vertices only)
   int* csc_vert = nullptr;    // [nnz]   ORIGINAL vertex id
   float* csc_w = nullptr;     // [nnz]
@@ -63,6 +65,9 @@ struct SmplB200Model {
   int R = 0;             // regressed joints
   float* vt_pad = nullptr;   // [LD]
   float* Bm = nullptr;       // [kKPad][LD]
+  float* BT_hi = nullptr;    // [LD][kKPad]  Bm transposed (K-major) for the tensor-core forward, TF32 hi part
+  float* BT_lo = nullptr;    // [LD][kKPad]  ... and the exact remainder
+  int num_sms = 148;
   float* Jt = nullptr;       // [kJ*3]
   float* Jd = nullptr;       // [kJ*3][kBetas]
   uint8_t* lbs_idx = nullptr;  // [V][KW]
@@ -93,8 +98,23 @@ namespace smplb200 {
 const VsTables* get_vs_tables(const SmplB200Model* m, int vs);
 
 // kernels launchers (implemented in the *_kernels.cu files). All return cudaError_t of the launch.
-cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* A, float* Jtr,
-                            cudaStream_t st);
+// X_lo == null: X receives the blend coefficients.  Otherwise X receives their TF32 hi part and X_lo the remainder.
+cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* X_lo, float* A,
+                            float* Jtr, cudaStream_t st);
+cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const float* Xl, int N, float* v_posed,
+                                cudaStream_t st);
+cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const float* gvp_hi, const float* gvp_lo,
+                                size_t gvp_ld, int N, float* g_X, cudaStream_t st);
+constexpr int kDenseBatch = 64;   // from this batch on the blend products run on the tensor cores
+
+// exact split of an fp32 value for the 3xTF32 product: hi keeps the 10 mantissa bits TF32 has, lo = x - hi
+__host__ __device__ __forceinline__ float tf32_hi(float x) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+#else
+  union { float f; unsigned u; } c; c.f = x; c.u &= 0xffffe000u; return c.f;
+#endif
+}
 cudaError_t launch_blend_fwd(const SmplB200Model* m, const float* X, int N, float* v_posed, cudaStream_t st);
 cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
                            float* verts, float* projects, int vs, cudaStream_t st);
@@ -102,9 +122,10 @@ cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, in
                                   cudaStream_t st);
 // t = tables of the PROCESSING stride (1 = every vertex, g_vp rows [LD]; >1 = sampled vertices only, g_vp rows
 // [gvp_ld] compact); vs_proj = sampling stride of g_projects.
+// g_vp_lo == null: g_vp receives the gradient.  Otherwise g_vp receives its TF32 hi part and g_vp_lo the remainder.
 cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
                            const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
-                           float* g_vp, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st);
+                           float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st);
 cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
                              float* g_X, cudaStream_t st);
 // g_cam = [cam_chunks][N][4] partial camera-gradient sums from launch_lbs_bwd (or null)

@@ -141,7 +141,8 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
                       const float* __restrict__ params, int N, int V, const uint8_t* __restrict__ lbs_idx,
                       const float* __restrict__ lbs_w, const float* __restrict__ g_verts,
                       const float* __restrict__ g_projects, int vs_proc, int Vp, int vs_proj, int Vs_proj,
-                      float* __restrict__ g_vp, int gvp_ld, int Kp, float* __restrict__ g_cam) {
+                      float* __restrict__ g_vp, float* __restrict__ g_vp_lo, int gvp_ld, int Kp,
+                      float* __restrict__ g_cam) {
   __shared__ __align__(16) float As[kGroup * kARow];
   __shared__ float cam[kGroup * 4];
   __shared__ float red[kChunk / 32][4];
@@ -164,9 +165,17 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
       float T[12];
       blend_T<KW>(skin, As + s * kARow, T);
       float* o = g_vp + (size_t)n * gvp_ld + (size_t)q * 3;
-      o[0] = fmaf(T[0], gx, fmaf(T[4], gy, T[8] * gz));
-      o[1] = fmaf(T[1], gx, fmaf(T[5], gy, T[9] * gz));
-      o[2] = fmaf(T[2], gx, fmaf(T[6], gy, T[10] * gz));
+      float r3[3];
+      r3[0] = fmaf(T[0], gx, fmaf(T[4], gy, T[8] * gz));
+      r3[1] = fmaf(T[1], gx, fmaf(T[5], gy, T[9] * gz));
+      r3[2] = fmaf(T[2], gx, fmaf(T[6], gy, T[10] * gz));
+      if (g_vp_lo) {                                // tensor-core blend backward: exact TF32 split
+        float* ol = g_vp_lo + (size_t)n * gvp_ld + (size_t)q * 3;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { const float h = tf32_hi(r3[e]); o[e] = h; ol[e] = r3[e] - h; }
+      } else {
+        o[0] = r3[0]; o[1] = r3[1]; o[2] = r3[2];
+      }
       if (g_projects) {
         const float* p = vp + (size_t)n * LD + (size_t)v * 3;
         const float x = p[0], y = p[1], z = p[2];
@@ -177,7 +186,10 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
     }
     if (blockIdx.x == gridDim.x - 1) {              // zero the K padding the blend backward reads
       const int c = Vp * 3 + tid;
-      if (c < Kp) g_vp[(size_t)n * gvp_ld + c] = 0.f;
+      if (c < Kp) {
+        g_vp[(size_t)n * gvp_ld + c] = 0.f;
+        if (g_vp_lo) g_vp_lo[(size_t)n * gvp_ld + c] = 0.f;
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) c4[k] = warp_sum(c4[k]);
@@ -325,7 +337,7 @@ cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const f
 
 cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
                            const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
-                           float* g_vp, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st) {
+                           float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st) {
   const int V = m->V, Vp = t->Vs, Vs_proj = (V + vs_proj - 1) / vs_proj;
   dim3 grid((Vp + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
   cudaError_t e;
@@ -333,8 +345,8 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
     LaunchScope scope(KID_LBS_BWD_VERTEX, st);
 #define SMPL_LBS_BWD(KW)                                                                                           \
   lbs_bwd_vertex_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, g_verts,   \
-                                                     g_projects, t->vs, Vp, vs_proj, Vs_proj, g_vp, (int)gvp_ld, t->Kp, \
-                                                     g_cam)
+                                                     g_projects, t->vs, Vp, vs_proj, Vs_proj, g_vp, g_vp_lo, (int)gvp_ld, \
+                                                     t->Kp, g_cam)
   if (m->KW == 4) SMPL_LBS_BWD(4);
   else if (m->KW == 8) SMPL_LBS_BWD(8);
   else SMPL_LBS_BWD(24);

@@ -147,19 +147,24 @@ __device__ __forceinline__ Chain forward_chain(const float* __restrict__ prm, co
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pose_fwd_kernel(const float* __restrict__ params, int N, const float* __restrict__ Jt, const float* __restrict__ Jd,
-                const TreeInfo tree, float* __restrict__ X, float* __restrict__ A, float* __restrict__ Jtr) {
+                const TreeInfo tree, float* __restrict__ X, float* __restrict__ Xlo, float* __restrict__ A,
+                float* __restrict__ Jtr) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (n >= N) return;
   const float* prm = params + (size_t)n * kParams;
   const Chain ch = forward_chain(prm, Jt, Jd, tree, lane);
   float* x = X + (size_t)n * kKPad;
-  if (lane < kBetas) x[lane] = prm[76 + lane];
-  if (lane < kKPad - kK) x[kK + lane] = 0.f;
+  float* xl = Xlo ? Xlo + (size_t)n * kKPad : nullptr;
+  auto put = [&](int i, float v) {              // tensor-core path: exact TF32 split x = hi + lo
+    if (xl) { const float h = tf32_hi(v); x[i] = h; xl[i] = v - h; }
+    else x[i] = v;
+  };
+  if (lane < kBetas) put(lane, prm[76 + lane]);
+  if (lane < kKPad - kK) put(kK + lane, 0.f);
   if (lane >= 1 && lane < kJ) {                 // pose_feature = Rs[:,1:] - I (:122)
-    float* pf = x + kBetas + (lane - 1) * 9;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) pf[i] = ch.rod.R.m[i] - ((i % 4 == 0) ? 1.f : 0.f);
+    for (int i = 0; i < 9; ++i) put(kBetas + (lane - 1) * 9 + i, ch.rod.R.m[i] - ((i % 4 == 0) ? 1.f : 0.f));
   }
   if (lane < kJ) {
     // A = results - pad(results * [J;0]) (:222-226): rotation block unchanged, translation tG - RG*J
@@ -307,11 +312,11 @@ pose_bwd_kernel(const float* __restrict__ params, int N, const float* __restrict
 
 }  // namespace
 
-cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* A, float* Jtr,
-                            cudaStream_t st) {
+cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* X_lo, float* A,
+                            float* Jtr, cudaStream_t st) {
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
   LaunchScope scope(KID_POSE_FWD, st);
-  pose_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, X, A, Jtr);
+  pose_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, X, X_lo, A, Jtr);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,323 @@
+// K1 on the 5th-generation tensor cores: error-compensated 3xTF32 GEMM,  D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]).
+//
+// Both blend products of the SMPL layer are this GEMM (batch_smpl.py:106-108,126-128 forward, their TF autodiff
+// backward):
+//   forward   v_posed[N][LD]  = X[N][224]     * BT[LD][224]^T + v_template      (BT = [shapedirs; posedirs]^T, K-major)
+//   backward  g_X[N][224]     = g_vp[N][Kp]   * Bs[224][Kp]^T
+// fp32 parity (1e-5 on vertices, ~3 ulp on projections) rules out plain TF32, so every operand is supplied as an
+// exact split x = hi + lo with hi = x truncated to TF32 precision (13 low mantissa bits cleared) and lo = x - hi, and
+// the product is accumulated as lo*hi + hi*lo + hi*hi (the dropped lo*lo term is 2^-22 relative).  hi is exactly
+// representable in TF32, so the result does not depend on how the tensor core rounds its inputs.
+// The tensor core's own fp32 accumulation is not round-to-nearest, and its error grows with the length of the
+// accumulation chain (measured here: 1.1e-6 on vertices at K=224, 1e-4 relative on gradients at K=4160 when the whole
+// K loop accumulates in TMEM).  So TMEM only ever accumulates ONE K block (32 deep: 12 MMAs); the epilogue warps add
+// each block's partial tile into fp32 REGISTER accumulators with round-to-nearest (Ootomo & Yokota's scheme), while
+// the tensor core works on the next block in the other TMEM buffer.
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 x BN, BN = 128 forward / 112 backward):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the four operand boxes (A_hi, A_lo, B_hi, B_lo; 32 fp32 = 128 B
+//               wide, SWIZZLE_128B) into a 3-stage ring, completion on a transaction mbarrier
+//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) per K
+//               block into TMEM buffer (block & 1); tcgen05.commit releases the smem stage and publishes the buffer.
+//               Owns the TMEM allocation.
+//   warps 2-5   accumulate + epilogue: tcgen05.ld 32x32b.x16 of the block's partial tile, FADD into BN registers per
+//               thread (one output row each); after the last block add bias, st.global.v8.f32 (full 32-byte sectors)
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace smplb200 {
+
+namespace {
+
+constexpr int kBM = 128;         // rows of an output tile (UMMA M, cta_group::1)
+constexpr int kBK = 32;          // fp32 per K block = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kThreads = 192;    // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int kTmemCols = 256;   // two partial-tile buffers of up to 128 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives on `bar` when all prior MMAs have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);     // [0,14)  start address >> 4
+  d |= (uint64_t)1 << 16;                       // [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
+  d |= (uint64_t)(1024 >> 4) << 32;             // [32,46) stride byte offset >> 4: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                       // [46,48) descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                       // [61,64) layout type: SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4)                 // [4,6)   c_format = F32
+         | (2u << 7)               // [7,10)  a_format = TF32
+         | (2u << 10)              // [10,13) b_format = TF32
+         | ((uint32_t)(N >> 3) << 17)   // [17,23) n_dim
+         | ((uint32_t)(M >> 4) << 24);  // [24,29) m_dim
+}
+
+template <int BN, bool BIAS>
+__global__ void __launch_bounds__(kThreads, 1)
+tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                   float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int kblocks, int tiles_m,
+                   int tiles_n) {
+  constexpr int kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
+  constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr int kAccStride = 128;                      // TMEM columns between the two partial-tile buffers
+  static_assert(BN % 16 == 0 && BN <= 128, "BN registers per epilogue thread");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;                   // partial tile of one K block ready in TMEM buffer b
+  uint64_t* tempty = tfull + 2;                        // TMEM buffer b drained into registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                     // TMEM allocation is warp-collective; this warp also frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kStageBytes;
+          mbar_expect_tx(&full[stage], kStageBytes);
+          tma_load_2d(st, &tmAh, &full[stage], kb * kBK, m0);
+          tma_load_2d(st + kABytes, &tmAl, &full[stage], kb * kBK, m0);
+          tma_load_2d(st + 2 * kABytes, &tmBh, &full[stage], kb * kBK, n0);
+          tma_load_2d(st + 2 * kABytes + kBBytes, &tmBl, &full[stage], kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, buf_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&tempty[buf], buf_phase ^ 1);      // the accumulate warps have drained this TMEM buffer
+          mbar_wait(&full[stage], phase);              // TMA has landed this stage
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t dAh = make_smem_desc(sa), dAl = make_smem_desc(sa + kABytes);
+          const uint64_t dBh = make_smem_desc(sa + 2 * kABytes), dBl = make_smem_desc(sa + 2 * kABytes + kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {          // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32(tmem_d, dAl + o, dBh + o, idesc, k ? 1u : 0u);           // small terms first; fresh per K block
+            umma_tf32(tmem_d, dAh + o, dBl + o, idesc, 1u);
+          }
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32(tmem_d, dAh + o, dBh + o, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);                  // frees this smem stage once the MMAs above have read it
+          umma_commit(&tfull[buf]);                    // this K block's partial tile is complete
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== accumulate (fp32 registers, round-to-nearest) + epilogue =====
+    const int q = warp & 3;                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+      float acc[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&tfull[buf], buf_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride);
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {             // two x16 loads in flight per wait
+          uint32_t r0[16], r1[16];
+          tmem_ld_32x32b_x16(taddr + c, r0);
+          if (c + 16 < BN) tmem_ld_32x32b_x16(taddr + c + 16, r1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[c + e] += __uint_as_float(r0[e]);
+          if (c + 16 < BN) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[c + 16 + e] += __uint_as_float(r1[e]);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+      }
+      const int row = m0 + q * 32 + lane;
+      if (row < M) {
+        float* drow = D + (size_t)row * ldd + n0;
+#pragma unroll
+        for (int c = 0; c < BN; c += 8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = acc[c + e];
+          if (BIAS) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + c + 4);
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+          }
+          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + c), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                       "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                       : "memory");
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+cudaError_t load_encode() {
+  if (g_encode) return cudaSuccess;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return cudaSuccess;
+}
+
+// 2-D fp32 tensor [rows][cols] with row pitch ld (floats); box = 32 columns x box_rows, SWIZZLE_128B, zero OOB fill.
+cudaError_t make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int BN, bool BIAS>
+cudaError_t launch_gemm(const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb, float* D,
+                        int ldd, const float* bias, int M, int Ntot, int K, int num_sms, cudaStream_t st) {
+  cudaError_t e = load_encode();
+  if (e != cudaSuccess) return e;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if ((e = make_map(&mAh, Ah, M, K, lda, kBM)) != cudaSuccess) return e;
+  if ((e = make_map(&mAl, Al, M, K, lda, kBM)) != cudaSuccess) return e;
+  if ((e = make_map(&mBh, Bh, Ntot, K, ldb, BN)) != cudaSuccess) return e;
+  if ((e = make_map(&mBl, Bl, Ntot, K, ldb, BN)) != cudaSuccess) return e;
+  constexpr int kStageBytes = 2 * kBM * kBK * 4 + 2 * BN * kBK * 4;
+  const size_t smem = (size_t)kStages * kStageBytes + 256 + 1024;
+  e = cudaFuncSetAttribute(tf32x3_gemm_kernel<BN, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int tiles_m = (M + kBM - 1) / kBM, tiles_n = Ntot / BN;
+  const int grid = min(tiles_m * tiles_n, num_sms);
+  tf32x3_gemm_kernel<BN, BIAS><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, K / kBK, tiles_m, tiles_n);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// v_posed[N][LD] = X[N][224] * BT[LD][224]^T + v_template   (LD is a multiple of 768, hence of BN = 128)
+cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const float* Xl, int N, float* v_posed,
+                                cudaStream_t st) {
+  LaunchScope scope(KID_BLEND_FWD, st);
+  return launch_gemm<128, true>(Xh, Xl, kKPad, m->BT_hi, m->BT_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD, kKPad,
+                                m->num_sms, st);
+}
+
+// g_X[N][224] = g_vp[N][Kp] * Bs[224][Kp]^T   (Kp a multiple of 32)
+cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const float* gvp_hi, const float* gvp_lo,
+                                size_t gvp_ld, int N, float* g_X, cudaStream_t st) {
+  LaunchScope scope(KID_BLEND_BWD, st);
+  return launch_gemm<kKPad / 2, false>(gvp_hi, gvp_lo, (int)gvp_ld, t->Bs_hi, t->Bs_lo, t->Kp, g_X, kKPad, nullptr, N,
+                                       kKPad, t->Kp, m->num_sms, st);
+}
+
+}  // namespace smplb200

@@ -86,7 +86,7 @@ class DeviceModel:
         self.handle = handle
         self.V = int(lib.smpl_b200_model_num_verts(handle))
         self.lbs_width = int(lib.smpl_b200_model_lbs_width(handle))
-        self.LD = (self.V * 3 + 127) // 128 * 128
+        self.LD = (self.V + 255) // 256 * 768            # SMPL_B200_VPOSED_LD
         self.R = int(host_model.joint_regressor.shape[1])
         self._finalizer = weakref.finalize(self, lib.smpl_b200_model_destroy, handle)
 
