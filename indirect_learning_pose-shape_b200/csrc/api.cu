@@ -92,15 +92,28 @@ static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
       bsl[(size_t)k * Kp + c] = x - h;
     }
   }
-  std::vector<int> ptr(kJ + 1, 0), vert;
+  std::vector<int> ptr(kJ + 1, 0), vert, vq;
   std::vector<float> w;
   for (int j = 0; j < kJ; ++j) {
     for (int v = 0; v < V; v += vs) {
       float x = m->h_W[(size_t)v * kJ + j];
-      if (x != 0.f) { vert.push_back(v); w.push_back(x); }
+      if (x != 0.f) { vert.push_back(v); vq.push_back(v / vs); w.push_back(x); }
     }
     ptr[j + 1] = (int)vert.size();
   }
+  // compact ELL skin weights of the sampled vertices (same packing as model_create)
+  std::vector<uint8_t> sidx((size_t)Vs * m->KW, 0);
+  std::vector<float> sw((size_t)Vs * m->KW, 0.f);
+  for (int q = 0; q < Vs; ++q) {
+    int nn = 0;
+    for (int j = 0; j < kJ; ++j) {
+      float x = m->h_W[(size_t)(q * vs) * kJ + j];
+      if (x != 0.f) { sidx[(size_t)q * m->KW + nn] = (uint8_t)j; sw[(size_t)q * m->KW + nn] = x; ++nn; }
+    }
+  }
+  CU_TRY(upload(&t->lbs_idx_s, sidx));
+  CU_TRY(upload(&t->lbs_w_s, sw));
+  CU_TRY(upload(&t->csc_q, vq));
   CU_TRY(upload(&t->BmT, bt));
   CU_TRY(upload(&t->Bs_hi, bsh));
   CU_TRY(upload(&t->Bs_lo, bsl));
@@ -331,7 +344,8 @@ void smpl_b200_model_destroy(SmplB200Model* m) {
   cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->BT_hi); cudaFree(m->BT_lo); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
   cudaFree(m->jr_ptr); cudaFree(m->jr_vert); cudaFree(m->jr_w);
   for (int i = 0; i < kMaxVsCache; ++i) {
-    cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].Bs_hi); cudaFree(m->vst[i].Bs_lo); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w);
+    cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].Bs_hi); cudaFree(m->vst[i].Bs_lo); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w); cudaFree(m->vst[i].csc_q);
+    cudaFree(m->vst[i].lbs_idx_s); cudaFree(m->vst[i].lbs_w_s);
   }
   free(m->h_Bm); free(m->h_W);
   cudaSetDevice(prev);
@@ -496,11 +510,12 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   cudaStream_t st = (cudaStream_t)stream;
   const bool dense = N >= kDenseBatch;
   CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, nullptr, w.A, w.Jtr, st));   // recompute A (cheap) instead of saving it
+  int cam_chunks = w.cam_chunks;
   CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp,
-                              dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, st));
+                              dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, &cam_chunks, st));
   if (dense) CHECK_LAUNCH(launch_blend_bwd_tc(m, t, w.gvp, w.gvplo, w.gvp_ld, N, w.gX, st));
   else CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
-  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, w.cam_chunks, N, g_params, st));
+  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, cam_chunks, N, g_params, st));
   return SMPL_B200_OK;
 }
 

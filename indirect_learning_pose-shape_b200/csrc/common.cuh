@@ -45,7 +45,10 @@ struct VsTables {       // per vertex_sampling derived tables (device pointers)
   float* Bs_lo = nullptr;     // [kKPad][Kp] : ... and the exact remainder (x = hi + lo)
   int* csc_ptr = nullptr;     // [kJ+1]  joint -> entries (sampled vertices only)
   int* csc_vert = nullptr;    // [nnz]   ORIGINAL vertex id
+  int* csc_q = nullptr;       // [nnz]   sampled-space vertex index (vertex id / vs)
   float* csc_w = nullptr;     // [nnz]
+  uint8_t* lbs_idx_s = nullptr;  // [Vs][KW] skin-weight joints of the sampled vertices (compact copy of lbs_idx)
+  float* lbs_w_s = nullptr;      // [Vs][KW]
 };
 
 struct TreeInfo {       // passed by value to the pose kernels
@@ -125,7 +128,8 @@ cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, in
 // g_vp_lo == null: g_vp receives the gradient.  Otherwise g_vp receives its TF32 hi part and g_vp_lo the remainder.
 cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
                            const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
-                           float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st);
+                           float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, int* cam_chunks,
+                           cudaStream_t st);   // cam_chunks: how many [N][4] partial-sum planes of g_cam were written
 cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
                              float* g_X, cudaStream_t st);
 // g_cam = [cam_chunks][N][4] partial camera-gradient sums from launch_lbs_bwd (or null)

@@ -247,6 +247,100 @@ lbs_bwd_joint_kernel(const float* __restrict__ vp, int LD, const float* __restri
   }
 }
 
+// Sampled backward (the training configuration: the gradient arrives only through the projection of every vs-th
+// vertex).  One block per sample, one pass over global memory:
+//   phase 1 (thread = sampled vertex): g_vert = (k_u g_u, k_v g_v, g_z), T = sum_k w_k A[j_k], g_vp = R_T^T g_vert (written
+//           as an exact TF32 hi/lo pair for the tensor-core blend backward), camera-gradient partials; g_vert and
+//           v_posed of the sampled vertices are parked in shared memory;
+//   phase 2 (warp = joint, 3 joints per warp): g_A[j] = sum_{v in joint j} w_vj g_vert_v (x) [v_posed_v; 1] from shared
+//           memory through the joint's CSC list, warp-reduced: no atomics, deterministic.
+template <int KW>
+__global__ void __launch_bounds__(256)
+lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A,
+                       const float* __restrict__ params, int N, int vs, int Vs, const uint8_t* __restrict__ sidx,
+                       const float* __restrict__ sw, const int* __restrict__ csc_ptr, const int* __restrict__ csc_q,
+                       const float* __restrict__ csc_w, const float* __restrict__ g_projects,
+                       float* __restrict__ g_vp, float* __restrict__ g_vp_lo, int gvp_ld, int Kp,
+                       float* __restrict__ g_A, float* __restrict__ g_cam) {
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                         // [24][12]
+  float* sg = As + kARow;                 // [Vs][3] gradient at the sampled vertices
+  float* sp = sg + Vs * 3;                // [Vs][3] their rest-pose positions
+  __shared__ float red[8][4];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kARow / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(As)[i] = reinterpret_cast<const float4*>(A + (size_t)n * kARow)[i];
+  const float ku = params[(size_t)n * kParams], kv = params[(size_t)n * kParams + 1];
+  __syncthreads();
+  const float* gp = g_projects + (size_t)n * Vs * 3;
+  const float* vrow = vp + (size_t)n * LD;
+  float* orow = g_vp + (size_t)n * gvp_ld;
+  float* lrow = g_vp_lo ? g_vp_lo + (size_t)n * gvp_ld : nullptr;
+  float c4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q = tid; q < Vs; q += blockDim.x) {
+    const Skin<KW> skin = load_skin<KW>(sidx, sw, q);
+    const float gu = gp[q * 3], gv = gp[q * 3 + 1], gz = gp[q * 3 + 2];
+    const float x = vrow[(size_t)q * vs * 3], y = vrow[(size_t)q * vs * 3 + 1], z = vrow[(size_t)q * vs * 3 + 2];
+    const float gx = gu * ku, gy = gv * kv;                       // u = u0 + x k_u, v = v0 + y k_v (projection.py:77-78)
+    float T[12];
+    blend_T<KW>(skin, As, T);
+    float r3[3];
+    r3[0] = fmaf(T[0], gx, fmaf(T[4], gy, T[8] * gz));
+    r3[1] = fmaf(T[1], gx, fmaf(T[5], gy, T[9] * gz));
+    r3[2] = fmaf(T[2], gx, fmaf(T[6], gy, T[10] * gz));
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      if (lrow) { const float h = tf32_hi(r3[e]); orow[q * 3 + e] = h; lrow[q * 3 + e] = r3[e] - h; }
+      else orow[q * 3 + e] = r3[e];
+    }
+    const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+    const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+    c4[0] = fmaf(gu, ox, c4[0]); c4[1] = fmaf(gv, oy, c4[1]); c4[2] += gu; c4[3] += gv;
+    sg[q * 3] = gx; sg[q * 3 + 1] = gy; sg[q * 3 + 2] = gz;
+    sp[q * 3] = x; sp[q * 3 + 1] = y; sp[q * 3 + 2] = z;
+  }
+  for (int c = Vs * 3 + tid; c < Kp; c += blockDim.x) {           // zero the K padding the blend backward reads
+    orow[c] = 0.f;
+    if (lrow) lrow[c] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c4[k] = warp_sum(c4[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[warp][k] = c4[k];
+  }
+  __syncthreads();
+  if (tid < 4) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][tid];
+    g_cam[(size_t)n * 4 + tid] = t;
+  }
+  for (int j = warp; j < kJ; j += (int)(blockDim.x >> 5)) {
+    float acc[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+    const int e1 = csc_ptr[j + 1];
+    for (int e = csc_ptr[j] + lane; e < e1; e += 32) {
+      const int q = csc_q[e];
+      const float w = csc_w[e];
+      const float gx = sg[q * 3] * w, gy = sg[q * 3 + 1] * w, gz = sg[q * 3 + 2] * w;
+      const float x = sp[q * 3], y = sp[q * 3 + 1], z = sp[q * 3 + 2];
+      acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
+      acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
+      acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
+    if (lane < 3) {
+      float4 r;
+      if (lane == 0) r = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else if (lane == 1) r = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      else r = make_float4(acc[8], acc[9], acc[10], acc[11]);
+      reinterpret_cast<float4*>(g_A + ((size_t)n * kJ + j) * 12)[lane] = r;
+    }
+  }
+}
+
 // ---- stand-alone projection (projection.py:54-81) ---------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 project_fwd_kernel(const float* __restrict__ verts, const float* __restrict__ params, int N, int V, int vs, int Vs,
@@ -337,8 +431,29 @@ cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const f
 
 cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
                            const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
-                           float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, cudaStream_t st) {
+                           float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, int* cam_chunks,
+                           cudaStream_t st) {
   const int V = m->V, Vp = t->Vs, Vs_proj = (V + vs_proj - 1) / vs_proj;
+  if (t->vs > 1 && !g_verts && g_projects && t->vs == vs_proj) {
+    // sampled backward: one fused kernel, one block per sample
+    const size_t smem = (size_t)(kARow + 6 * Vp) * sizeof(float);
+    LaunchScope scope(KID_LBS_BWD_VERTEX, st);
+    *cam_chunks = 1;
+#define SMPL_LBS_BWD_S(KW)                                                                                          \
+  do {                                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(lbs_bwd_sampled_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                \
+    lbs_bwd_sampled_kernel<KW><<<N, 256, smem, st>>>(v_posed, m->LD, A, params, N, t->vs, Vp, t->lbs_idx_s, t->lbs_w_s, \
+                                                     t->csc_ptr, t->csc_q, t->csc_w, g_projects, g_vp, g_vp_lo,      \
+                                                     (int)gvp_ld, t->Kp, g_A, g_cam);                              \
+  } while (0)
+    if (m->KW == 4) SMPL_LBS_BWD_S(4);
+    else if (m->KW == 8) SMPL_LBS_BWD_S(8);
+    else SMPL_LBS_BWD_S(24);
+#undef SMPL_LBS_BWD_S
+    return cudaGetLastError();
+  }
+  *cam_chunks = (Vp + kChunk - 1) / kChunk;
   dim3 grid((Vp + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
   cudaError_t e;
   {

@@ -184,6 +184,7 @@ class _DecodeFn(torch.autograd.Function):
                                                 num_keypoints, _ptr(vp), _ptr(proj), max(project_vs, 1), _ptr(ws),
                                                 ws.numel(), _stream()), "smpl_b200_decode_fwd")
         ctx.dm, ctx.project_vs = dm, project_vs
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as dense zero tensors
         ctx.save_for_backward(params, vp)
         if keyp is not None:
             ctx.mark_non_differentiable(keyp)     # dead code in the reference (batch_smpl.py:147-151): forward only
@@ -193,6 +194,8 @@ class _DecodeFn(torch.autograd.Function):
     def backward(ctx, g_verts, g_joints, g_keyp, g_proj):
         lib = _lib.load()
         params, vp = ctx.saved_tensors
+        if g_verts is None and g_joints is None and g_proj is None:
+            return None, None, None, None, None
         dm = ctx.dm
         N = params.shape[0]
         dev = params.device
