@@ -216,8 +216,8 @@ struct SegGeom {
 };
 SegGeom seg_geom(int wh) {
   SegGeom g;
-  if (wh % 48 == 0) { g.BW = 3; g.BH = 2; g.LX = 16; }        // 48 x 4 pixel tiles
-  else { g.BW = 4; g.BH = 2; g.LX = 16; }                     // 64 x 4 pixel tiles
+  if (wh % 12 == 0) { g.BW = 3; g.BH = 2; g.LX = 4; }         // 12 x 16 pixel tiles (48 = 4 x 3 tiles)
+  else { g.BW = 4; g.BH = 2; g.LX = 4; }                      // 16 x 16 pixel tiles
   g.LY = 32 / g.LX; g.TW = g.LX * g.BW; g.TH = g.LY * g.BH; g.NB = g.BW * g.BH;
   g.tiles_x = (wh + g.TW - 1) / g.TW; g.tiles_y = (wh + g.TH - 1) / g.TH; g.ntiles = g.tiles_x * g.tiles_y;
   return g;
@@ -227,6 +227,8 @@ SegGeom seg_geom(int wh) {
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 constexpr float kBigD2 = 1e30f;      // "no vertex yet": rsqrt/ex2 map it to a score of exactly 0 without a branch
+constexpr int kNoPrune = 3;          // parts with this few visible vertices skip the pruning pass
+constexpr float kPruneMargin = 0.01f;
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float r;
@@ -268,6 +270,9 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   for (int t = t0 + warp; t < t1; t += nwarps) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int c0 = tx * TW + lx * BW, r0 = ty * TH + ly * BH;      // this lane's block origin (grid = (column,row), :26-31)
+    const float cx0 = (float)(tx * TW), cx1 = (float)(tx * TW + TW - 1);   // tile corners (pixel centres) and centre
+    const float cy0 = (float)(ty * TH), cy1 = (float)(ty * TH + TH - 1);
+    const float tcx = 0.5f * (cx0 + cx1), tcy = 0.5f * (cy0 + cy1);
     float gxs[BW], gys[BH];
 #pragma unroll
     for (int i = 0; i < BW; ++i) gxs[i] = (float)(c0 + i);
@@ -284,6 +289,36 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     float S[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q) S[q] = 0.f;
+
+    // Exact pruning, once per tile, lane k working on part k.  i0 = the part's vertex nearest the tile centre.
+    // f(g) = d_j^2(g) - d_i0^2(g) is linear in the pixel g, so f >= margin at the tile's four corners implies f >= margin on
+    // every pixel of the tile: vertex j can never be the arg-min there and is dropped from the part's survivor mask.
+    // The margin (0.01 px^2) dwarfs the fp32 rounding of the squared distances (< 3e-3 at wh <= 128), so the survivors
+    // always contain the exact fp32 arg-min.
+    unsigned keepmask = 0xffffffffu;
+    {
+      const int kp = lane < P ? lane : 0;
+      const int q0 = sm.pptr[kp], n0 = (lane < P) ? sm.lcount[kp] : 0;
+      if (n0 > kNoPrune && n0 <= 32) {
+        float bd = CUDART_INF_F;
+        int bi = 0;
+        for (int v = 0; v < n0; ++v) {
+          const float2 e = *reinterpret_cast<const float2*>(&sm.ent[q0 + v]);
+          const float d = dist2(e.x, e.y, tcx, tcy);
+          if (d < bd) { bd = d; bi = v; }
+        }
+        const float2 e0 = *reinterpret_cast<const float2*>(&sm.ent[q0 + bi]);
+        const float a0 = dist2(e0.x, e0.y, cx0, cy0), a1 = dist2(e0.x, e0.y, cx1, cy0);
+        const float a2 = dist2(e0.x, e0.y, cx0, cy1), a3 = dist2(e0.x, e0.y, cx1, cy1);
+        keepmask = 0u;
+        for (int v = 0; v < n0; ++v) {
+          const float2 e = *reinterpret_cast<const float2*>(&sm.ent[q0 + v]);
+          const bool dominated = dist2(e.x, e.y, cx0, cy0) - a0 >= kPruneMargin && dist2(e.x, e.y, cx1, cy0) - a1 >= kPruneMargin &&
+                                 dist2(e.x, e.y, cx0, cy1) - a2 >= kPruneMargin && dist2(e.x, e.y, cx1, cy1) - a3 >= kPruneMargin;
+          keepmask |= dominated ? 0u : (1u << v);
+        }
+      }
+    }
 
     // channel chunks 1, 2, 3, then chunk 0 last: its channel 0 (background) needs the sum over all parts
     for (int cc = 1; cc <= 4; ++cc) {
@@ -307,22 +342,29 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
         int barg[NB];
 #pragma unroll
         for (int q = 0; q < NB; ++q) { best[q] = kBigD2; barg[q] = -1; }
-#pragma unroll 2
-        for (int v = 0; v < nl; ++v) {
-          const float4 e = sm.ent[p0 + v];                         // same address on every lane: broadcast
-          float du2[BW], dv2[BH], d2[NB];
+        const unsigned pm = __shfl_sync(0xffffffffu, keepmask, ch - 1);   // survivors of this part (lane ch-1 pruned it)
+        for (int cb = 0; cb < nl; cb += 32) {
+          const int cnt = min(32, nl - cb);
+          unsigned m = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+          if (nl <= 32) m &= pm;                                     // parts with more than 32 visible vertices are not pruned
+          while (m) {
+            const int v = cb + __ffs(m) - 1;
+            m &= m - 1;
+            const float2 e = *reinterpret_cast<const float2*>(&sm.ent[p0 + v]);   // same address on every lane: broadcast
+            float du2[BW], dv2[BH], d2[NB];
 #pragma unroll
-          for (int i = 0; i < BW; ++i) { const float d = __fsub_rn(e.x, gxs[i]); du2[i] = __fmul_rn(d, d); }
+            for (int i = 0; i < BW; ++i) { const float d = __fsub_rn(e.x, gxs[i]); du2[i] = __fmul_rn(d, d); }
 #pragma unroll
-          for (int j = 0; j < BH; ++j) { const float d = __fsub_rn(e.y, gys[j]); dv2[j] = __fmul_rn(d, d); }
+            for (int j = 0; j < BH; ++j) { const float d = __fsub_rn(e.y, gys[j]); dv2[j] = __fmul_rn(d, d); }
 #pragma unroll
-          for (int j = 0; j < BH; ++j)
+            for (int j = 0; j < BH; ++j)
 #pragma unroll
-            for (int i = 0; i < BW; ++i) d2[j * BW + i] = __fadd_rn(du2[i], dv2[j]);
+              for (int i = 0; i < BW; ++i) d2[j * BW + i] = __fadd_rn(du2[i], dv2[j]);
 #pragma unroll
-          for (int q = 0; q < NB; ++q) {
-            if (TRACK) barg[q] = (d2[q] < best[q]) ? v : barg[q];
-            best[q] = fminf(best[q], d2[q]);
+            for (int q = 0; q < NB; ++q) {
+              if (TRACK) barg[q] = (d2[q] < best[q]) ? v : barg[q];
+              best[q] = fminf(best[q], d2[q]);
+            }
           }
         }
 #pragma unroll
@@ -409,14 +451,14 @@ __device__ __noinline__ void slow_pixel_grad(const SegSmem& sm, const int* __res
   atomicAdd(&gacc[vid * 2 + 1], coef * dv);
 }
 
-template <int BW, int BH, int LX, bool C32>
+template <int BW, int BH, int LX, bool C32, bool ALLIN>
 __global__ void __launch_bounds__(256, 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
                const int* __restrict__ idx, int P, int E, int wh, int tiles_x, int ntiles,
                float* __restrict__ g_projects) {
   constexpr int LY = 32 / LX, TW = LX * BW, TH = LY * BH, NB = BW * BH;
-  static_assert(LX % kBatch == 0, "a batch must stay inside one lane row");
+  static_assert(LX == 4 && kBatch == 8, "a batch of 8 records = two lane rows of 4 blocks");
   extern __shared__ __align__(16) unsigned char raw[];
   const SegSmem sm = carve(raw, E, wh);
   float* gacc = reinterpret_cast<float*>(sm.rest);                  // [Vs][2]
@@ -438,12 +480,15 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const unsigned char* sv = saved + (size_t)n * plane * 4 + (size_t)(lane >> 3) * plane + (lane & 7);
   const float* g_n = g_seg + (size_t)n * wh * wh * C + (lane < C ? lane : 0);
   const int nrec = ntiles * NB * 32;
-  const bool all_in = (wh % TW == 0) && (wh % TH == 0);             // every record is a pixel of the image
 
+  // Runs of equal arg-min vertices are merged in registers; a run ends with one load/add/store on the lane's private
+  // slot.  Light indices beyond the private capacity (only possible when the sample has more than kAccSlots visible
+  // part vertices) fall back to atomics behind a warp-uniform flag, so the common path carries no such branch.
+  const bool overflow = (sm.lbase[31] + sm.lcount[31]) > kAccSlots;
   int run_li = -1;                                                  // current run: light index within this lane's part
   float run_u = 0.f, run_v = 0.f;
-  auto flush = [&]() {
-    if (run_li < acc_cap) {                                         // private slot: this lane is its only writer
+  auto flush_slow = [&]() {
+    if (run_li < acc_cap) {
       float2 a = wacc[run_li];
       a.x += run_u; a.y += run_v;
       wacc[run_li] = a;
@@ -452,54 +497,71 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
     }
   };
-  // records in the forward's order: id = (tile*NB + b)*32 + l32 ; a batch = kBatch consecutive lanes of one block row
-  for (int base = warp * kBatch; base < nrec; base += nwarps * kBatch) {
+  // Records follow the forward's order, id = (tile*NB + b)*32 + l32, l32 = ly*4 + lx.  Each warp owns a contiguous
+  // range of whole 32-record groups; a batch is 8 records = two lane rows visited in serpentine order (even rows left
+  // to right, odd rows right to left), so consecutive records are neighbouring pixel blocks and runs stay long.
+  struct Batch { int code[kBatch]; float g[kBatch]; int r0, c0; };
+  auto load_batch = [&](int base, Batch& bt) {
     const int l0 = base & 31, tb = base >> 5;
     const int b = tb % NB, t = tb / NB;                             // compile-time divisors
     const int ty = (tiles_x == 1) ? t : t / tiles_x, tx = t - ty * tiles_x;
-    const int r = ty * TH + (l0 / LX) * BH + b / BW;
-    const int cb = tx * TW + (l0 % LX) * BW + b % BW;               // column of the batch's first record; +BW per record
-    const bool row_in = all_in || r < wh;
-    const float* grow = g_n + ((wh - 1 - r) * wh + cb) * C;         // rows flipped (:68)
+    bt.r0 = ty * TH + (l0 >> 2) * BH + b / BW;                      // first lane row of the batch; the second is +BH
+    bt.c0 = tx * TW + b % BW;                                       // lx = 0 ; +BW per lane column
     const unsigned char* srow = sv + (size_t)base * 8;
-    int code[kBatch];
-    float g[kBatch];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {                              // issue the whole batch of loads first
-      const bool in = row_in && (all_in || (cb + j * BW) < wh);
-      code[j] = in ? (int)srow[j * 8] : 0;
-      g[j] = (in && (C32 || lane < C)) ? grow[j * BW * C] : 0.f;
-    }
-    const float gy = (float)r, gxb = (float)cb;
+    const float* grow = g_n + ((wh - 1 - bt.r0) * wh + bt.c0) * C;  // rows flipped (:68): next lane row is -BH*wh*C
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {
-      const int gate = __shfl_sync(0xffffffffu, code[j], 0);
-      const float g0 = __shfl_sync(0xffffffffu, g[j], 0);
-      const float G = g[j] - ((gate & 1) ? g0 : 0.f);               // d bg / d s_k = -gate
-      const float gx = gxb + (float)(j * BW);
-      int li = live ? code[j] - 1 : -1;                             // 0 -> -1 none
-      float cu = 0.f, cv = 0.f;
-      if (li == 254) {                                              // code 255: rare exact re-query, atomics
-        slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gx, gy, sm.head[r * wh + cb + j * BW], ghead, G);
-        li = -1;
-      } else if (li >= 0) {
-        const float4 e = ent_k[li];                                 // light entry: w == 1
-        const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
-        const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
-        const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
-        const float s = ex2_approx((d2 * rs) * (-kLog2e));
-        const float coef = -(s * G) * rs;                           // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
-        cu = coef * du; cv = coef * dv;
-      }
-      if (li != run_li) {
-        if (run_li >= 0) flush();
-        run_li = li; run_u = cu; run_v = cv;
-      } else {
-        run_u += cu; run_v += cv;
-      }
+      const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);  // serpentine
+      const bool in = ALLIN || (bt.r0 + ly * BH < wh && bt.c0 + lx * BW < wh);
+      bt.code[j] = in ? (int)srow[(ly * 4 + lx) * 8] : 0;
+      bt.g[j] = (in && (C32 || lane < C)) ? grow[(lx * BW - ly * BH * wh) * C] : 0.f;
     }
+  };
+  const int ngroups = nrec >> 5;
+  const int grp0 = (int)(((long long)ngroups * warp) / nwarps), grp1 = (int)(((long long)ngroups * (warp + 1)) / nwarps);
+  const int rec_end = grp1 * 32;
+  Batch cur, nxt;
+  int base = grp0 * 32;
+  if (base < rec_end) load_batch(base, cur);
+  for (; base < rec_end; base += kBatch) {
+    if (base + kBatch < rec_end) load_batch(base + kBatch, nxt);    // next batch's loads fly while this one is consumed
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);
+      const int gate = __shfl_sync(0xffffffffu, cur.code[j], 0);
+      const float g0 = __shfl_sync(0xffffffffu, cur.g[j], 0);
+      const float G = cur.g[j] - ((gate & 1) ? g0 : 0.f);           // d bg / d s_k = -gate
+      const float gx = (float)(cur.c0 + lx * BW), gy = (float)(cur.r0 + ly * BH);
+      int li = live ? cur.code[j] - 1 : -1;                         // 0 -> -1 none
+      if (li == 254) {                                              // code 255: rare exact re-query, atomics
+        slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gx, gy, sm.head[(cur.r0 + ly * BH) * wh + cur.c0 + lx * BW], ghead, G);
+        li = -1;
+      }
+      // light entry (w == 1); lanes without a vertex read slot 0 and contribute zero
+      const float2 e = *reinterpret_cast<const float2*>(&ent_k[li < 0 ? 0 : li]);
+      const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+      const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+      const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
+      const float s = ex2_approx((d2 * rs) * (-kLog2e));
+      const float coef = (li < 0) ? 0.f : -(s * G) * rs;            // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
+      const float cu = coef * du, cv = coef * dv;
+      const bool brk = li != run_li;
+      if (brk && run_li >= 0) {
+        if (!overflow) {                                            // private slot: this lane is its only writer
+          float2 a = wacc[run_li];
+          a.x += run_u; a.y += run_v;
+          wacc[run_li] = a;
+        } else {
+          flush_slow();
+        }
+      }
+      run_u = brk ? cu : run_u + cu;
+      run_v = brk ? cv : run_v + cv;
+      run_li = li;
+    }
+    cur = nxt;
   }
-  if (run_li >= 0) flush();
+  if (run_li >= 0) flush_slow();
   __syncthreads();
   // fold the warps' private slots into the per-vertex sums (a vertex may sit in more than one part)
   const int nlight = min(sm.lbase[31] + sm.lcount[31], kAccSlots);
@@ -562,8 +624,8 @@ size_t seg_saved_bytes(int N, int wh) {
 
 cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
                            float* seg, unsigned char* saved, cudaStream_t st) {
-  if (wh % 48 == 0) return launch_fwd_cfg<3, 2, 16>(p, projects, mask, N, Vs, wh, seg, saved, st);
-  return launch_fwd_cfg<4, 2, 16>(p, projects, mask, N, Vs, wh, seg, saved, st);
+  if (wh % 12 == 0) return launch_fwd_cfg<3, 2, 4>(p, projects, mask, N, Vs, wh, seg, saved, st);
+  return launch_fwd_cfg<4, 2, 4>(p, projects, mask, N, Vs, wh, seg, saved, st);
 }
 
 cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
@@ -573,16 +635,25 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   const SegGeom g = seg_geom(wh);
   LaunchScope scope(KID_SEG_BWD, st);
-#define SMPL_SEG_BWD(BW, BH, LX, C32)                                                                                  \
+#define SMPL_SEG_BWD(BW, BH, LX, C32, ALLIN)                                                                           \
   do {                                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<BW, BH, LX, C32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<BW, BH, LX, C32, ALLIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    seg_bwd_kernel<BW, BH, LX, C32><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx,  \
-                                                                 p->P, p->E, wh, g.tiles_x, g.ntiles, g_projects);     \
+    seg_bwd_kernel<BW, BH, LX, C32, ALLIN><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr,    \
+                                                                        p->idx, p->P, p->E, wh, g.tiles_x, g.ntiles,    \
+                                                                        g_projects);                                   \
   } while (0)
   const bool c32 = p->P == 31;
-  if (wh % 48 == 0) { if (c32) SMPL_SEG_BWD(3, 2, 16, true); else SMPL_SEG_BWD(3, 2, 16, false); }
-  else { if (c32) SMPL_SEG_BWD(4, 2, 16, true); else SMPL_SEG_BWD(4, 2, 16, false); }
+  const bool allin = (wh % g.TW == 0) && (wh % g.TH == 0);          // every record is a pixel of the image
+  if (wh % 12 == 0) {
+    if (c32 && allin) SMPL_SEG_BWD(3, 2, 4, true, true);
+    else if (c32) SMPL_SEG_BWD(3, 2, 4, true, false);
+    else SMPL_SEG_BWD(3, 2, 4, false, false);
+  } else {
+    if (c32 && allin) SMPL_SEG_BWD(4, 2, 4, true, true);
+    else if (c32) SMPL_SEG_BWD(4, 2, 4, true, false);
+    else SMPL_SEG_BWD(4, 2, 4, false, false);
+  }
 #undef SMPL_SEG_BWD
   return cudaGetLastError();
 }
