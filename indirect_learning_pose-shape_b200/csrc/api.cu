@@ -498,7 +498,7 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!m || !params || !v_posed_save || !g_params || N < 0) { set_error("decode_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   const int vs_in = vertex_sampling < 1 ? 1 : vertex_sampling;
-  const bool full = (g_verts != nullptr) || !g_projects;     // dense vertex gradient (or none at all)
+  const bool full = (g_verts != nullptr) || !g_projects;     // dense vertex gradient (or none at all): every vertex
   const int vs_t = full ? 1 : vs_in;
   const VsTables* t = get_vs_tables(m, vs_t);
   if (!t) return SMPL_B200_ERR_CUDA;

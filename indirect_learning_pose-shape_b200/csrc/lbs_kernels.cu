@@ -254,7 +254,7 @@ lbs_bwd_joint_kernel(const float* __restrict__ vp, int LD, const float* __restri
 //           v_posed of the sampled vertices are parked in shared memory;
 //   phase 2 (warp = joint, 3 joints per warp): g_A[j] = sum_{v in joint j} w_vj g_vert_v (x) [v_posed_v; 1] from shared
 //           memory through the joint's CSC list, warp-reduced: no atomics, deterministic.
-template <int KW>
+template <int KW, bool STAGE>
 __global__ void __launch_bounds__(256)
 lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A,
                        const float* __restrict__ params, int N, int vs, int Vs, const uint8_t* __restrict__ sidx,
@@ -264,8 +264,8 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
                        float* __restrict__ g_A, float* __restrict__ g_cam) {
   extern __shared__ __align__(16) float sm[];
   float* As = sm;                         // [24][12]
-  float* sg = As + kARow;                 // [Vs][3] gradient at the sampled vertices
-  float* sp = sg + Vs * 3;                // [Vs][3] their rest-pose positions
+  float* sg = As + kARow;                 // [Vs][3] gradient at the sampled vertices   (STAGE only; otherwise phase 2
+  float* sp = sg + Vs * 3;                // [Vs][3] their rest-pose positions           re-reads them through L1/L2)
   __shared__ float red[8][4];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kARow / 4; i += blockDim.x)
@@ -296,8 +296,10 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
     const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
     const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
     c4[0] = fmaf(gu, ox, c4[0]); c4[1] = fmaf(gv, oy, c4[1]); c4[2] += gu; c4[3] += gv;
-    sg[q * 3] = gx; sg[q * 3 + 1] = gy; sg[q * 3 + 2] = gz;
-    sp[q * 3] = x; sp[q * 3 + 1] = y; sp[q * 3 + 2] = z;
+    if (STAGE) {
+      sg[q * 3] = gx; sg[q * 3 + 1] = gy; sg[q * 3 + 2] = gz;
+      sp[q * 3] = x; sp[q * 3 + 1] = y; sp[q * 3 + 2] = z;
+    }
   }
   for (int c = Vs * 3 + tid; c < Kp; c += blockDim.x) {           // zero the K padding the blend backward reads
     orow[c] = 0.f;
@@ -323,8 +325,14 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
     for (int e = csc_ptr[j] + lane; e < e1; e += 32) {
       const int q = csc_q[e];
       const float w = csc_w[e];
-      const float gx = sg[q * 3] * w, gy = sg[q * 3 + 1] * w, gz = sg[q * 3 + 2] * w;
-      const float x = sp[q * 3], y = sp[q * 3 + 1], z = sp[q * 3 + 2];
+      float gx, gy, gz, x, y, z;
+      if (STAGE) {
+        gx = sg[q * 3] * w; gy = sg[q * 3 + 1] * w; gz = sg[q * 3 + 2] * w;
+        x = sp[q * 3]; y = sp[q * 3 + 1]; z = sp[q * 3 + 2];
+      } else {
+        gx = gp[q * 3] * ku * w; gy = gp[q * 3 + 1] * kv * w; gz = gp[q * 3 + 2] * w;
+        x = vrow[(size_t)q * vs * 3]; y = vrow[(size_t)q * vs * 3 + 1]; z = vrow[(size_t)q * vs * 3 + 2];
+      }
       acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
       acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
       acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
@@ -434,22 +442,23 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
                            float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, int* cam_chunks,
                            cudaStream_t st) {
   const int V = m->V, Vp = t->Vs, Vs_proj = (V + vs_proj - 1) / vs_proj;
-  if (t->vs > 1 && !g_verts && g_projects && t->vs == vs_proj) {
-    // sampled backward: one fused kernel, one block per sample
-    const size_t smem = (size_t)(kARow + 6 * Vp) * sizeof(float);
+  if (!g_verts && g_projects && t->vs == vs_proj) {
+    // gradient arrives through the projection only: one fused kernel, one block per sample
+    const bool stage = (size_t)6 * Vp * sizeof(float) <= 48 * 1024;   // park g_vert / v_posed in smem only when small
+    const size_t smem = (size_t)(kARow + (stage ? 6 * Vp : 0)) * sizeof(float);
     LaunchScope scope(KID_LBS_BWD_VERTEX, st);
     *cam_chunks = 1;
-#define SMPL_LBS_BWD_S(KW)                                                                                          \
+#define SMPL_LBS_BWD_S(KW, ST)                                                                                      \
   do {                                                                                                             \
-    cudaError_t e = cudaFuncSetAttribute(lbs_bwd_sampled_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(lbs_bwd_sampled_kernel<KW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                \
-    lbs_bwd_sampled_kernel<KW><<<N, 256, smem, st>>>(v_posed, m->LD, A, params, N, t->vs, Vp, t->lbs_idx_s, t->lbs_w_s, \
-                                                     t->csc_ptr, t->csc_q, t->csc_w, g_projects, g_vp, g_vp_lo,      \
-                                                     (int)gvp_ld, t->Kp, g_A, g_cam);                              \
+    lbs_bwd_sampled_kernel<KW, ST><<<N, 256, smem, st>>>(v_posed, m->LD, A, params, N, t->vs, Vp, t->lbs_idx_s,      \
+                                                         t->lbs_w_s, t->csc_ptr, t->csc_q, t->csc_w, g_projects, g_vp, \
+                                                         g_vp_lo, (int)gvp_ld, t->Kp, g_A, g_cam);                  \
   } while (0)
-    if (m->KW == 4) SMPL_LBS_BWD_S(4);
-    else if (m->KW == 8) SMPL_LBS_BWD_S(8);
-    else SMPL_LBS_BWD_S(24);
+    if (m->KW == 4) { if (stage) SMPL_LBS_BWD_S(4, true); else SMPL_LBS_BWD_S(4, false); }
+    else if (m->KW == 8) { if (stage) SMPL_LBS_BWD_S(8, true); else SMPL_LBS_BWD_S(8, false); }
+    else { if (stage) SMPL_LBS_BWD_S(24, true); else SMPL_LBS_BWD_S(24, false); }
 #undef SMPL_LBS_BWD_S
     return cudaGetLastError();
   }

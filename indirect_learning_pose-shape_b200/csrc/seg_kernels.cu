@@ -594,7 +594,7 @@ cudaError_t launch_fwd_cfg(const SmplB200Parts* p, const float* projects, const 
   int split = 1;
   if (N < 2 * 148) {
     split = max(1, min(g.ntiles, (2 * 148 + N - 1) / N));
-    warps = max(1, min(warps, (g.ntiles + split - 1) / split));
+    warps = 8;     // every block re-classifies the sample's vertices: keep 8 warps for that even if it owns few tiles
   }
   const size_t smem = seg_base_smem(p->E, wh) + (size_t)warps * 8 * g.NB * 32 * 4;
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
