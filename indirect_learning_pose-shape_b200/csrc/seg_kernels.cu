@@ -241,6 +241,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
+// explicit shared-window accesses (a generic pointer into dynamic smem makes the compiler rebuild the window base)
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
 // saved layout: 4 planes (channels 8q..8q+7); plane q holds, for record id = (tile*NB + b)*32 + lane, 8 bytes.
 // byte of channel 0: bit 0 = clip gate.  byte of channel 1+k: 0 none, 1..254 light index + 1, 255 re-query.
 template <int BW, int BH, int LX, bool TRACK>
@@ -475,6 +485,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int p0 = sm.pptr[k], p1 = sm.pptr[k + 1], nl = sm.lcount[k];
   const float4* ent_k = sm.ent + p0;
   float2* wacc = wacc_all + (size_t)warp * kAccSlots + sm.lbase[k]; // this lane's part, private to (warp, lane)
+  const uint32_t ent_sa = (uint32_t)__cvta_generic_to_shared(ent_k);   // shared-window addresses of the two hot arrays
+  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(wacc);
   const int acc_cap = kAccSlots - sm.lbase[k];                      // light indices >= acc_cap overflow to atomics
   const size_t plane = (size_t)ntiles * NB * 32 * 8;
   const unsigned char* sv = saved + (size_t)n * plane * 4 + (size_t)(lane >> 3) * plane + (lane & 7);
@@ -525,39 +537,63 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   if (base < rec_end) load_batch(base, cur);
   for (; base < rec_end; base += kBatch) {
     if (base + kBatch < rec_end) load_batch(base + kBatch, nxt);    // next batch's loads fly while this one is consumed
+    const float gxb = (float)cur.c0, gyb = (float)cur.r0;
+    unsigned slowmask = 0u;
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);
-      const int gate = __shfl_sync(0xffffffffu, cur.code[j], 0);
-      const float g0 = __shfl_sync(0xffffffffu, cur.g[j], 0);
-      const float G = cur.g[j] - ((gate & 1) ? g0 : 0.f);           // d bg / d s_k = -gate
-      const float gx = (float)(cur.c0 + lx * BW), gy = (float)(cur.r0 + ly * BH);
-      int li = live ? cur.code[j] - 1 : -1;                         // 0 -> -1 none
-      if (li == 254) {                                              // code 255: rare exact re-query, atomics
-        slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gx, gy, sm.head[(cur.r0 + ly * BH) * wh + cur.c0 + lx * BW], ghead, G);
-        li = -1;
+    for (int h = 0; h < kBatch; h += 4) {
+      // (a) four records at a time, branch-free and mutually independent: the compiler interleaves the four chains
+      int li4[4];
+      float cu4[4], cv4[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = h + jj;
+        const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);
+        const int gate = __shfl_sync(0xffffffffu, cur.code[j], 0);
+        const float g0 = __shfl_sync(0xffffffffu, cur.g[j], 0);
+        const float G = cur.g[j] - ((gate & 1) ? g0 : 0.f);         // d bg / d s_k = -gate
+        const float gx = gxb + (float)(lx * BW), gy = gyb + (float)(ly * BH);   // small integers: exact in fp32
+        int li = live ? cur.code[j] - 1 : -1;                       // 0 -> -1 none
+        if (li == 254) { slowmask |= 1u << j; li = -1; }            // code 255: rare exact re-query, deferred
+        // light entry (w == 1); lanes without a vertex read slot 0 and contribute zero
+        const float2 e = lds_f2(ent_sa + (uint32_t)(li < 0 ? 0 : li) * 16u);
+        const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+        const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+        const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
+        const float s = ex2_approx((d2 * rs) * (-kLog2e));
+        const float coef = (li < 0) ? 0.f : -(s * G) * rs;          // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
+        li4[jj] = li; cu4[jj] = coef * du; cv4[jj] = coef * dv;
       }
-      // light entry (w == 1); lanes without a vertex read slot 0 and contribute zero
-      const float2 e = *reinterpret_cast<const float2*>(&ent_k[li < 0 ? 0 : li]);
-      const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
-      const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
-      const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
-      const float s = ex2_approx((d2 * rs) * (-kLog2e));
-      const float coef = (li < 0) ? 0.f : -(s * G) * rs;            // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
-      const float cu = coef * du, cv = coef * dv;
-      const bool brk = li != run_li;
-      if (brk && run_li >= 0) {
-        if (!overflow) {                                            // private slot: this lane is its only writer
-          float2 a = wacc[run_li];
-          a.x += run_u; a.y += run_v;
-          wacc[run_li] = a;
-        } else {
-          flush_slow();
+      // (b) sequential run merge over the four results
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const bool brk = li4[jj] != run_li;
+        if (brk && run_li >= 0) {
+          if (!overflow) {                                          // private slot: this lane is its only writer
+            const uint32_t a_sa = wacc_sa + (uint32_t)run_li * 8u;
+            float2 a = lds_f2(a_sa);
+            a.x += run_u; a.y += run_v;
+            sts_f2(a_sa, a);
+          } else {
+            flush_slow();
+          }
+        }
+        run_u = brk ? cu4[jj] : run_u + cu4[jj];
+        run_v = brk ? cv4[jj] : run_v + cv4[jj];
+        run_li = li4[jj];
+      }
+    }
+    if (__any_sync(0xffffffffu, slowmask != 0u)) {                  // rare: heavy / generic winners, exact, atomics
+#pragma unroll 1
+      for (int j = 0; j < kBatch; ++j) {                            // warp-uniform loop: every lane takes the shuffles
+        const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);
+        const int gate = __shfl_sync(0xffffffffu, cur.code[j], 0);
+        const float g0 = __shfl_sync(0xffffffffu, cur.g[j], 0);
+        if ((slowmask >> j) & 1u) {
+          const float G = cur.g[j] - ((gate & 1) ? g0 : 0.f);
+          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gxb + (float)(lx * BW), gyb + (float)(ly * BH),
+                          sm.head[(cur.r0 + ly * BH) * wh + cur.c0 + lx * BW], ghead, G);
         }
       }
-      run_u = brk ? cu : run_u + cu;
-      run_v = brk ? cv : run_v + cv;
-      run_li = li;
     }
     cur = nxt;
   }
