@@ -63,6 +63,16 @@ __device__ __forceinline__ void load_group_A(float* As, float* cam, const float*
   if (threadIdx.x < rows * 4) cam[threadIdx.x] = params[(size_t)(n0 + (threadIdx.x >> 2)) * kParams + (threadIdx.x & 3)];
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kLbsStages = 4;   // v_posed slices in flight per block (cp.async ring)
+
 template <int KW>
 __global__ void __launch_bounds__(kChunk)
 lbs_fwd_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A, const float* __restrict__ params,
@@ -70,27 +80,31 @@ lbs_fwd_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A
                float* __restrict__ verts, float* __restrict__ projects, int vs, int Vs) {
   __shared__ __align__(16) float As[kGroup * kARow];
   __shared__ float cam[kGroup * 4];
-  __shared__ __align__(16) float stage[2][kChunk * 3];
+  __shared__ __align__(16) float stage[kLbsStages][kChunk * 3];
   const int tid = threadIdx.x;
   const int n0 = blockIdx.y * kGroup;
   const int rows = min(kGroup, N - n0);
   const int v = blockIdx.x * kChunk + tid;
   const bool valid = v < V;
   const int col0 = blockIdx.x * kChunk * 3;
+  // the group's v_posed slices stream through a cp.async ring: kLbsStages x 3 KB in flight per block, no register staging
+  auto issue = [&](int s) {
+    if (s < rows && tid < kChunk * 3 / 4) cp_async16(&stage[s % kLbsStages][tid * 4], vp + (size_t)(n0 + s) * LD + col0 + tid * 4);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kLbsStages - 1; ++s) issue(s);
   load_group_A(As, cam, A, params, n0, rows);
   const Skin<KW> skin = load_skin<KW>(lbs_idx, lbs_w, valid ? v : 0);
   const bool sampled = valid && projects && (v % vs == 0);
   const bool need = valid && (verts || sampled);
   const int q = v / vs;
-  if (tid < kChunk * 3 / 4)
-    reinterpret_cast<float4*>(stage[0])[tid] = *reinterpret_cast<const float4*>(vp + (size_t)n0 * LD + col0 + tid * 4);
-  __syncthreads();
   for (int s = 0; s < rows; ++s) {
     const int n = n0 + s;
-    float* st = stage[s & 1];
-    if (s + 1 < rows && tid < kChunk * 3 / 4)     // prefetch the next sample's slice into the other buffer
-      reinterpret_cast<float4*>(stage[(s + 1) & 1])[tid] =
-          *reinterpret_cast<const float4*>(vp + (size_t)(n + 1) * LD + col0 + tid * 4);
+    issue(s + kLbsStages - 1);                     // keeps kLbsStages-1 slices in flight behind the one consumed now
+    cp_async_wait<kLbsStages - 1>();               // slice s has landed (for this thread's copies) ...
+    __syncthreads();                               // ... and for everyone's; also publishes As/cam on the first pass
+    float* st = stage[s % kLbsStages];
     if (need) {
       const float x = st[tid * 3], y = st[tid * 3 + 1], z = st[tid * 3 + 2];
       float T[12];
@@ -113,7 +127,7 @@ lbs_fwd_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A
       for (int i = tid; i < kChunk * 3 / 2; i += kChunk)
         if (i < lim) dst[i] = reinterpret_cast<const float2*>(st)[i];
     }
-    __syncthreads();
+    __syncthreads();                               // the next iteration's issue() overwrites the slot consumed before this one
   }
 }
 
