@@ -271,6 +271,42 @@ def test_seg_backward_weighted_and_gate(pkg, parts_by_vs):
     assert bad.mean() <= 2e-3, (bad.mean(), np.abs(got - ref64).max(), scale)
 
 
+def test_seg_all_visible_full_resolution(pkg, host_model, parts_by_vs, make_params):
+    """mask == 1 everywhere at full resolution: parts hold hundreds of light vertices, which exercises the un-pruned
+    chunk loop (> 32 per part), arg-min indices that do not fit the saved byte (>= 254 -> re-query in the backward)
+    and the backward's accumulator overflow path (> 512 light vertices per sample -> atomics)."""
+    n, wh, vs = 1, 48, None
+    p, pr, _ = _oracle_inputs(host_model, make_params, n, wh, vs, seed=91)
+    mask = np.ones(pr.shape[:2], np.float32)
+    g = np.random.default_rng(6).standard_normal((n, wh, wh, 32)).astype(np.float32)
+    ref = np_oracle.projects_to_seg([pr, mask], wh, vs, parts_by_vs[vs])
+    ref64 = _seg_grad_oracle(pr, mask, wh, vs, parts_by_vs[vs], g, torch.float64)
+    x = t(pr).requires_grad_(True)
+    out = pkg.projects_to_seg([x, t(mask)], wh, vs, parts=parts_by_vs[vs])
+    got = out.detach().cpu().numpy()
+    assert np.abs(got - ref).max() <= TOL_SCORE
+    assert (_labels(got) != _labels(ref)).mean() <= LABEL_MISMATCH_MAX
+    (out * t(g)).sum().backward()
+    gg = x.grad.cpu().numpy().astype(np.float64)
+    scale = np.abs(ref64).max() + 1e-9
+    bad = np.abs(gg - ref64) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(gg - ref64).max(), scale)
+
+
+@pytest.mark.parametrize("n", [64, 130])
+def test_full_path_dense_batch(pkg, host_model, parts_by_vs, make_params, n):
+    """Batches >= 64 take the tensor-core (tcgen05, 3xTF32) blend path; same tolerances as the small-batch path."""
+    wh, vs = 48, 5
+    p = make_params(n, wh, seed=101)
+    ref = np_oracle.decode(host_model, p, wh, vs, parts_by_vs[vs])
+    dec = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev())
+    out = dec(t(p))
+    assert np.abs(out["verts"].cpu().numpy() - ref["verts"]).max() <= TOL_GEOM
+    assert np.abs(out["joints"].cpu().numpy() - ref["J_transformed"]).max() <= TOL_GEOM
+    assert np.abs(out["projects"].cpu().numpy() - ref["projects"]).max() <= 2.5 * TOL_GEOM   # see test_projection
+    assert (_labels(out["seg"].cpu().numpy()) != _labels(ref["seg"])).mean() <= 5e-3
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # silhouette
 # ---------------------------------------------------------------------------------------------------------------
