@@ -30,7 +30,7 @@ __device__ __forceinline__ int cell_of(float u, float v) {
   return (int)pv * kMaskGrid + (int)pu;        // column = u, row = v (meshgrid 'xy', :49-54)
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict__ mask) {
   __shared__ unsigned int zmax[kCells];        // 0 = empty (orderable() never returns 0 for a non-NaN float)
   __shared__ unsigned int win[kCells];
@@ -69,7 +69,7 @@ mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict
 
 cudaError_t launch_mask_fwd(const float* projects, int N, int Vs, float* mask, cudaStream_t st) {
   LaunchScope scope(KID_MASK, st);
-  mask_kernel<<<N, 256, 0, st>>>(projects, N, Vs, mask);
+  mask_kernel<<<N, N < 64 ? 1024 : 256, 0, st>>>(projects, N, Vs, mask);   // few samples: spend threads on each
   return cudaGetLastError();
 }
 

@@ -94,29 +94,45 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
   for (int k = warp; k < P; k += nwarps) {
     const int p0 = ptr[k], p1 = ptr[k + 1];
     int nl = 0, no = 0;
-    for (int base = p0; base < p1; base += 32) {
-      const int e = base + lane;
-      const bool in = e < p1;
-      float u = 0.f, v = 0.f, w = 0.f;
-      int vid = 0;
-      if (in) {
-        vid = idx[e];
-        u = proj[vid * 3]; v = proj[vid * 3 + 1]; w = mask[vid];
+    constexpr int kU = 4;                                // chunks of 32 entries whose gather chains overlap
+    for (int base0 = p0; base0 < p1; base0 += 32 * kU) {
+      int vids[kU];
+      float us[kU], vv[kU], ws[kU];
+#pragma unroll
+      for (int c = 0; c < kU; ++c) {                     // idx -> (proj, mask) is a dependent chain: issue kU of them
+        const int e = base0 + c * 32 + lane;
+        vids[c] = (e < p1) ? idx[e] : 0;
       }
-      const bool light = in && (w == 1.0f);
-      const bool other = in && !light;
-      const unsigned bl = __ballot_sync(0xffffffffu, light), bo = __ballot_sync(0xffffffffu, other);
-      const unsigned lt = (1u << lane) - 1u;
-      if (light) sm.ent[p0 + nl + __popc(bl & lt)] = make_float4(u, v, 1.0f, __int_as_float(vid));
-      if (other) {
-        const int slot = p1 - 1 - (no + __popc(bo & lt));
-        unsigned next = kNone16;
-        // heavy entries are linked in a second pass (below), once the part's light list is complete
-        if (!(w >= kHeavyMin)) next = (unsigned)atomicExch(sm.ghead, slot) & 0xffffu;
-        sm.ent[slot] = make_float4(u, v, w, __uint_as_float(((unsigned)e & 0xffffu) | (next << 16)));
+#pragma unroll
+      for (int c = 0; c < kU; ++c) {
+        const bool in = base0 + c * 32 + lane < p1;
+        us[c] = in ? proj[vids[c] * 3] : 0.f;
+        vv[c] = in ? proj[vids[c] * 3 + 1] : 0.f;
+        ws[c] = in ? mask[vids[c]] : 0.f;
       }
-      nl += __popc(bl);
-      no += __popc(bo);
+#pragma unroll
+      for (int c = 0; c < kU; ++c) {
+        const int base = base0 + c * 32;
+        if (base >= p1) break;
+        const int e = base + lane;
+        const bool in = e < p1;
+        const float u = us[c], v = vv[c], w = ws[c];
+        const int vid = vids[c];
+        const bool light = in && (w == 1.0f);
+        const bool other = in && !light;
+        const unsigned bl = __ballot_sync(0xffffffffu, light), bo = __ballot_sync(0xffffffffu, other);
+        const unsigned lt = (1u << lane) - 1u;
+        if (light) sm.ent[p0 + nl + __popc(bl & lt)] = make_float4(u, v, 1.0f, __int_as_float(vid));
+        if (other) {
+          const int slot = p1 - 1 - (no + __popc(bo & lt));
+          unsigned next = kNone16;
+          // heavy entries are linked in a second pass (below), once the part's light list is complete
+          if (!(w >= kHeavyMin)) next = (unsigned)atomicExch(sm.ghead, slot) & 0xffffu;
+          sm.ent[slot] = make_float4(u, v, w, __uint_as_float(((unsigned)e & 0xffffu) | (next << 16)));
+        }
+        nl += __popc(bl);
+        no += __popc(bo);
+      }
     }
     if (lane == 0) sm.lcount[k] = nl;
     __syncwarp();
