@@ -1,0 +1,98 @@
+"""C-ABI calls on raw device pointers with guard bands around every output and workspace buffer: any out-of-bounds
+global write by a kernel shows up as a damaged sentinel (compute-sanitizer is not available on this pool)."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle
+
+pytestmark = pytest.mark.gpu
+GUARD = 4096          # bytes on each side
+SENT = 0xA5
+
+
+class Guarded:
+    def __init__(self, nbytes, dev):
+        self.n = int(nbytes)
+        pad = (-self.n) % 256
+        self.buf = torch.full((GUARD + self.n + pad + GUARD,), SENT, dtype=torch.uint8, device=dev)
+        self.pad = pad
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + GUARD)
+
+    def view(self, dtype, shape):
+        return self.buf[GUARD:GUARD + self.n].view(dtype).view(shape)
+
+    def intact(self):
+        lo = self.buf[:GUARD]
+        hi = self.buf[GUARD + self.n:]
+        return bool((lo == SENT).all().item()) and bool((hi == SENT).all().item())
+
+
+@pytest.mark.parametrize("n,vs,wh", [(3, 5, 48), (65, 5, 48), (2, 1, 64), (1, 2, 33)])
+def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
+    lib = pkg.load_library()
+    binding = importlib.import_module("indirect_learning_pose-shape_b200._lib")
+    layers = importlib.import_module("indirect_learning_pose-shape_b200.layers")
+    dev = torch.device("cuda", 0)
+    dm = layers.get_device_model(host_model, dev)
+    V, LD = dm.V, dm.LD
+    Vs = -(-V // vs)
+    vsk = None if vs == 1 else vs
+    table = layers.get_part_table(vsk, Vs, dev, parts=parts_by_vs[vsk])
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p_np = make_params(n, wh, seed=7)
+    params = Guarded(n * 86 * 4, dev)
+    params.view(torch.float32, (n, 86)).copy_(torch.from_numpy(p_np))
+    verts, joints = Guarded(n * V * 12, dev), Guarded(n * 24 * 12, dev)
+    vposed, proj = Guarded(n * LD * 4, dev), Guarded(n * Vs * 12, dev)
+    ws_f = Guarded(dm.workspace_bytes(binding.OP_DECODE_FWD, n), dev)
+    binding.check(lib.smpl_b200_decode_fwd(dm.handle, params.ptr, n, verts.ptr, joints.ptr, None, 0, vposed.ptr, proj.ptr, vs,
+                                           ws_f.ptr, ws_f.n, stream), "decode_fwd")
+    mask = Guarded(n * Vs * 4, dev)
+    binding.check(lib.smpl_b200_mask_fwd(proj.ptr, n, Vs, mask.ptr, stream), "mask_fwd")
+    seg = Guarded(n * wh * wh * 32 * 4, dev)
+    saved = Guarded(lib.smpl_b200_seg_saved_bytes(n, wh), dev)
+    binding.check(lib.smpl_b200_seg_fwd(table.handle, proj.ptr, mask.ptr, n, Vs, wh, seg.ptr, saved.ptr, stream), "seg_fwd")
+    g_seg = Guarded(n * wh * wh * 32 * 4, dev)
+    g_seg.view(torch.float32, (n, wh, wh, 32)).normal_()
+    g_proj = Guarded(n * Vs * 12, dev)
+    binding.check(lib.smpl_b200_seg_bwd(table.handle, proj.ptr, mask.ptr, g_seg.ptr, saved.ptr, n, Vs, wh, g_proj.ptr, stream),
+                  "seg_bwd")
+    sil, g_sil, g_proj2 = Guarded(n * wh * wh * 8, dev), Guarded(n * wh * wh * 8, dev), Guarded(n * Vs * 12, dev)
+    g_sil.view(torch.float32, (n, wh, wh, 2)).normal_()
+    binding.check(lib.smpl_b200_silhouette_fwd(proj.ptr, n, Vs, wh, sil.ptr, None, 0, stream), "sil_fwd")
+    binding.check(lib.smpl_b200_silhouette_bwd(proj.ptr, g_sil.ptr, n, Vs, wh, g_proj2.ptr, None, 0, stream), "sil_bwd")
+    g_params = Guarded(n * 86 * 4, dev)
+    ws_b = Guarded(dm.workspace_bytes(binding.OP_DECODE_BWD, n, 0, vs), dev)
+    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, None, g_proj.ptr, vs, None, g_params.ptr,
+                                           ws_b.ptr, ws_b.n, stream), "decode_bwd")
+    # dense-gradient variant (g_verts given) needs the full-size workspace
+    g_verts = Guarded(n * V * 12, dev)
+    g_verts.view(torch.float32, (n, V, 3)).normal_()
+    g_params2 = Guarded(n * 86 * 4, dev)
+    ws_b2 = Guarded(dm.workspace_bytes(binding.OP_DECODE_BWD, n, 0, 1), dev)
+    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, g_verts.ptr, g_proj.ptr, vs, None,
+                                           g_params2.ptr, ws_b2.ptr, ws_b2.n, stream), "decode_bwd dense")
+    # stand-alone projection
+    proj_s, g_verts_s, g_params_s = Guarded(n * Vs * 12, dev), Guarded(n * V * 12, dev), Guarded(n * 86 * 4, dev)
+    binding.check(lib.smpl_b200_project_fwd(verts.ptr, params.ptr, n, V, vs, proj_s.ptr, stream), "project_fwd")
+    binding.check(lib.smpl_b200_project_bwd(verts.ptr, params.ptr, g_proj.ptr, n, V, vs, g_verts_s.ptr, g_params_s.ptr, stream),
+                  "project_bwd")
+    torch.cuda.synchronize()
+    for name, g in dict(params=params, verts=verts, joints=joints, vposed=vposed, proj=proj, ws_f=ws_f, mask=mask, seg=seg,
+                        saved=saved, g_seg=g_seg, g_proj=g_proj, sil=sil, g_sil=g_sil, g_proj2=g_proj2, g_params=g_params,
+                        ws_b=ws_b, g_verts=g_verts, g_params2=g_params2, ws_b2=ws_b2, proj_s=proj_s, g_verts_s=g_verts_s,
+                        g_params_s=g_params_s).items():
+        assert g.intact(), "guard band damaged around %s" % name
+    # and the results are the real thing
+    ref = np_oracle.smpl_layer_call(host_model, p_np)
+    assert np.abs(verts.view(torch.float32, (n, V, 3)).cpu().numpy() - ref).max() <= 1e-5
+    assert np.array_equal(proj.view(torch.float32, (n, Vs, 3)).cpu().numpy(), proj_s.view(torch.float32, (n, Vs, 3)).cpu().numpy())
+    assert torch.isfinite(g_params.view(torch.float32, (n, 86))).all() and torch.isfinite(g_params2.view(torch.float32, (n, 86))).all()
+    assert float(seg.view(torch.float32, (n, wh, wh, 32)).sum(-1).min()) > 0.99
