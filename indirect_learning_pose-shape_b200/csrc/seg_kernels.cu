@@ -13,20 +13,24 @@
 //                           reach the one pixel it rounds to: chained per pixel, visited by that pixel alone
 //   generic  anything else evaluated against every pixel (never produced by compute_mask; kept for drop-in inputs)
 //
-// Forward: a warp owns a tile of (LX*BW) x (LY*BH) pixels, a lane a BW x BH block of it, so the per-axis squared
-// offsets du^2 (BW values) and dv^2 (BH values) are shared by the block's pixels.  Eight channels of each pixel are
-// kept in registers and leave as ONE 32-byte store (st.global.v8.f32 = a full DRAM sector; partial-sector stores cost
-// a read-fill).  The score epilogue is d = d2*rsqrt(d2), s = ex2(-d*log2 e): <= 3e-7 absolute from exp(-sqrt(d2)),
-// an order of magnitude inside the 1e-5 geometry tolerance that bounds the inputs.
+// Forward: a warp owns a 16 x 8 pixel tile, a lane a 2 x 2 block of it, so the per-axis squared offsets du^2 and dv^2
+// are shared by the block's pixels.  Once per tile, lane k prunes part k EXACTLY: with i0 the part's vertex nearest the
+// tile centre c, f(g) = d_j^2(g) - d_i0^2(g) is linear in the pixel g, f(g) >= f(c) - 2(|du_j0| hw + |dv_j0| hh) on the
+// tile, so a vertex whose bound clears a margin (far above the fp32 rounding of the squared distances) can never be the
+// arg-min inside the tile and is dropped from the part's survivor words; the hot loop visits survivors only (about 3
+// per (tile, part) instead of 12).  Eight channels of each pixel are staged per lane and leave as ONE 32-byte store
+// (st.global.v8.f32 = a full DRAM sector; partial-sector stores cost a read-fill).  The score epilogue is
+// d = sqrt.approx(d2), s = ex2.approx(-d*log2 e): <= 3e-7 absolute from exp(-sqrt(d2)), an order of magnitude inside
+// the 1e-5 geometry tolerance that bounds the inputs.
 // When a backward will follow, the forward also records per pixel the clip gate and the arg-min of every part as one
-// byte (`saved`, 32 B per pixel, laid out in the forward's own (tile, block, lane) order), so the backward never
+// byte (`saved`, 32 B per pixel, in the layout of the output itself: [n][wh-1-r][c][channel]), so the backward never
 // searches.
 //
-// Backward: lane = channel.  Records are read back in the forward's order (no index arithmetic beyond shifts), the
-// upstream gradient row of the pixel is one coalesced 128-byte load, s is recomputed at the recorded arg-min, and the
+// Backward: lane = channel, a warp walks a contiguous range of output pixels.  The pixel's upstream gradient row is
+// one coalesced 128-byte load and its saved row one 32-byte load; s is recomputed at the recorded arg-min and the
 // per-vertex sums accumulate in per-warp PRIVATE shared-memory slots indexed by the part's light slot: lane k is the
-// only writer of part k's slots, so plain load/add/store replaces atomics (shared fp32 atomicAdd is a CAS loop on
-// sm_100).  Runs of equal arg-min vertices along a row are merged in registers first.
+// only writer of part k's slots, so a plain load/add/store replaces atomics (shared fp32 atomicAdd is a CAS loop on
+// sm_100) and no cross-lane reduction is needed.
 // Gradient conventions (TF autodiff): the first arg-min takes the whole gradient on exact ties (TF splits
 // evenly; measure zero); d == 0 yields 0 where TF yields NaN; the clip gate is inclusive (0 <= sum <= 1).
 #include <math_constants.h>
@@ -49,6 +53,7 @@ struct SegSmem {
   int* lcount;     // [32] light entries per part (packed at the front of the part's CSR segment)
   int* lbase;      // [32] exclusive prefix sum of lcount
   int* pptr;       // [36] the part table's CSR pointers (P+1 used)
+  int* woff;       // [36] exclusive prefix sum of ceil(lcount / 32): offsets of the parts' survivor words
   int* ghead;      // [1]  chain of generic slots, -1 none
   int* nheavy;     // [1]  number of chained heavy entries
   unsigned char* rest;
@@ -68,18 +73,19 @@ __device__ __forceinline__ float score_from_d2(float d2) {
 __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
   SegSmem sm;
   size_t off = 0;
-  sm.ent = reinterpret_cast<float4*>(raw + off); off += (size_t)((E + 1) & ~1) * 16;
+  sm.ent = reinterpret_cast<float4*>(raw + off) + 1; off += (size_t)(E + 2) * 16;   // ent[-1], ent[E]: readable dummies
   sm.head = reinterpret_cast<int*>(raw + off); off += ((size_t)wh * wh * 4 + 15) & ~(size_t)15;
   sm.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.lbase = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.pptr = reinterpret_cast<int*>(raw + off); off += 36 * 4;
+  sm.woff = reinterpret_cast<int*>(raw + off); off += 36 * 4;
   sm.ghead = reinterpret_cast<int*>(raw + off);
   sm.nheavy = sm.ghead + 1; off += 16;
   sm.rest = raw + off;
   return sm;
 }
 size_t seg_base_smem(int E, int wh) {
-  return (size_t)((E + 1) & ~1) * 16 + (((size_t)wh * wh * 4 + 15) & ~(size_t)15) + 2 * 32 * 4 + 36 * 4 + 16;
+  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 4 + 15) & ~(size_t)15) + 2 * 32 * 4 + 2 * 36 * 4 + 16;
 }
 
 // Split the sample's part vertices into weight classes (one warp per part, ballot compaction).
@@ -165,15 +171,17 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
     }
   }
   __syncthreads();
-  if (threadIdx.x < 32) {                               // exclusive scan of the light counts
+  if (threadIdx.x < 32) {                               // exclusive scans of the light counts and of their word counts
     const int c = sm.lcount[threadIdx.x];
-    int s = c;
+    const int cw = (c + 31) >> 5;
+    int s = c, sw = cw;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
-      if ((int)threadIdx.x >= o) s += t;
+      const int t = __shfl_up_sync(0xffffffffu, s, o), tw = __shfl_up_sync(0xffffffffu, sw, o);
+      if ((int)threadIdx.x >= o) { s += t; sw += tw; }
     }
     sm.lbase[threadIdx.x] = s - c;
+    sm.woff[threadIdx.x] = sw - cw;
   }
   __syncthreads();
 }
@@ -226,34 +234,47 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
                : "memory");
 }
 
-// Tile geometry shared by forward and backward (the `saved` layout depends on it).
+// Tile geometry shared by forward and launchers: a warp owns kTW x kTH pixels, lane (lx, ly) = (lane & 7, lane >> 3) a
+// 2 x 2 block of it.
+constexpr int kTW = 16, kTH = 8, kNB = 4;
+constexpr float kTileHW = 0.5f * (kTW - 1), kTileHH = 0.5f * (kTH - 1);
 struct SegGeom {
-  int BW, BH, LX, LY, TW, TH, NB, tiles_x, tiles_y, ntiles;
+  int tiles_x, tiles_y, ntiles;
 };
 SegGeom seg_geom(int wh) {
   SegGeom g;
-  if (wh % 12 == 0) { g.BW = 3; g.BH = 2; g.LX = 4; }         // 12 x 16 pixel tiles (48 = 4 x 3 tiles)
-  else { g.BW = 4; g.BH = 2; g.LX = 4; }                      // 16 x 16 pixel tiles
-  g.LY = 32 / g.LX; g.TW = g.LX * g.BW; g.TH = g.LY * g.BH; g.NB = g.BW * g.BH;
-  g.tiles_x = (wh + g.TW - 1) / g.TW; g.tiles_y = (wh + g.TH - 1) / g.TH; g.ntiles = g.tiles_x * g.tiles_y;
+  g.tiles_x = (wh + kTW - 1) / kTW; g.tiles_y = (wh + kTH - 1) / kTH; g.ntiles = g.tiles_x * g.tiles_y;
   return g;
 }
+// survivor words one warp needs: sum_k ceil(lcount_k / 32) <= E / 32 + P
+__host__ __device__ __forceinline__ int seg_keep_words(int E) { return E / 32 + 33; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
-constexpr float kBigD2 = 1e30f;      // "no vertex yet": rsqrt/ex2 map it to a score of exactly 0 without a branch
-constexpr int kNoPrune = 3;          // parts with this few visible vertices skip the pruning pass
-constexpr float kPruneMargin = 0.01f;
+constexpr float kBigD2 = 1e30f;      // "no vertex yet": sqrt/ex2 map it to a score of exactly 0 without a branch
+constexpr float kPruneMargin = 0.01f;   // px^2; plus a relative term, see prune_tile
+constexpr float kPruneRel = 4e-6f;
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ unsigned bfind_u32(unsigned x) {           // index of the highest set bit (x != 0)
+  unsigned r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
   return r;
 }
 
@@ -263,18 +284,89 @@ __device__ __forceinline__ float2 lds_f2(uint32_t a) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
   return r;
 }
+__device__ __forceinline__ float2 lds_f2_nv(uint32_t a) {            // read-only data: free to be scheduled early
+  float2 r;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
+  return r;
+}
 __device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// saved layout: 4 planes (channels 8q..8q+7); plane q holds, for record id = (tile*NB + b)*32 + lane, 8 bytes.
-// byte of channel 0: bit 0 = clip gate.  byte of channel 1+k: 0 none, 1..254 light index + 1, 255 re-query.
-template <int BW, int BH, int LX, bool TRACK>
+// Exact pruning of one tile, lane k working on part k: writes the part's survivor words to kw[woff[k] ..].
+// i0 = the part's vertex nearest the tile centre (tcx, tcy).  f(g) = d_j^2(g) - d_i0^2(g) is linear in the pixel g:
+// f(g) = f(c) + 2 (p_i0 - p_j).(g - c) >= f(c) - 2 (|u_j - u_i0| hw + |v_j - v_i0| hh) on the tile.  If that bound is at
+// least margin = 0.01 + 4e-6 d_j^2(c), vertex j can never be the fp32 arg-min inside the tile (the rounding of the
+// squared distances and of this test is below 1e-6 relative) and is dropped.  i0 itself always survives (bound = 0).
+__device__ __forceinline__ void prune_tile(const SegSmem& sm, unsigned* kw, int P, int lane, float tcx, float tcy) {
+  if (lane < P) {
+    const int n0 = sm.lcount[lane];
+    if (n0 > 0) {
+      const float4* ek = sm.ent + sm.pptr[lane];
+      unsigned* kwp = kw + sm.woff[lane];
+      float bd = CUDART_INF_F, u0 = 0.f, v0 = 0.f;
+      for (int v = 0; v < n0; ++v) {
+        const float2 e = *reinterpret_cast<const float2*>(&ek[v]);
+        const float du = e.x - tcx, dv = e.y - tcy;
+        const float d = du * du + dv * dv;
+        if (d < bd) { bd = d; u0 = e.x; v0 = e.y; }
+      }
+      unsigned word = 0u;
+      for (int v = 0; v < n0; ++v) {
+        const float2 e = *reinterpret_cast<const float2*>(&ek[v]);
+        const float du = e.x - tcx, dv = e.y - tcy;
+        const float d = du * du + dv * dv;
+        const float slack = 2.0f * (fabsf(e.x - u0) * kTileHW + fabsf(e.y - v0) * kTileHH);
+        const bool keep = (d - bd) - slack < kPruneMargin + kPruneRel * d;
+        word |= (keep ? 1u : 0u) << (v & 31);
+        if ((v & 31) == 31) { kwp[v >> 5] = word; word = 0u; }
+      }
+      if (n0 & 31) kwp[n0 >> 5] = word;
+    }
+  }
+  __syncwarp();
+}
+
+// One word of a part's survivor mask against a lane's 2 x 2 pixel block: best[q] = min squared distance, barg[q] = code of
+// its arg-min, (index + 1) << sh.  CLAMP: indices >= 254 do not fit a byte and are recorded as 255 (re-queried by the
+// backward); only words 7 and up can hold them.
+template <bool TRACK, bool CLAMP>
+__device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsigned sh, float gx0, float gx1, float gy0,
+                                          float gy1, float (&best)[kNB], unsigned (&barg)[kNB]) {
+  const unsigned shmul = 1u << sh, wcode = (unsigned)(w * 32 + 1) << sh;
+  while (m) {
+    const unsigned b = bfind_u32(m);
+    m ^= 1u << b;
+    const float2 e = lds_f2(eb + b * 16u);
+    const float dxa = __fsub_rn(e.x, gx0), dxb = __fsub_rn(e.x, gx1);
+    const float dya = __fsub_rn(e.y, gy0), dyb = __fsub_rn(e.y, gy1);
+    const float ux0 = __fmul_rn(dxa, dxa), ux1 = __fmul_rn(dxb, dxb);
+    const float vy0 = __fmul_rn(dya, dya), vy1 = __fmul_rn(dyb, dyb);
+    float d2[kNB];
+    d2[0] = __fadd_rn(ux0, vy0); d2[1] = __fadd_rn(ux1, vy0);
+    d2[2] = __fadd_rn(ux0, vy1); d2[3] = __fadd_rn(ux1, vy1);
+    if (TRACK) {
+      const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)b + 1, 255) << sh : b * shmul + wcode;
+#pragma unroll
+      for (int q = 0; q < kNB; ++q) {
+        const bool le = d2[q] <= best[q];
+        barg[q] = le ? vcode : barg[q];
+        best[q] = le ? d2[q] : best[q];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kNB; ++q) best[q] = fminf(best[q], d2[q]);
+    }
+  }
+}
+
+// saved layout: 32 bytes per OUTPUT pixel, [n][wh-1-r][c][32].  byte 0: bit 0 = clip gate.  byte 1+k (part k): 0 none,
+// 1..254 light index + 1, 255 re-query (heavy / generic winner or light index >= 254).
+template <bool TRACK>
 __global__ void __launch_bounds__(256, 3)
 seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, int N, int Vs,
                const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh,
                float* __restrict__ seg, unsigned char* __restrict__ saved) {
-  constexpr int LY = 32 / LX, TW = LX * BW, TH = LY * BH, NB = BW * BH;
   extern __shared__ __align__(16) unsigned char raw[];
   const SegSmem sm = carve(raw, E, wh);
   const int n = blockIdx.x;
@@ -283,173 +375,121 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int ghead = *sm.ghead;
   const bool any_heavy = *sm.nheavy > 0;
   const int C = P + 1;
-  const int tiles_x = (wh + TW - 1) / TW, tiles_y = (wh + TH - 1) / TH, ntiles = tiles_x * tiles_y;
+  const int tiles_x = (wh + kTW - 1) / kTW, tiles_y = (wh + kTH - 1) / kTH, ntiles = tiles_x * tiles_y;
   const int t0 = (int)(((long long)ntiles * blockIdx.y) / gridDim.y);
   const int t1 = (int)(((long long)ntiles * (blockIdx.y + 1)) / gridDim.y);
-  const int lx = lane % LX, ly = lane / LX;
-  const size_t plane = (size_t)ntiles * NB * 32 * 8;               // bytes of one saved plane of one sample
-  unsigned char* sv = TRACK ? saved + (size_t)n * plane * 4 : nullptr;
+  const int lx = lane & 7, ly = lane >> 3;
+  unsigned char* sv = TRACK ? saved + (size_t)n * wh * wh * 32 : nullptr;
   float* seg_n = seg ? seg + (size_t)n * wh * wh * C : nullptr;
-  // per-lane staging of one chunk: stage[(sub*NB + q)*32 + lane]  (lane-contiguous: conflict-free, no sync needed)
-  float* stage = reinterpret_cast<float*>(sm.rest) + (size_t)warp * (8 * NB * 32) + lane;
+  const int KW = seg_keep_words(E);
+  unsigned* kw = reinterpret_cast<unsigned*>(sm.rest) + (size_t)warp * KW;
+  // per-lane staging of one chunk: stage[(sub*4 + q)*32 + lane]  (lane-contiguous: conflict-free, no sync needed)
+  float* stage = reinterpret_cast<float*>(sm.rest + (((size_t)nwarps * KW * 4 + 15) & ~(size_t)15)) +
+                 (size_t)warp * (8 * kNB * 32) + lane;
+  const uint32_t ent_sa = (uint32_t)__cvta_generic_to_shared(sm.ent);   // shared-window address of entry 0
 
   for (int t = t0 + warp; t < t1; t += nwarps) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
-    const int c0 = tx * TW + lx * BW, r0 = ty * TH + ly * BH;      // this lane's block origin (grid = (column,row), :26-31)
-    const float cx0 = (float)(tx * TW), cx1 = (float)(tx * TW + TW - 1);   // tile corners (pixel centres) and centre
-    const float cy0 = (float)(ty * TH), cy1 = (float)(ty * TH + TH - 1);
-    const float tcx = 0.5f * (cx0 + cx1), tcy = 0.5f * (cy0 + cy1);
-    float gxs[BW], gys[BH];
-#pragma unroll
-    for (int i = 0; i < BW; ++i) gxs[i] = (float)(c0 + i);
-#pragma unroll
-    for (int j = 0; j < BH; ++j) gys[j] = (float)(r0 + j);
-    bool blk_slow = ghead >= 0;                                    // any heavy vertex chained to one of my pixels?
+    const int c0 = tx * kTW + lx * 2, r0 = ty * kTH + ly * 2;        // this lane's block origin (grid = (column,row), :26-31)
+    const float gx0 = (float)c0, gx1 = (float)(c0 + 1), gy0 = (float)r0, gy1 = (float)(r0 + 1);
+    prune_tile(sm, kw, P, lane, (float)(tx * kTW) + kTileHW, (float)(ty * kTH) + kTileHH);
+
+    bool blk_slow = ghead >= 0;                                      // any heavy vertex chained to one of my pixels?
     if (any_heavy) {
 #pragma unroll
-      for (int j = 0; j < BH; ++j)
-#pragma unroll
-        for (int i = 0; i < BW; ++i)
-          if (c0 + i < wh && r0 + j < wh) blk_slow |= sm.head[(r0 + j) * wh + c0 + i] >= 0;
-    }
-    float S[NB];
-#pragma unroll
-    for (int q = 0; q < NB; ++q) S[q] = 0.f;
-
-    // Exact pruning, once per tile, lane k working on part k.  i0 = the part's vertex nearest the tile centre.
-    // f(g) = d_j^2(g) - d_i0^2(g) is linear in the pixel g, so f >= margin at the tile's four corners implies f >= margin on
-    // every pixel of the tile: vertex j can never be the arg-min there and is dropped from the part's survivor mask.
-    // The margin (0.01 px^2) dwarfs the fp32 rounding of the squared distances (< 3e-3 at wh <= 128), so the survivors
-    // always contain the exact fp32 arg-min.
-    unsigned keepmask = 0xffffffffu;
-    {
-      const int kp = lane < P ? lane : 0;
-      const int q0 = sm.pptr[kp], n0 = (lane < P) ? sm.lcount[kp] : 0;
-      if (n0 > kNoPrune && n0 <= 32) {
-        float bd = CUDART_INF_F;
-        int bi = 0;
-        for (int v = 0; v < n0; ++v) {
-          const float2 e = *reinterpret_cast<const float2*>(&sm.ent[q0 + v]);
-          const float d = dist2(e.x, e.y, tcx, tcy);
-          if (d < bd) { bd = d; bi = v; }
-        }
-        const float2 e0 = *reinterpret_cast<const float2*>(&sm.ent[q0 + bi]);
-        const float a0 = dist2(e0.x, e0.y, cx0, cy0), a1 = dist2(e0.x, e0.y, cx1, cy0);
-        const float a2 = dist2(e0.x, e0.y, cx0, cy1), a3 = dist2(e0.x, e0.y, cx1, cy1);
-        keepmask = 0u;
-        for (int v = 0; v < n0; ++v) {
-          const float2 e = *reinterpret_cast<const float2*>(&sm.ent[q0 + v]);
-          const bool dominated = dist2(e.x, e.y, cx0, cy0) - a0 >= kPruneMargin && dist2(e.x, e.y, cx1, cy0) - a1 >= kPruneMargin &&
-                                 dist2(e.x, e.y, cx0, cy1) - a2 >= kPruneMargin && dist2(e.x, e.y, cx1, cy1) - a3 >= kPruneMargin;
-          keepmask |= dominated ? 0u : (1u << v);
-        }
+      for (int q = 0; q < kNB; ++q) {
+        const int r = r0 + (q >> 1), c = c0 + (q & 1);
+        if (c < wh && r < wh) blk_slow |= sm.head[r * wh + c] >= 0;
       }
     }
+    float S[kNB];
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) S[q] = 0.f;
 
     // channel chunks 1, 2, 3, then chunk 0 last: its channel 0 (background) needs the sum over all parts
     for (int cc = 1; cc <= 4; ++cc) {
       const int chunk = cc & 3;
       if (chunk * 8 >= C) continue;
-      unsigned clo[NB], chi[NB];                                   // packed saved bytes, channels 0-3 / 4-7 of the chunk
+      unsigned cw[2][kNB];                                           // packed saved bytes, channels 0-3 / 4-7 of the chunk
 #pragma unroll
-      for (int q = 0; q < NB; ++q) { clo[q] = 0u; chi[q] = 0u; }
+      for (int q = 0; q < kNB; ++q) { cw[0][q] = 0u; cw[1][q] = 0u; }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
-      for (int sub = 0; sub < 8; ++sub) {
-        const int ch = chunk * 8 + sub;
-        float sc[NB];
-        int code[NB];
-        if (ch == 0 || ch >= C) {                                  // background is filled in after the loop
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int sub = half * 4 + s4;
+          const int ch = chunk * 8 + sub;
+          if (ch == 0 || ch >= C) {                                  // background is filled in after the loop
 #pragma unroll
-          for (int q = 0; q < NB; ++q) stage[(sub * NB + q) * 32] = 0.f;
-          continue;
-        }
-        const int p0 = sm.pptr[ch - 1], p1 = sm.pptr[ch], nl = sm.lcount[ch - 1];
-        float best[NB];
-        int barg[NB];
-#pragma unroll
-        for (int q = 0; q < NB; ++q) { best[q] = kBigD2; barg[q] = -1; }
-        const unsigned pm = __shfl_sync(0xffffffffu, keepmask, ch - 1);   // survivors of this part (lane ch-1 pruned it)
-        for (int cb = 0; cb < nl; cb += 32) {
-          const int cnt = min(32, nl - cb);
-          unsigned m = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
-          if (nl <= 32) m &= pm;                                     // parts with more than 32 visible vertices are not pruned
-          while (m) {
-            const int v = cb + __ffs(m) - 1;
-            m &= m - 1;
-            const float2 e = *reinterpret_cast<const float2*>(&sm.ent[p0 + v]);   // same address on every lane: broadcast
-            float du2[BW], dv2[BH], d2[NB];
-#pragma unroll
-            for (int i = 0; i < BW; ++i) { const float d = __fsub_rn(e.x, gxs[i]); du2[i] = __fmul_rn(d, d); }
-#pragma unroll
-            for (int j = 0; j < BH; ++j) { const float d = __fsub_rn(e.y, gys[j]); dv2[j] = __fmul_rn(d, d); }
-#pragma unroll
-            for (int j = 0; j < BH; ++j)
-#pragma unroll
-              for (int i = 0; i < BW; ++i) d2[j * BW + i] = __fadd_rn(du2[i], dv2[j]);
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-              if (TRACK) barg[q] = (d2[q] < best[q]) ? v : barg[q];
-              best[q] = fminf(best[q], d2[q]);
-            }
+            for (int q = 0; q < kNB; ++q) stage[(sub * kNB + q) * 32] = 0.f;
+            continue;
           }
-        }
+          const int p0 = sm.pptr[ch - 1], p1 = sm.pptr[ch], nl = sm.lcount[ch - 1];
+          const unsigned* kwp = kw + sm.woff[ch - 1];
+          const unsigned sh = 8u * (unsigned)s4;
+          float best[kNB];
+          unsigned barg[kNB];                                        // arg-min code, already shifted to its byte
 #pragma unroll
-        for (int q = 0; q < NB; ++q) {
-          const float rs = rsqrt_approx(fmaxf(best[q], 1e-30f));
-          sc[q] = ex2_approx((best[q] * rs) * (-kLog2e));          // exp(-sqrt(d2)); kBigD2 -> 0, d2 == 0 -> 1
-          code[q] = min(barg[q] + 1, 255);                         // 0 none, 1..254 index+1, 255 re-query
-        }
-        if (blk_slow) {                                            // rare: heavy / generic vertices
+          for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
+          // survivors are visited from the highest index down and replace on <=, so the LOWEST index wins exact ties
+          for (int w = (nl + 31) >> 5; w-- > 0;) {
+            const unsigned m = kwp[w];                               // same address on every lane: broadcast
+            const uint32_t eb = ent_sa + (uint32_t)(p0 + w * 32) * 16u;
+            if (TRACK && w >= 7) scan_word<TRACK, true>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
+            else scan_word<TRACK, false>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
+          }
+          float sc[kNB];
 #pragma unroll
-          for (int q = 0; q < NB; ++q) {
-            const int i = q % BW, j = q / BW;
-            if (c0 + i < wh && r0 + j < wh) {
-              const int hd = any_heavy ? sm.head[(r0 + j) * wh + c0 + i] : -1;
-              if (hd >= 0 || ghead >= 0) {
-                const float ss = slow_pixel_score(sm, p0, p1, gxs[i], gys[j], hd, ghead, best[q]);
-                if (ss >= 0.f) { sc[q] = ss; code[q] = 255; }
+          for (int q = 0; q < kNB; ++q)
+            sc[q] = ex2_approx(sqrt_approx(best[q]) * (-kLog2e));    // exp(-sqrt(d2)); kBigD2 -> 0, d2 == 0 -> 1
+          if (blk_slow) {                                            // rare: heavy / generic vertices
+#pragma unroll
+            for (int q = 0; q < kNB; ++q) {
+              const int r = r0 + (q >> 1), c = c0 + (q & 1);
+              if (c < wh && r < wh) {
+                const int hd = any_heavy ? sm.head[r * wh + c] : -1;
+                if (hd >= 0 || ghead >= 0) {
+                  const float ss = slow_pixel_score(sm, p0, p1, (q & 1) ? gx1 : gx0, (q >> 1) ? gy1 : gy0, hd, ghead, best[q]);
+                  if (ss >= 0.f) { sc[q] = ss; barg[q] = 255u << sh; }
+                }
               }
             }
           }
-        }
-        const unsigned sh = 8u * (sub & 3);
 #pragma unroll
-        for (int q = 0; q < NB; ++q) {
-          stage[(sub * NB + q) * 32] = sc[q];
-          S[q] += sc[q];
-          if (TRACK) {
-            if (sub < 4) clo[q] |= (unsigned)code[q] << sh;
-            else chi[q] |= (unsigned)code[q] << sh;
+          for (int q = 0; q < kNB; ++q) {
+            stage[(sub * kNB + q) * 32] = sc[q];
+            S[q] += sc[q];
+            if (TRACK) cw[half][q] |= barg[q];
           }
         }
       }
       if (chunk == 0) {
 #pragma unroll
-        for (int q = 0; q < NB; ++q) {
-          stage[q * 32] = 1.0f - fminf(fmaxf(S[q], 0.f), 1.f);     // :61-64
-          if (TRACK) clo[q] |= (S[q] >= 0.f && S[q] <= 1.f) ? 1u : 0u;   // clip gate (inclusive), for the backward
+        for (int q = 0; q < kNB; ++q) {
+          stage[q * 32] = 1.0f - fminf(fmaxf(S[q], 0.f), 1.f);       // :61-64
+          if (TRACK) cw[0][q] |= (S[q] >= 0.f && S[q] <= 1.f) ? 1u : 0u;   // clip gate (inclusive), for the backward
         }
       }
       // one 32-byte sector per pixel; rows flipped (:68)
 #pragma unroll
-      for (int q = 0; q < NB; ++q) {
-        const int r = r0 + q / BW, c = c0 + q % BW;
-        if (seg_n && r < wh && c < wh) {
-          float* o = seg_n + ((wh - 1 - r) * wh + c) * C + chunk * 8;
-          float v8[8];
+      for (int q = 0; q < kNB; ++q) {
+        const int r = r0 + (q >> 1), c = c0 + (q & 1);
+        if (r < wh && c < wh) {
+          const size_t opx = (size_t)(wh - 1 - r) * wh + c;
+          if (seg_n) {
+            float* o = seg_n + opx * C + chunk * 8;
+            float v8[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v8[e] = stage[(e * NB + q) * 32];
-          if (C == 32) {
-            st_global_v8(o, v8);
-          } else {
+            for (int e = 0; e < 8; ++e) v8[e] = stage[(e * kNB + q) * 32];
+            if (C == 32) {
+              st_global_v8(o, v8);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (chunk * 8 + e < C) o[e] = v8[e];
+              for (int e = 0; e < 8; ++e)
+                if (chunk * 8 + e < C) o[e] = v8[e];
+            }
           }
-        }
-        if (TRACK) {
-          uint2* so = reinterpret_cast<uint2*>(sv + (size_t)chunk * plane) + ((t * NB + q) * 32 + lane);
-          *so = make_uint2(clo[q], chi[q]);
+          if (TRACK) *reinterpret_cast<uint2*>(sv + opx * 32 + chunk * 8) = make_uint2(cw[0][q], cw[1][q]);
         }
       }
     }
@@ -459,7 +499,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 // ---------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBatch = 8;          // records whose loads are in flight together (consecutive lanes of one block row)
+constexpr int kBatch = 8;          // pixels whose loads are in flight together
 constexpr int kAccSlots = 512;     // private accumulator slots per warp (light entries beyond this use atomics)
 
 // rare: winner is a heavy/generic vertex (or a light index that did not fit a byte): exact re-query, atomics
@@ -477,14 +517,85 @@ __device__ __noinline__ void slow_pixel_grad(const SegSmem& sm, const int* __res
   atomicAdd(&gacc[vid * 2 + 1], coef * dv);
 }
 
-template <int BW, int BH, int LX, bool C32, bool ALLIN>
+// Generic pixel walk of the backward (any wh): per-pixel bounds and row bookkeeping; the aligned path in the kernel is the
+// tuned one.
+template <bool C32>
+__device__ __noinline__ void generic_pixel_walk(const SegSmem& sm, const int* __restrict__ idx, float* gacc,
+                                                const unsigned char* __restrict__ sv, const float* __restrict__ g_n,
+                                                bool ld_g, bool live, int lane, int warp, int nwarps, int wh, int C, int p0,
+                                                int p1, int nl, int ghead, uint32_t ent_sa, uint32_t wacc_sa, int acc_cap,
+                                                const float4* ent_k) {
+  const int npx = wh * wh;
+  // Each warp owns a contiguous range of output pixels (row-major, rows already flipped: grid row = wh-1-row).
+  const int px0 = (int)(((long long)npx * warp) / nwarps), px1 = (int)(((long long)npx * (warp + 1)) / nwarps);
+  struct Batch { int code[kBatch]; float g[kBatch]; };
+  auto load_batch = [&](int base, Batch& bt) {
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const bool in = base + j < px1;
+      bt.code[j] = in ? (int)sv[(size_t)(base + j) * 32] : 0;
+      bt.g[j] = (in && ld_g) ? g_n[(size_t)(base + j) * C] : 0.f;
+    }
+  };
+  Batch cur, nxt;
+  if (px0 < px1) load_batch(px0, cur);
+  int orow = px0 / wh, col = px0 - orow * wh;                       // output row / column of the batch's first pixel
+  for (int base = px0; base < px1; base += kBatch) {
+    if (base + kBatch < px1) load_batch(base + kBatch, nxt);        // next batch's loads fly while this one is consumed
+    unsigned slowmask = 0u;
+    int c = col, orw = orow;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const float gx = (float)c, gy = (float)(wh - 1 - orw);        // small integers: exact in fp32
+      const int code = cur.code[j];
+      const float t0 = (code & 1) ? cur.g[j] : 0.f;                 // lane 0: gate * g_bg   (d bg / d s_k = -gate)
+      const float G = cur.g[j] - __shfl_sync(0xffffffffu, t0, 0);
+      const bool fast = live && code != 0 && code != 255;
+      if (live && code == 255) slowmask |= 1u << j;                 // rare exact re-query, deferred
+      const int li = fast ? code - 1 : 0;
+      const float2 e = lds_f2(ent_sa + (uint32_t)li * 16u);        // light entry (w == 1)
+      const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+      const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+      const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
+      const float s = ex2_approx((d2 * rs) * (-kLog2e));
+      const float coef = -(s * G) * rs;                             // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
+      if (fast) {
+        if (li < acc_cap) {                                         // private slot: this lane is its only writer
+          const uint32_t a_sa = wacc_sa + (uint32_t)li * 8u;
+          float2 a = lds_f2(a_sa);
+          a.x += coef * du; a.y += coef * dv;
+          sts_f2(a_sa, a);
+        } else {
+          const int vid = __float_as_int(ent_k[li].w);
+          atomicAdd(&gacc[vid * 2], coef * du); atomicAdd(&gacc[vid * 2 + 1], coef * dv);
+        }
+      }
+      if (++c == wh) { c = 0; ++orw; }
+    }
+    if (__any_sync(0xffffffffu, slowmask != 0u)) {                  // rare: heavy / generic winners, exact, atomics
+      int c2 = col, orw2 = orow;
+#pragma unroll 1
+      for (int j = 0; j < kBatch; ++j) {                            // warp-uniform loop: every lane takes the shuffle
+        const float t0 = (cur.code[j] & 1) ? cur.g[j] : 0.f;
+        const float G = cur.g[j] - __shfl_sync(0xffffffffu, t0, 0);
+        if ((slowmask >> j) & 1u) {
+          const int gr = wh - 1 - orw2;
+          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, (float)c2, (float)gr, sm.head[gr * wh + c2], ghead, G);
+        }
+        if (++c2 == wh) { c2 = 0; ++orw2; }
+      }
+    }
+    col += kBatch;
+    while (col >= wh) { col -= wh; ++orow; }
+    cur = nxt;
+  }
+}
+
+template <bool C32, bool ALIGNED>
 __global__ void __launch_bounds__(256, 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
-               const int* __restrict__ idx, int P, int E, int wh, int tiles_x, int ntiles,
-               float* __restrict__ g_projects) {
-  constexpr int LY = 32 / LX, TW = LX * BW, TH = LY * BH, NB = BW * BH;
-  static_assert(LX == 4 && kBatch == 8, "a batch of 8 records = two lane rows of 4 blocks");
+               const int* __restrict__ idx, int P, int E, int wh, float* __restrict__ g_projects) {
   extern __shared__ __align__(16) unsigned char raw[];
   const SegSmem sm = carve(raw, E, wh);
   float* gacc = reinterpret_cast<float*>(sm.rest);                  // [Vs][2]
@@ -503,117 +614,95 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   float2* wacc = wacc_all + (size_t)warp * kAccSlots + sm.lbase[k]; // this lane's part, private to (warp, lane)
   const uint32_t ent_sa = (uint32_t)__cvta_generic_to_shared(ent_k);   // shared-window addresses of the two hot arrays
   const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(wacc);
-  const int acc_cap = kAccSlots - sm.lbase[k];                      // light indices >= acc_cap overflow to atomics
-  const size_t plane = (size_t)ntiles * NB * 32 * 8;
-  const unsigned char* sv = saved + (size_t)n * plane * 4 + (size_t)(lane >> 3) * plane + (lane & 7);
-  const float* g_n = g_seg + (size_t)n * wh * wh * C + (lane < C ? lane : 0);
-  const int nrec = ntiles * NB * 32;
+  // light indices >= acc_cap (only possible when the sample has more than kAccSlots visible part vertices) go to
+  // shared atomics instead of the private slots
+  const int acc_cap = kAccSlots - sm.lbase[k];
+  const int npx = wh * wh;
+  const unsigned char* sv = saved + (size_t)n * npx * 32 + lane;
+  const float* g_n = g_seg + (size_t)n * npx * C + (lane < C ? lane : 0);
+  const bool ld_g = C32 || lane < C;
 
-  // Runs of equal arg-min vertices are merged in registers; a run ends with one load/add/store on the lane's private
-  // slot.  Light indices beyond the private capacity (only possible when the sample has more than kAccSlots visible
-  // part vertices) fall back to atomics behind a warp-uniform flag, so the common path carries no such branch.
-  const bool overflow = (sm.lbase[31] + sm.lcount[31]) > kAccSlots;
-  int run_li = -1;                                                  // current run: light index within this lane's part
-  float run_u = 0.f, run_v = 0.f;
-  auto flush_slow = [&]() {
-    if (run_li < acc_cap) {
-      float2 a = wacc[run_li];
-      a.x += run_u; a.y += run_v;
-      wacc[run_li] = a;
-    } else {
-      const int vid = __float_as_int(ent_k[run_li].w);
-      atomicAdd(&gacc[vid * 2], run_u); atomicAdd(&gacc[vid * 2 + 1], run_v);
-    }
-  };
-  // Records follow the forward's order, id = (tile*NB + b)*32 + l32, l32 = ly*4 + lx.  Each warp owns a contiguous
-  // range of whole 32-record groups; a batch is 8 records = two lane rows visited in serpentine order (even rows left
-  // to right, odd rows right to left), so consecutive records are neighbouring pixel blocks and runs stay long.
-  struct Batch { int code[kBatch]; float g[kBatch]; int r0, c0; };
-  auto load_batch = [&](int base, Batch& bt) {
-    const int l0 = base & 31, tb = base >> 5;
-    const int b = tb % NB, t = tb / NB;                             // compile-time divisors
-    const int ty = (tiles_x == 1) ? t : t / tiles_x, tx = t - ty * tiles_x;
-    bt.r0 = ty * TH + (l0 >> 2) * BH + b / BW;                      // first lane row of the batch; the second is +BH
-    bt.c0 = tx * TW + b % BW;                                       // lx = 0 ; +BW per lane column
-    const unsigned char* srow = sv + (size_t)base * 8;
-    const float* grow = g_n + ((wh - 1 - bt.r0) * wh + bt.c0) * C;  // rows flipped (:68): next lane row is -BH*wh*C
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);  // serpentine
-      const bool in = ALLIN || (bt.r0 + ly * BH < wh && bt.c0 + lx * BW < wh);
-      bt.code[j] = in ? (int)srow[(ly * 4 + lx) * 8] : 0;
-      bt.g[j] = (in && (C32 || lane < C)) ? grow[(lx * BW - ly * BH * wh) * C] : 0.f;
-    }
-  };
-  const int ngroups = nrec >> 5;
-  const int grp0 = (int)(((long long)ngroups * warp) / nwarps), grp1 = (int)(((long long)ngroups * (warp + 1)) / nwarps);
-  const int rec_end = grp1 * 32;
-  Batch cur, nxt;
-  int base = grp0 * 32;
-  if (base < rec_end) load_batch(base, cur);
-  for (; base < rec_end; base += kBatch) {
-    if (base + kBatch < rec_end) load_batch(base + kBatch, nxt);    // next batch's loads fly while this one is consumed
-    const float gxb = (float)cur.c0, gyb = (float)cur.r0;
-    unsigned slowmask = 0u;
-#pragma unroll
-    for (int h = 0; h < kBatch; h += 4) {
-      // (a) four records at a time, branch-free and mutually independent: the compiler interleaves the four chains
-      int li4[4];
-      float cu4[4], cv4[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = h + jj;
-        const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);
-        const int gate = __shfl_sync(0xffffffffu, cur.code[j], 0);
-        const float g0 = __shfl_sync(0xffffffffu, cur.g[j], 0);
-        const float G = cur.g[j] - ((gate & 1) ? g0 : 0.f);         // d bg / d s_k = -gate
-        const float gx = gxb + (float)(lx * BW), gy = gyb + (float)(ly * BH);   // small integers: exact in fp32
-        int li = live ? cur.code[j] - 1 : -1;                       // 0 -> -1 none
-        if (li == 254) { slowmask |= 1u << j; li = -1; }            // code 255: rare exact re-query, deferred
-        // light entry (w == 1); lanes without a vertex read slot 0 and contribute zero
-        const float2 e = lds_f2(ent_sa + (uint32_t)(li < 0 ? 0 : li) * 16u);
-        const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
-        const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
-        const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
-        const float s = ex2_approx((d2 * rs) * (-kLog2e));
-        const float coef = (li < 0) ? 0.f : -(s * G) * rs;          // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
-        li4[jj] = li; cu4[jj] = coef * du; cv4[jj] = coef * dv;
-      }
-      // (b) sequential run merge over the four results
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const bool brk = li4[jj] != run_li;
-        if (brk && run_li >= 0) {
-          if (!overflow) {                                          // private slot: this lane is its only writer
-            const uint32_t a_sa = wacc_sa + (uint32_t)run_li * 8u;
-            float2 a = lds_f2(a_sa);
-            a.x += run_u; a.y += run_v;
-            sts_f2(a_sa, a);
-          } else {
-            flush_slow();
-          }
-        }
-        run_u = brk ? cu4[jj] : run_u + cu4[jj];
-        run_v = brk ? cv4[jj] : run_v + cv4[jj];
-        run_li = li4[jj];
+  // more visible part vertices than private slots (never at vertex_sampling=5): the generic walk handles the spill
+  const bool overflow = sm.lbase[31] + sm.lcount[31] > kAccSlots;   // warp-uniform
+  if (ALIGNED && !overflow) {
+    // wh % 8 == 0: groups of 4 consecutive output pixels never straddle a row.  Each warp owns a contiguous range of
+    // groups; loads run one group ahead in two named register sets (no copies), pointers advance linearly.
+    const int nb = npx >> 2;
+    const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
+    const unsigned char* svp = sv + (size_t)b0 * 4 * 32;
+    const float* gp = g_n + (size_t)b0 * 4 * C;
+    int col = (b0 * 4) % wh;
+    float gy = (float)(wh - 1 - (b0 * 4) / wh);                     // grid row of the group (rows flipped, :68)
+#define SEG_LOAD4(code, g)                                                                                             \
+  do {                                                                                                                 \
+    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
+      code[j] = (int)svp[j * 32];                                                                                      \
+      g[j] = ld_g ? gp[j * C] : 0.f;                                                                                   \
+    }                                                                                                                  \
+    svp += 4 * 32; gp += 4 * C;                                                                                        \
+  } while (0)
+#define SEG_COMPUTE4(code, g, back)                                                                                    \
+  do {                                                                                                                 \
+    const float gxb = (float)col;                                                                                      \
+    float cu[4], cv[4];                                                                                                \
+    int li[4];                                                                                                         \
+    /* (a) four pixels, mutually independent: the arithmetic of the four chains interleaves */                        \
+    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
+      const float t0 = (code[j] & 1) ? g[j] : 0.f;                 /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
+      const float G = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                          \
+      li[j] = (live ? code[j] : 0) - 1;                             /* -1 (none), 254 (re-query): harmless slots */    \
+      const float2 e = lds_f2_nv(ent_sa + (uint32_t)(li[j] * 16));                                                     \
+      const float du = __fsub_rn(e.x, gxb + (float)j), dv = __fsub_rn(e.y, gy);                                        \
+      const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));                                                \
+      const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));                                                                \
+      const float s = ex2_approx((d2 * rs) * (-kLog2e));                                                               \
+      const float coef = (s * G) * (-rs);                           /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
+      cu[j] = coef * du; cv[j] = coef * dv;                                                                            \
+    }                                                                                                                  \
+    /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order */            \
+    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
+      if ((unsigned)li[j] < 254u) {                                                                                    \
+        const uint32_t a_sa = wacc_sa + (uint32_t)li[j] * 8u;                                                          \
+        float2 a = lds_f2(a_sa);                                                                                       \
+        a.x += cu[j]; a.y += cv[j];                                                                                    \
+        sts_f2(a_sa, a);                                                                                               \
+      }                                                                                                                \
+    }                                                                                                                  \
+    if (__any_sync(0xffffffffu, max(max(li[0], li[1]), max(li[2], li[3])) == 254)) {   /* rare: heavy / generic */     \
+      const unsigned char* svb = svp - (back) * 4 * 32;             /* this group again, from memory: no indexed regs */ \
+      const float* gb = gp - (back) * 4 * C;                                                                           \
+      const int gr = (int)gy;                                                                                          \
+      _Pragma("unroll 1") for (int j = 0; j < 4; ++j) {             /* warp-uniform loop: every lane takes the shuffle */ \
+        const int cj = (int)svb[j * 32];                                                                               \
+        const float gj = ld_g ? gb[j * C] : 0.f;                                                                       \
+        const float t0 = (cj & 1) ? gj : 0.f;                                                                          \
+        const float G = gj - __shfl_sync(0xffffffffu, t0, 0);                                                          \
+        if (live && cj == 255)                                                                                         \
+          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, (float)(col + j), gy, sm.head[gr * wh + col + j], ghead, G);      \
+      }                                                                                                                \
+    }                                                                                                                  \
+    col += 4;                                                                                                          \
+    if (col == wh) { col = 0; gy -= 1.0f; }                                                                            \
+  } while (0)
+    int codeA[4], codeB[4];
+    float gA[4], gB[4];
+    const int nbw = b1 - b0;
+    if (nbw > 0) SEG_LOAD4(codeA, gA);
+    for (int i = 0; i < nbw; i += 2) {
+      const bool hasB = i + 1 < nbw, moreA = i + 2 < nbw;
+      if (hasB) SEG_LOAD4(codeB, gB);
+      SEG_COMPUTE4(codeA, gA, hasB ? 2 : 1);                        // pointers are `back` groups past this one
+      if (hasB) {
+        if (moreA) SEG_LOAD4(codeA, gA);
+        SEG_COMPUTE4(codeB, gB, moreA ? 2 : 1);
       }
     }
-    if (__any_sync(0xffffffffu, slowmask != 0u)) {                  // rare: heavy / generic winners, exact, atomics
-#pragma unroll 1
-      for (int j = 0; j < kBatch; ++j) {                            // warp-uniform loop: every lane takes the shuffles
-        const int ly = j >> 2, lx = (j & 4) ? 3 - (j & 3) : (j & 3);
-        const int gate = __shfl_sync(0xffffffffu, cur.code[j], 0);
-        const float g0 = __shfl_sync(0xffffffffu, cur.g[j], 0);
-        if ((slowmask >> j) & 1u) {
-          const float G = cur.g[j] - ((gate & 1) ? g0 : 0.f);
-          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, gxb + (float)(lx * BW), gyb + (float)(ly * BH),
-                          sm.head[(cur.r0 + ly * BH) * wh + cur.c0 + lx * BW], ghead, G);
-        }
-      }
-    }
-    cur = nxt;
+#undef SEG_LOAD4
+#undef SEG_COMPUTE4
+  } else {
+    generic_pixel_walk<C32>(sm, idx, gacc, sv, g_n, ld_g, live, lane, warp, nwarps, wh, C, p0, p1, nl, ghead, ent_sa,
+                            wacc_sa, acc_cap, ent_k);
   }
-  if (run_li >= 0) flush_slow();
   __syncthreads();
   // fold the warps' private slots into the per-vertex sums (a vertex may sit in more than one part)
   const int nlight = min(sm.lbase[31] + sm.lcount[31], kAccSlots);
@@ -635,9 +724,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int BW, int BH, int LX>
-cudaError_t launch_fwd_cfg(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
-                           float* seg, unsigned char* saved, cudaStream_t st) {
+cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
+                            float* seg, unsigned char* saved, cudaStream_t st) {
   const SegGeom g = seg_geom(wh);
   int warps = 1;
   for (int w = 8; w >= 1; --w)                 // the largest warp count <= 8 that divides the tile count evenly
@@ -648,36 +736,32 @@ cudaError_t launch_fwd_cfg(const SmplB200Parts* p, const float* projects, const 
     split = max(1, min(g.ntiles, (2 * 148 + N - 1) / N));
     warps = 8;     // every block re-classifies the sample's vertices: keep 8 warps for that even if it owns few tiles
   }
-  const size_t smem = seg_base_smem(p->E, wh) + (size_t)warps * 8 * g.NB * 32 * 4;
+  const size_t smem = seg_base_smem(p->E, wh) + (((size_t)warps * seg_keep_words(p->E) * 4 + 15) & ~(size_t)15) +
+                      (size_t)warps * 8 * kNB * 32 * 4;
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   dim3 grid(N, split);
   LaunchScope scope(KID_SEG_FWD, st);
   cudaError_t e;
   if (saved) {
-    e = cudaFuncSetAttribute(seg_fwd_kernel<BW, BH, LX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(seg_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    seg_fwd_kernel<BW, BH, LX, true><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh,
-                                                                    seg, saved);
+    seg_fwd_kernel<true><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg, saved);
   } else {
-    e = cudaFuncSetAttribute(seg_fwd_kernel<BW, BH, LX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(seg_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    seg_fwd_kernel<BW, BH, LX, false><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh,
-                                                                     seg, nullptr);
+    seg_fwd_kernel<false><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg,
+                                                          nullptr);
   }
   return cudaGetLastError();
 }
 
 }  // namespace
 
-size_t seg_saved_bytes(int N, int wh) {
-  const SegGeom g = seg_geom(wh);
-  return (size_t)N * g.ntiles * g.NB * 32 * 8 * 4;
-}
+size_t seg_saved_bytes(int N, int wh) { return (size_t)N * wh * wh * 32; }
 
 cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
                            float* seg, unsigned char* saved, cudaStream_t st) {
-  if (wh % 12 == 0) return launch_fwd_cfg<3, 2, 4>(p, projects, mask, N, Vs, wh, seg, saved, st);
-  return launch_fwd_cfg<4, 2, 4>(p, projects, mask, N, Vs, wh, seg, saved, st);
+  return launch_fwd_impl(p, projects, mask, N, Vs, wh, seg, saved, st);
 }
 
 cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
@@ -685,27 +769,19 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
   const int warps = 8;
   const size_t smem = seg_base_smem(p->E, wh) + (size_t)((Vs * 2 + 3) & ~3) * 4 + (size_t)warps * kAccSlots * 8;
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
-  const SegGeom g = seg_geom(wh);
   LaunchScope scope(KID_SEG_BWD, st);
-#define SMPL_SEG_BWD(BW, BH, LX, C32, ALLIN)                                                                           \
+#define SMPL_SEG_BWD(C32, AL)                                                                                          \
   do {                                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<BW, BH, LX, C32, ALLIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    seg_bwd_kernel<BW, BH, LX, C32, ALLIN><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr,    \
-                                                                        p->idx, p->P, p->E, wh, g.tiles_x, g.ntiles,    \
-                                                                        g_projects);                                   \
+    seg_bwd_kernel<C32, AL><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->P, p->E, \
+                                                          wh, g_projects);                                             \
   } while (0)
-  const bool c32 = p->P == 31;
-  const bool allin = (wh % g.TW == 0) && (wh % g.TH == 0);          // every record is a pixel of the image
-  if (wh % 12 == 0) {
-    if (c32 && allin) SMPL_SEG_BWD(3, 2, 4, true, true);
-    else if (c32) SMPL_SEG_BWD(3, 2, 4, true, false);
-    else SMPL_SEG_BWD(3, 2, 4, false, false);
-  } else {
-    if (c32 && allin) SMPL_SEG_BWD(4, 2, 4, true, true);
-    else if (c32) SMPL_SEG_BWD(4, 2, 4, true, false);
-    else SMPL_SEG_BWD(4, 2, 4, false, false);
-  }
+  const bool c32 = p->P == 31, al = wh % 8 == 0;
+  if (c32 && al) SMPL_SEG_BWD(true, true);
+  else if (c32) SMPL_SEG_BWD(true, false);
+  else if (al) SMPL_SEG_BWD(false, true);
+  else SMPL_SEG_BWD(false, false);
 #undef SMPL_SEG_BWD
   return cudaGetLastError();
 }
