@@ -391,6 +391,10 @@ int smpl_b200_parts_create(int device, int num_parts, const int32_t* part_ptr, c
   CU_TRY(upload(&p->ptr, ptr));
   CU_TRY(upload(&p->idx, idx));
   CU_TRY(upload(&p->part_of, po));
+  std::vector<int> ob(num_parts + 1, 0);
+  for (int k = 0; k < num_parts; ++k) ob[k + 1] = ob[k] + std::max(ptr[k + 1] - ptr[k] - 32, 0);
+  p->ovf = ob[num_parts];
+  CU_TRY(upload(&p->obase, ob));
   CU_TRY(cudaDeviceSynchronize());
   cudaSetDevice(prev);
   *out = p;
@@ -402,7 +406,7 @@ void smpl_b200_parts_destroy(SmplB200Parts* p) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
-  cudaFree(p->ptr); cudaFree(p->idx); cudaFree(p->part_of);
+  cudaFree(p->ptr); cudaFree(p->idx); cudaFree(p->part_of); cudaFree(p->obase);
   cudaSetDevice(prev);
   delete p;
 }

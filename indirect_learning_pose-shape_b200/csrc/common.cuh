@@ -94,6 +94,8 @@ struct SmplB200Parts {
   int* idx = nullptr;        // [E]   device, sampled-space vertex index
   uint8_t* part_of = nullptr;  // [E] device, part id of each entry
   int max_part = 0;
+  int ovf = 0;               // sum_k max(size_k - 32, 0): overflow slots of the seg backward's interleaved light lists
+  int* obase = nullptr;      // [P+1] device, exclusive prefix of max(size_k - 32, 0)
 };
 
 namespace smplb200 {

@@ -212,22 +212,6 @@ __device__ __noinline__ float slow_pixel_score(const SegSmem& sm, int p0, int p1
   return (a >= 0) ? expf(-x) : -1.0f;
 }
 
-// Out-of-line slow path of the backward: full weighted nearest-vertex query of part [p0,p1) for one pixel.
-__device__ __noinline__ int slow_pixel_query(const SegSmem& sm, int p0, int p1, int nl, float gx, float gy, int head,
-                                             int ghead) {
-  float best = CUDART_INF_F;
-  int barg = -1;
-  for (int i = 0; i < nl; ++i) {
-    const float4 e = sm.ent[p0 + i];
-    const float d2 = dist2(e.x, e.y, gx, gy);
-    if (d2 < best) { best = d2; barg = p0 + i; }
-  }
-  float x = sqrtf(best);
-  if (head >= 0) walk_chain(sm, head, p0, p1, gx, gy, x, barg);
-  if (ghead >= 0) walk_chain(sm, ghead, p0, p1, gx, gy, x, barg);
-  return barg;
-}
-
 __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -499,226 +483,286 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 // ---------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBatch = 8;          // pixels whose loads are in flight together
-constexpr int kAccSlots = 512;     // private accumulator slots per warp (light entries beyond this use atomics)
+// Shared memory of the backward: only the LIGHT vertices (w == 1) are kept, in a lane-interleaved layout: slot i of part
+// k sits at [i][k], so when lane = part every lane's 8-byte access falls in its own bank pair whatever i is (a warp-wide
+// 64-bit access is exactly two conflict-free wavefronts).  The private accumulators of each warp use the same layout.
+// Parts with more than kIL visible vertices spill to a compact overflow list (shared accumulators, atomics; 0.3 % of
+// the entries at vertex_sampling=5).  Heavy / generic winners (code 255) are re-queried from global memory.
+constexpr int kIL = 32;            // interleaved light slots per part
+constexpr unsigned kNoVid = 0xffffu;
+constexpr int kOvPriv = 64;        // private overflow slots per warp; a sample that needs more spills to shared atomics
 
-// rare: winner is a heavy/generic vertex (or a light index that did not fit a byte): exact re-query, atomics
-__device__ __noinline__ void slow_pixel_grad(const SegSmem& sm, const int* __restrict__ idx, float* gacc, int p0, int p1,
-                                             int nl, float gx, float gy, int head, int ghead, float G) {
-  const int slot = slow_pixel_query(sm, p0, p1, nl, gx, gy, head, ghead);
-  if (slot < 0) return;
-  const float4 e = sm.ent[slot];
-  const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
-  const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
-  const float s = expf(-__fmul_rn(d, e.z));
-  const float coef = (d > 0.f) ? (-e.z * s * G) / d : 0.f;         // d(exp(-d w))/dp = -w s (p - g)/d
-  const int vid = (e.z == 1.0f) ? __float_as_int(e.w) : idx[__float_as_uint(e.w) & 0xffffu];
-  atomicAdd(&gacc[vid * 2], coef * du);
-  atomicAdd(&gacc[vid * 2 + 1], coef * dv);
+struct BwdSmem {
+  float2* lpos;          // [kIL][32]   (preceded by one readable row: index -1 = "none" reads it)
+  unsigned short* lvid;  // [kIL][32]
+  int* lcount;           // [32]
+  int* obase;            // [36]  overflow offsets of the parts (prefix of max(size_k - kIL, 0))
+  float2* opos;          // [OV]
+  float2* oacc;          // [OV]
+  unsigned short* ovid;  // [OV]  kNoVid = unused
+  float2* wacc;          // [nwarps][kIL][32]
+  float2* wov;           // [nwarps][kOvPriv]  private overflow accumulators, slots handed out per sample (odyn)
+  int* odyn;             // [32]  exclusive prefix of max(lcount_k - kIL, 0) for THIS sample
+};
+__host__ __device__ __forceinline__ size_t bwd_smem_bytes(int OV, int nwarps) {
+  const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
+  return 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + ov * 8 * 2 + ov * 2 +
+         (size_t)nwarps * (kIL * 32 + kOvPriv) * 8;
+}
+__device__ __forceinline__ BwdSmem carve_bwd(unsigned char* raw, int OV, int nwarps) {
+  BwdSmem b;
+  const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
+  size_t off = 256;
+  b.lpos = reinterpret_cast<float2*>(raw + off); off += (size_t)kIL * 32 * 8;
+  b.wacc = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kIL * 32 * 8;
+  b.wov = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kOvPriv * 8;
+  b.opos = reinterpret_cast<float2*>(raw + off); off += ov * 8;
+  b.oacc = reinterpret_cast<float2*>(raw + off); off += ov * 8;
+  b.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
+  b.odyn = reinterpret_cast<int*>(raw + off); off += 32 * 4;
+  b.obase = reinterpret_cast<int*>(raw + off); off += 36 * 4;
+  b.lvid = reinterpret_cast<unsigned short*>(raw + off); off += (size_t)kIL * 32 * 2;
+  b.ovid = reinterpret_cast<unsigned short*>(raw + off);
+  return b;
 }
 
-// Generic pixel walk of the backward (any wh): per-pixel bounds and row bookkeeping; the aligned path in the kernel is the
-// tuned one.
-template <bool C32>
-__device__ __noinline__ void generic_pixel_walk(const SegSmem& sm, const int* __restrict__ idx, float* gacc,
-                                                const unsigned char* __restrict__ sv, const float* __restrict__ g_n,
-                                                bool ld_g, bool live, int lane, int warp, int nwarps, int wh, int C, int p0,
-                                                int p1, int nl, int ghead, uint32_t ent_sa, uint32_t wacc_sa, int acc_cap,
-                                                const float4* ent_k) {
-  const int npx = wh * wh;
-  // Each warp owns a contiguous range of output pixels (row-major, rows already flipped: grid row = wh-1-row).
-  const int px0 = (int)(((long long)npx * warp) / nwarps), px1 = (int)(((long long)npx * (warp + 1)) / nwarps);
-  struct Batch { int code[kBatch]; float g[kBatch]; };
-  auto load_batch = [&](int base, Batch& bt) {
+// The light list of every part, in the forward's order (entries of the part's CSR segment with w == 1, compacted).
+__device__ void classify_light(const BwdSmem& b, const float* __restrict__ proj, const float* __restrict__ mask,
+                               const int* __restrict__ ptr, const int* __restrict__ idx, const int* __restrict__ obase,
+                               int P, int OV) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x < 32) b.lcount[threadIdx.x] = 0;
+  if (threadIdx.x < 36) b.obase[threadIdx.x] = obase[min((int)threadIdx.x, P)];
+  for (int i = threadIdx.x; i < OV; i += blockDim.x) { b.ovid[i] = (unsigned short)kNoVid; b.oacc[i] = make_float2(0.f, 0.f); }
+  for (int k = warp; k < P; k += nwarps) {
+    const int p0 = ptr[k], p1 = ptr[k + 1], ob = obase[k];
+    int nl = 0;
+    constexpr int kU = 4;                                  // chunks of 32 entries whose gather chains overlap
+    for (int base0 = p0; base0 < p1; base0 += 32 * kU) {
+      int vids[kU];
+      float us[kU], vv[kU], ws[kU];
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const bool in = base + j < px1;
-      bt.code[j] = in ? (int)sv[(size_t)(base + j) * 32] : 0;
-      bt.g[j] = (in && ld_g) ? g_n[(size_t)(base + j) * C] : 0.f;
-    }
-  };
-  Batch cur, nxt;
-  if (px0 < px1) load_batch(px0, cur);
-  int orow = px0 / wh, col = px0 - orow * wh;                       // output row / column of the batch's first pixel
-  for (int base = px0; base < px1; base += kBatch) {
-    if (base + kBatch < px1) load_batch(base + kBatch, nxt);        // next batch's loads fly while this one is consumed
-    unsigned slowmask = 0u;
-    int c = col, orw = orow;
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const float gx = (float)c, gy = (float)(wh - 1 - orw);        // small integers: exact in fp32
-      const int code = cur.code[j];
-      const float t0 = (code & 1) ? cur.g[j] : 0.f;                 // lane 0: gate * g_bg   (d bg / d s_k = -gate)
-      const float G = cur.g[j] - __shfl_sync(0xffffffffu, t0, 0);
-      const bool fast = live && code != 0 && code != 255;
-      if (live && code == 255) slowmask |= 1u << j;                 // rare exact re-query, deferred
-      const int li = fast ? code - 1 : 0;
-      const float2 e = lds_f2(ent_sa + (uint32_t)li * 16u);        // light entry (w == 1)
-      const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
-      const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
-      const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
-      const float s = ex2_approx((d2 * rs) * (-kLog2e));
-      const float coef = -(s * G) * rs;                             // -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0
-      if (fast) {
-        if (li < acc_cap) {                                         // private slot: this lane is its only writer
-          const uint32_t a_sa = wacc_sa + (uint32_t)li * 8u;
-          float2 a = lds_f2(a_sa);
-          a.x += coef * du; a.y += coef * dv;
-          sts_f2(a_sa, a);
-        } else {
-          const int vid = __float_as_int(ent_k[li].w);
-          atomicAdd(&gacc[vid * 2], coef * du); atomicAdd(&gacc[vid * 2 + 1], coef * dv);
-        }
+      for (int c = 0; c < kU; ++c) {
+        const int e = base0 + c * 32 + lane;
+        vids[c] = (e < p1) ? idx[e] : 0;
       }
-      if (++c == wh) { c = 0; ++orw; }
-    }
-    if (__any_sync(0xffffffffu, slowmask != 0u)) {                  // rare: heavy / generic winners, exact, atomics
-      int c2 = col, orw2 = orow;
-#pragma unroll 1
-      for (int j = 0; j < kBatch; ++j) {                            // warp-uniform loop: every lane takes the shuffle
-        const float t0 = (cur.code[j] & 1) ? cur.g[j] : 0.f;
-        const float G = cur.g[j] - __shfl_sync(0xffffffffu, t0, 0);
-        if ((slowmask >> j) & 1u) {
-          const int gr = wh - 1 - orw2;
-          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, (float)c2, (float)gr, sm.head[gr * wh + c2], ghead, G);
+#pragma unroll
+      for (int c = 0; c < kU; ++c) {
+        const bool in = base0 + c * 32 + lane < p1;
+        us[c] = in ? proj[vids[c] * 3] : 0.f;
+        vv[c] = in ? proj[vids[c] * 3 + 1] : 0.f;
+        ws[c] = in ? mask[vids[c]] : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < kU; ++c) {
+        if (base0 + c * 32 >= p1) break;
+        const bool light = (base0 + c * 32 + lane < p1) && (ws[c] == 1.0f);
+        const unsigned bl = __ballot_sync(0xffffffffu, light);
+        if (light) {
+          const int pos = nl + __popc(bl & ((1u << lane) - 1u));
+          if (pos < kIL) {
+            b.lpos[pos * 32 + k] = make_float2(us[c], vv[c]);
+            b.lvid[pos * 32 + k] = (unsigned short)vids[c];
+          } else {
+            b.opos[ob + pos - kIL] = make_float2(us[c], vv[c]);
+            b.ovid[ob + pos - kIL] = (unsigned short)vids[c];
+          }
         }
-        if (++c2 == wh) { c2 = 0; ++orw2; }
+        nl += __popc(bl);
       }
     }
-    col += kBatch;
-    while (col >= wh) { col -= wh; ++orow; }
-    cur = nxt;
+    if (lane == 0) b.lcount[k] = nl;
+  }
+}
+
+// rare: the forward's winner at this pixel was a heavy / generic vertex (or a light index that did not fit a byte):
+// exact weighted nearest-vertex re-query of part [p0,p1) straight from global memory, with the forward's rule -- the
+// light minimum over squared distances (lowest index on ties), beaten only by a strictly smaller d*w of another vertex.
+__device__ __noinline__ void slow_pixel_grad_global(const float* __restrict__ proj, const float* __restrict__ mask,
+                                                    const int* __restrict__ idx, int p0, int p1, float gx, float gy,
+                                                    float G, float* __restrict__ out) {
+  float best = CUDART_INF_F, xo = CUDART_INF_F;
+  int lv = -1, ov = -1;
+  for (int e = p0; e < p1; ++e) {
+    const int vid = idx[e];
+    const float w = mask[vid];
+    const float d2 = dist2(proj[vid * 3], proj[vid * 3 + 1], gx, gy);
+    if (w == 1.0f) {
+      if (d2 < best) { best = d2; lv = vid; }
+    } else {
+      const float xe = __fmul_rn(sqrtf(d2), w);
+      if (xe < xo) { xo = xe; ov = vid; }
+    }
+  }
+  const int vid = (ov >= 0 && xo < sqrtf(best)) ? ov : lv;
+  if (vid < 0) return;
+  const float w = mask[vid];
+  const float du = __fsub_rn(proj[vid * 3], gx), dv = __fsub_rn(proj[vid * 3 + 1], gy);
+  const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+  const float s = expf(-__fmul_rn(d, w));
+  const float coef = (d > 0.f) ? (-w * s * G) / d : 0.f;           // d(exp(-d w))/dp = -w s (p - g)/d
+  atomicAdd(&out[vid * 3], coef * du);
+  atomicAdd(&out[vid * 3 + 1], coef * dv);
+}
+
+// rare: light winner beyond the interleaved slots (a part with more than kIL visible vertices).  j = li - kIL.  The
+// first kOvPriv overflow slots of a sample are private to (warp, lane = part): plain read-modify-write; beyond that,
+// shared atomics.
+__device__ __forceinline__ void overflow_pixel_grad(const BwdSmem& b, float2* wov_w, int ob, int od, int j, float gx,
+                                                    float gy, float G) {
+  const float2 e = b.opos[ob + j];
+  const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
+  const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
+  const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
+  const float s = ex2_approx((d2 * rs) * (-kLog2e));
+  const float coef = (s * G) * (-rs);
+  if (od + j < kOvPriv) {
+    float2 a = wov_w[od + j];
+    a.x += coef * du; a.y += coef * dv;
+    wov_w[od + j] = a;
+  } else {
+    atomicAdd(&b.oacc[ob + j].x, coef * du);
+    atomicAdd(&b.oacc[ob + j].y, coef * dv);
   }
 }
 
 template <bool C32, bool ALIGNED>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(192, 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
-               const int* __restrict__ idx, int P, int E, int wh, float* __restrict__ g_projects) {
+               const int* __restrict__ idx, const int* __restrict__ obase, int P, int OV, int wh,
+               float* __restrict__ g_projects) {
   extern __shared__ __align__(16) unsigned char raw[];
-  const SegSmem sm = carve(raw, E, wh);
-  float* gacc = reinterpret_cast<float*>(sm.rest);                  // [Vs][2]
-  float2* wacc_all = reinterpret_cast<float2*>(gacc + (size_t)((Vs * 2 + 3) & ~3));   // [nwarps][kAccSlots]
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < Vs * 2; i += blockDim.x) gacc[i] = 0.f;
-  for (int i = threadIdx.x; i < nwarps * kAccSlots; i += blockDim.x) wacc_all[i] = make_float2(0.f, 0.f);
-  classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
-  const int ghead = *sm.ghead;
+  const BwdSmem b = carve_bwd(raw, OV, nwarps);
+  const float* proj_n = projects + (size_t)n * Vs * 3;
+  const float* mask_n = mask + (size_t)n * Vs;
+  float* out = g_projects + (size_t)n * Vs * 3;
+  for (int i = threadIdx.x; i < Vs * 3; i += blockDim.x) out[i] = 0.f;   // z and untouched vertices stay 0
+  for (int i = threadIdx.x; i < nwarps * (kIL * 32 + kOvPriv); i += blockDim.x) b.wacc[i] = make_float2(0.f, 0.f);   // + wov
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) reinterpret_cast<float2*>(raw)[i] = make_float2(0.f, 0.f);
+  classify_light(b, proj_n, mask_n, ptr, idx, obase, P, OV);
+  __syncthreads();
+  if (threadIdx.x < 32) {                                           // this sample's overflow slots, handed out in part order
+    const int c = max(b.lcount[threadIdx.x] - kIL, 0);
+    int sc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, sc, o);
+      if ((int)threadIdx.x >= o) sc += t;
+    }
+    b.odyn[threadIdx.x] = sc - c;
+  }
+  __syncthreads();
   const int C = C32 ? 32 : P + 1;
   const bool live = lane >= 1 && lane < C;                          // lane = channel; channel 0 carries the gate
   const int k = live ? lane - 1 : 0;
-  const int p0 = sm.pptr[k], p1 = sm.pptr[k + 1], nl = sm.lcount[k];
-  const float4* ent_k = sm.ent + p0;
-  float2* wacc = wacc_all + (size_t)warp * kAccSlots + sm.lbase[k]; // this lane's part, private to (warp, lane)
-  const uint32_t ent_sa = (uint32_t)__cvta_generic_to_shared(ent_k);   // shared-window addresses of the two hot arrays
-  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(wacc);
-  // light indices >= acc_cap (only possible when the sample has more than kAccSlots visible part vertices) go to
-  // shared atomics instead of the private slots
-  const int acc_cap = kAccSlots - sm.lbase[k];
+  const int p0 = ptr[k], p1 = ptr[k + 1];
+  const uint32_t lpos_sa = (uint32_t)__cvta_generic_to_shared(b.lpos) + (uint32_t)k * 8u;
+  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(b.wacc + (size_t)warp * kIL * 32) + (uint32_t)k * 8u;
+  const int ob = b.obase[k], od = b.odyn[k];
+  float2* wov_w = b.wov + (size_t)warp * kOvPriv;
   const int npx = wh * wh;
   const unsigned char* sv = saved + (size_t)n * npx * 32 + lane;
   const float* g_n = g_seg + (size_t)n * npx * C + (lane < C ? lane : 0);
   const bool ld_g = C32 || lane < C;
 
-  // more visible part vertices than private slots (never at vertex_sampling=5): the generic walk handles the spill
-  const bool overflow = sm.lbase[31] + sm.lcount[31] > kAccSlots;   // warp-uniform
-  if (ALIGNED && !overflow) {
-    // wh % 8 == 0: groups of 4 consecutive output pixels never straddle a row.  Each warp owns a contiguous range of
-    // groups; loads run one group ahead in two named register sets (no copies), pointers advance linearly.
-    const int nb = npx >> 2;
-    const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
-    const unsigned char* svp = sv + (size_t)b0 * 4 * 32;
-    const float* gp = g_n + (size_t)b0 * 4 * C;
-    int col = (b0 * 4) % wh;
-    float gy = (float)(wh - 1 - (b0 * 4) / wh);                     // grid row of the group (rows flipped, :68)
+  // Each warp owns a contiguous range of groups of 4 consecutive output pixels (row-major, rows already flipped: grid
+  // row = wh-1-row); loads run one group ahead in two named register sets (no copies), pointers advance linearly.
+  // ALIGNED (wh % 4 == 0): a group never straddles a row and there is no tail.
+  const int nb = (npx + 3) >> 2;
+  const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
+  const unsigned char* svp = sv + (size_t)b0 * 4 * 32;
+  const float* gp = g_n + (size_t)b0 * 4 * C;
+  int px = b0 * 4;                                                  // first pixel of the group being COMPUTED
+  int pxl = px;                                                     // first pixel of the group being LOADED
+  int col = px % wh;
+  float gy = (float)(wh - 1 - px / wh);                             // grid row of the group (rows flipped, :68)
 #define SEG_LOAD4(code, g)                                                                                             \
   do {                                                                                                                 \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
-      code[j] = (int)svp[j * 32];                                                                                      \
-      g[j] = ld_g ? gp[j * C] : 0.f;                                                                                   \
+      const bool in = ALIGNED || pxl + j < npx;                                                                        \
+      code[j] = in ? (int)svp[j * 32] : 0;                                                                             \
+      g[j] = (in && ld_g) ? gp[j * C] : 0.f;                                                                           \
     }                                                                                                                  \
-    svp += 4 * 32; gp += 4 * C;                                                                                        \
+    svp += 4 * 32; gp += 4 * C; pxl += 4;                                                                              \
   } while (0)
-#define SEG_COMPUTE4(code, g, back)                                                                                    \
+#define SEG_COMPUTE4(code, g)                                                                                          \
   do {                                                                                                                 \
-    const float gxb = (float)col;                                                                                      \
-    float cu[4], cv[4];                                                                                                \
+    float gxv[4], gyv[4];                                                                                              \
+    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
+      if (ALIGNED) { gxv[j] = (float)col + (float)j; gyv[j] = gy; }                                                    \
+      else { const int r = (px + j) / wh; gxv[j] = (float)(px + j - r * wh); gyv[j] = (float)(wh - 1 - r); }           \
+    }                                                                                                                  \
+    float cu[4], cv[4], Gv[4];                                                                                         \
     int li[4];                                                                                                         \
     /* (a) four pixels, mutually independent: the arithmetic of the four chains interleaves */                        \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
       const float t0 = (code[j] & 1) ? g[j] : 0.f;                 /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
-      const float G = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                          \
-      li[j] = (live ? code[j] : 0) - 1;                             /* -1 (none), 254 (re-query): harmless slots */    \
-      const float2 e = lds_f2_nv(ent_sa + (uint32_t)(li[j] * 16));                                                     \
-      const float du = __fsub_rn(e.x, gxb + (float)j), dv = __fsub_rn(e.y, gy);                                        \
+      Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                  \
+      li[j] = (live ? code[j] : 0) - 1;                             /* -1 none, >= kIL overflow, 254 re-query */       \
+      const float2 e = lds_f2_nv(lpos_sa + (uint32_t)(min(li[j], kIL - 1) * 256));                                     \
+      const float du = __fsub_rn(e.x, gxv[j]), dv = __fsub_rn(e.y, gyv[j]);                                            \
       const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));                                                \
       const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));                                                                \
       const float s = ex2_approx((d2 * rs) * (-kLog2e));                                                               \
-      const float coef = (s * G) * (-rs);                           /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
+      const float coef = (s * Gv[j]) * (-rs);                       /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
       cu[j] = coef * du; cv[j] = coef * dv;                                                                            \
     }                                                                                                                  \
     /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order */            \
+    const bool rare = __any_sync(0xffffffffu, max(max(li[0], li[1]), max(li[2], li[3])) >= kIL);                       \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
-      if ((unsigned)li[j] < 254u) {                                                                                    \
-        const uint32_t a_sa = wacc_sa + (uint32_t)li[j] * 8u;                                                          \
+      if ((unsigned)li[j] < (unsigned)kIL) {                                                                           \
+        const uint32_t a_sa = wacc_sa + (uint32_t)li[j] * 256u;                                                        \
         float2 a = lds_f2(a_sa);                                                                                       \
         a.x += cu[j]; a.y += cv[j];                                                                                    \
         sts_f2(a_sa, a);                                                                                               \
+      } else if (rare && li[j] >= kIL) {                            /* rare: overflow slot, or re-query (code 255) */  \
+        if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxv[j], gyv[j], Gv[j], out);             \
+        else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxv[j], gyv[j], Gv[j]);                                \
       }                                                                                                                \
     }                                                                                                                  \
-    if (__any_sync(0xffffffffu, max(max(li[0], li[1]), max(li[2], li[3])) == 254)) {   /* rare: heavy / generic */     \
-      const unsigned char* svb = svp - (back) * 4 * 32;             /* this group again, from memory: no indexed regs */ \
-      const float* gb = gp - (back) * 4 * C;                                                                           \
-      const int gr = (int)gy;                                                                                          \
-      _Pragma("unroll 1") for (int j = 0; j < 4; ++j) {             /* warp-uniform loop: every lane takes the shuffle */ \
-        const int cj = (int)svb[j * 32];                                                                               \
-        const float gj = ld_g ? gb[j * C] : 0.f;                                                                       \
-        const float t0 = (cj & 1) ? gj : 0.f;                                                                          \
-        const float G = gj - __shfl_sync(0xffffffffu, t0, 0);                                                          \
-        if (live && cj == 255)                                                                                         \
-          slow_pixel_grad(sm, idx, gacc, p0, p1, nl, (float)(col + j), gy, sm.head[gr * wh + col + j], ghead, G);      \
-      }                                                                                                                \
-    }                                                                                                                  \
-    col += 4;                                                                                                          \
-    if (col == wh) { col = 0; gy -= 1.0f; }                                                                            \
+    px += 4; col += 4;                                                                                                 \
+    if (ALIGNED && col == wh) { col = 0; gy -= 1.0f; }                                                                 \
   } while (0)
+  {
     int codeA[4], codeB[4];
     float gA[4], gB[4];
     const int nbw = b1 - b0;
     if (nbw > 0) SEG_LOAD4(codeA, gA);
     for (int i = 0; i < nbw; i += 2) {
-      const bool hasB = i + 1 < nbw, moreA = i + 2 < nbw;
+      const bool hasB = i + 1 < nbw;
       if (hasB) SEG_LOAD4(codeB, gB);
-      SEG_COMPUTE4(codeA, gA, hasB ? 2 : 1);                        // pointers are `back` groups past this one
+      SEG_COMPUTE4(codeA, gA);
       if (hasB) {
-        if (moreA) SEG_LOAD4(codeA, gA);
-        SEG_COMPUTE4(codeB, gB, moreA ? 2 : 1);
+        if (i + 2 < nbw) SEG_LOAD4(codeA, gA);
+        SEG_COMPUTE4(codeB, gB);
       }
     }
+  }
 #undef SEG_LOAD4
 #undef SEG_COMPUTE4
-  } else {
-    generic_pixel_walk<C32>(sm, idx, gacc, sv, g_n, ld_g, live, lane, warp, nwarps, wh, C, p0, p1, nl, ghead, ent_sa,
-                            wacc_sa, acc_cap, ent_k);
-  }
   __syncthreads();
-  // fold the warps' private slots into the per-vertex sums (a vertex may sit in more than one part)
-  const int nlight = min(sm.lbase[31] + sm.lcount[31], kAccSlots);
-  for (int li = threadIdx.x; li < nlight; li += blockDim.x) {
-    float su = 0.f, sv2 = 0.f;
-    for (int w = 0; w < nwarps; ++w) { const float2 a = wacc_all[(size_t)w * kAccSlots + li]; su += a.x; sv2 += a.y; }
-    int kk = 0;                                                     // part kk with lbase[kk] <= li < lbase[kk] + lcount[kk]
-    while (kk < 31 && li >= sm.lbase[kk + 1]) ++kk;
-    const int vid = __float_as_int(sm.ent[sm.pptr[kk] + (li - sm.lbase[kk])].w);
-    atomicAdd(&gacc[vid * 2], su); atomicAdd(&gacc[vid * 2 + 1], sv2);
+  // fold the warps' private slots and the overflow list into the output (a vertex may sit in more than one part)
+  for (int s = threadIdx.x; s < kIL * 32; s += blockDim.x) {
+    const int i = s >> 5, kk = s & 31;
+    if (kk < P && i < b.lcount[kk]) {
+      float su = 0.f, sv2 = 0.f;
+      for (int w = 0; w < nwarps; ++w) { const float2 a = b.wacc[(size_t)w * kIL * 32 + s]; su += a.x; sv2 += a.y; }
+      const int vid = b.lvid[s];
+      atomicAdd(&out[vid * 3], su); atomicAdd(&out[vid * 3 + 1], sv2);
+    }
   }
-  __syncthreads();
-  float* out = g_projects + (size_t)n * Vs * 3;
-  for (int i = threadIdx.x; i < Vs * 3; i += blockDim.x) {
-    const int v = i / 3, c = i - v * 3;
-    out[i] = (c < 2) ? gacc[v * 2 + c] : 0.f;                       // z receives no gradient from the rasteriser
+  for (int kk = threadIdx.x; kk < P; kk += blockDim.x) {
+    const int cnt = max(b.lcount[kk] - kIL, 0), obk = b.obase[kk], odk = b.odyn[kk];
+    for (int j = 0; j < cnt; ++j) {
+      float2 a = b.oacc[obk + j];
+      if (odk + j < kOvPriv)
+        for (int w = 0; w < nwarps; ++w) { const float2 t = b.wov[(size_t)w * kOvPriv + odk + j]; a.x += t.x; a.y += t.y; }
+      const int vid = b.ovid[obk + j];
+      atomicAdd(&out[vid * 3], a.x); atomicAdd(&out[vid * 3 + 1], a.y);
+    }
   }
 }
 
@@ -766,18 +810,21 @@ cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const 
 
 cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
                            const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st) {
-  const int warps = 8;
-  const size_t smem = seg_base_smem(p->E, wh) + (size_t)((Vs * 2 + 3) & ~3) * 4 + (size_t)warps * kAccSlots * 8;
+  if (Vs >= (int)kNoVid) return cudaErrorInvalidValue;              // vertex ids are kept as 16 bits
+  // the largest warp count whose blocks still fit three to an SM; at least 4
+  int warps = 6;
+  while (warps > 4 && 3 * (bwd_smem_bytes(p->ovf, warps) + 1024) > kMaxSmem + 1024) --warps;
+  const size_t smem = bwd_smem_bytes(p->ovf, warps);
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   LaunchScope scope(KID_SEG_BWD, st);
 #define SMPL_SEG_BWD(C32, AL)                                                                                          \
   do {                                                                                                                 \
     cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    seg_bwd_kernel<C32, AL><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->P, p->E, \
-                                                          wh, g_projects);                                             \
+    seg_bwd_kernel<C32, AL><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->obase, \
+                                                          p->P, p->ovf, wh, g_projects);                               \
   } while (0)
-  const bool c32 = p->P == 31, al = wh % 8 == 0;
+  const bool c32 = p->P == 31, al = wh % 4 == 0;
   if (c32 && al) SMPL_SEG_BWD(true, true);
   else if (c32) SMPL_SEG_BWD(true, false);
   else if (al) SMPL_SEG_BWD(false, true);
