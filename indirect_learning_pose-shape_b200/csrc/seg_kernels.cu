@@ -506,8 +506,10 @@ struct BwdSmem {
 };
 __host__ __device__ __forceinline__ size_t bwd_smem_bytes(int OV, int nwarps) {
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
-  return 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + ov * 8 * 2 + ov * 2 +
-         (size_t)nwarps * (kIL * 32 + kOvPriv) * 8;
+  const size_t need = 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + ov * 8 * 2 + ov * 2 +
+                      (size_t)nwarps * (kIL * 32 + kOvPriv) * 8;
+  const size_t floor_ = 256 + 256 * 256;   // a lane reads lpos row (code - 1) unclamped: rows -1 .. 254 must be mapped
+  return need > floor_ ? need : floor_;
 }
 __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* raw, int OV, int nwarps) {
   BwdSmem b;
@@ -561,8 +563,8 @@ __device__ void classify_light(const BwdSmem& b, const float* __restrict__ proj,
         if (light) {
           const int pos = nl + __popc(bl & ((1u << lane) - 1u));
           if (pos < kIL) {
-            b.lpos[pos * 32 + k] = make_float2(us[c], vv[c]);
-            b.lvid[pos * 32 + k] = (unsigned short)vids[c];
+            b.lpos[pos * 32 + k + 1] = make_float2(us[c], vv[c]);        // column = channel = part + 1
+            b.lvid[pos * 32 + k + 1] = (unsigned short)vids[c];
           } else {
             b.opos[ob + pos - kIL] = make_float2(us[c], vv[c]);
             b.ovid[ob + pos - kIL] = (unsigned short)vids[c];
@@ -659,8 +661,9 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const bool live = lane >= 1 && lane < C;                          // lane = channel; channel 0 carries the gate
   const int k = live ? lane - 1 : 0;
   const int p0 = ptr[k], p1 = ptr[k + 1];
-  const uint32_t lpos_sa = (uint32_t)__cvta_generic_to_shared(b.lpos) + (uint32_t)k * 8u;
-  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(b.wacc + (size_t)warp * kIL * 32) + (uint32_t)k * 8u;
+  // column = lane: lane 0 (the gate channel) and dead lanes own harmless columns of their own, so no lane needs masking
+  const uint32_t lpos_sa = (uint32_t)__cvta_generic_to_shared(b.lpos) + (uint32_t)lane * 8u;
+  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(b.wacc + (size_t)warp * kIL * 32) + (uint32_t)lane * 8u;
   const int ob = b.obase[k], od = b.odyn[k];
   float2* wov_w = b.wov + (size_t)warp * kOvPriv;
   const int npx = wh * wh;
@@ -701,8 +704,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
       const float t0 = (code[j] & 1) ? g[j] : 0.f;                 /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
       Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                  \
-      li[j] = (live ? code[j] : 0) - 1;                             /* -1 none, >= kIL overflow, 254 re-query */       \
-      const float2 e = lds_f2_nv(lpos_sa + (uint32_t)(min(li[j], kIL - 1) * 256));                                     \
+      li[j] = code[j] - 1;                                          /* -1 none, >= kIL overflow, 254 re-query */       \
+      const float2 e = lds_f2_nv(lpos_sa + (uint32_t)(li[j] * 256));   /* rows -1 .. 254 are inside the allocation */   \
       const float du = __fsub_rn(e.x, gxv[j]), dv = __fsub_rn(e.y, gyv[j]);                                            \
       const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));                                                \
       const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));                                                                \
@@ -711,14 +714,14 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       cu[j] = coef * du; cv[j] = coef * dv;                                                                            \
     }                                                                                                                  \
     /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order */            \
-    const bool rare = __any_sync(0xffffffffu, max(max(li[0], li[1]), max(li[2], li[3])) >= kIL);                       \
+    const bool rare = __any_sync(0xffffffffu, live && max(max(li[0], li[1]), max(li[2], li[3])) >= kIL);                       \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
       if ((unsigned)li[j] < (unsigned)kIL) {                                                                           \
         const uint32_t a_sa = wacc_sa + (uint32_t)li[j] * 256u;                                                        \
         float2 a = lds_f2(a_sa);                                                                                       \
         a.x += cu[j]; a.y += cv[j];                                                                                    \
         sts_f2(a_sa, a);                                                                                               \
-      } else if (rare && li[j] >= kIL) {                            /* rare: overflow slot, or re-query (code 255) */  \
+      } else if (rare && live && li[j] >= kIL) {                            /* rare: overflow slot, or re-query (code 255) */  \
         if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxv[j], gyv[j], Gv[j], out);             \
         else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxv[j], gyv[j], Gv[j]);                                \
       }                                                                                                                \
@@ -746,8 +749,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   __syncthreads();
   // fold the warps' private slots and the overflow list into the output (a vertex may sit in more than one part)
   for (int s = threadIdx.x; s < kIL * 32; s += blockDim.x) {
-    const int i = s >> 5, kk = s & 31;
-    if (kk < P && i < b.lcount[kk]) {
+    const int i = s >> 5, kk = (s & 31) - 1;                       // column = part + 1
+    if (kk >= 0 && kk < P && i < b.lcount[kk]) {
       float su = 0.f, sv2 = 0.f;
       for (int w = 0; w < nwarps; ++w) { const float2 a = b.wacc[(size_t)w * kIL * 32 + s]; su += a.x; sv2 += a.y; }
       const int vid = b.lvid[s];
