@@ -49,7 +49,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct SegSmem {
   float4* ent;     // [E]  light: {u, v, 1, vid}   heavy/generic: {u, v, w, entry | next << 16}
-  int* head;       // [wh*wh] first heavy slot of each pixel, -1 none
+  unsigned short* head;   // [wh*wh] first heavy slot of each pixel, kNone16 none (16 bits: shared memory is what caps occupancy)
   int* lcount;     // [32] light entries per part (packed at the front of the part's CSR segment)
   int* lbase;      // [32] exclusive prefix sum of lcount
   int* pptr;       // [36] the part table's CSR pointers (P+1 used)
@@ -58,6 +58,18 @@ struct SegSmem {
   int* nheavy;     // [1]  number of chained heavy entries
   unsigned char* rest;
 };
+
+// push `slot` on the 16-bit chain head of pixel `pix`; returns the previous head (kNone16 = none)
+__device__ __forceinline__ unsigned head_push(unsigned short* head, int pix, unsigned slot) {
+  unsigned* w = reinterpret_cast<unsigned*>(head) + (pix >> 1);
+  const unsigned sh = (pix & 1) * 16;
+  unsigned old = *w, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(w, assumed, (assumed & ~(0xffffu << sh)) | (slot << sh));
+  } while (old != assumed);
+  return (old >> sh) & 0xffffu;
+}
 
 __device__ __forceinline__ float dist2(float u, float v, float gx, float gy) {
   const float du = __fsub_rn(u, gx), dv = __fsub_rn(v, gy);
@@ -74,7 +86,7 @@ __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
   SegSmem sm;
   size_t off = 0;
   sm.ent = reinterpret_cast<float4*>(raw + off) + 1; off += (size_t)(E + 2) * 16;   // ent[-1], ent[E]: readable dummies
-  sm.head = reinterpret_cast<int*>(raw + off); off += ((size_t)wh * wh * 4 + 15) & ~(size_t)15;
+  sm.head = reinterpret_cast<unsigned short*>(raw + off); off += ((size_t)wh * wh * 2 + 15) & ~(size_t)15;
   sm.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.lbase = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.pptr = reinterpret_cast<int*>(raw + off); off += 36 * 4;
@@ -85,14 +97,14 @@ __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
   return sm;
 }
 size_t seg_base_smem(int E, int wh) {
-  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 4 + 15) & ~(size_t)15) + 2 * 32 * 4 + 2 * 36 * 4 + 16;
+  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 2 + 15) & ~(size_t)15) + 2 * 32 * 4 + 2 * 36 * 4 + 16;
 }
 
 // Split the sample's part vertices into weight classes (one warp per part, ballot compaction).
 __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, const float* __restrict__ mask,
                          const int* __restrict__ ptr, const int* __restrict__ idx, int P, int wh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < wh * wh; i += blockDim.x) sm.head[i] = -1;
+  for (int i = threadIdx.x; i < (wh * wh + 1) / 2; i += blockDim.x) reinterpret_cast<unsigned*>(sm.head)[i] = 0xffffffffu;
   if (threadIdx.x == 0) { *sm.ghead = -1; *sm.nheavy = 0; }
   if (threadIdx.x < 32) sm.lcount[threadIdx.x] = 0;
   if (threadIdx.x < 36) sm.pptr[threadIdx.x] = ptr[min((int)threadIdx.x, P)];
@@ -160,7 +172,7 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
                 best = fminf(best, dist2(l.x, l.y, pu, pv));
               }
               if (xh < sqrtf(best)) {
-                const unsigned next = (unsigned)atomicExch(&sm.head[(int)pv * wh + (int)pu], slot) & 0xffffu;
+                const unsigned next = head_push(sm.head, (int)pv * wh + (int)pu, (unsigned)slot);
                 sm.ent[slot].w = __uint_as_float((__float_as_uint(h.w) & 0xffffu) | (next << 16));
                 atomicAdd(sm.nheavy, 1);
               }
@@ -318,19 +330,29 @@ template <bool TRACK, bool CLAMP>
 __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsigned sh, float gx0, float gx1, float gy0,
                                           float gy1, float (&best)[kNB], unsigned (&barg)[kNB]) {
   const unsigned shmul = 1u << sh, wcode = (unsigned)(w * 32 + 1) << sh;
-  while (m) {
-    const unsigned b = bfind_u32(m);
-    m ^= 1u << b;
-    const float2 e = lds_f2(eb + b * 16u);
-    const float dxa = __fsub_rn(e.x, gx0), dxb = __fsub_rn(e.x, gx1);
-    const float dya = __fsub_rn(e.y, gy0), dyb = __fsub_rn(e.y, gy1);
+  if (!m) return;
+  // software-pipelined: the next survivor's coordinates are in flight while this one is compared
+  unsigned b = bfind_u32(m);
+  m ^= 1u << b;
+  float2 e = lds_f2_nv(eb + b * 16u);
+  for (;;) {
+    const unsigned bc = b;
+    const float2 ec = e;
+    const bool more = m != 0u;
+    if (more) {
+      b = bfind_u32(m);
+      m ^= 1u << b;
+      e = lds_f2_nv(eb + b * 16u);
+    }
+    const float dxa = __fsub_rn(ec.x, gx0), dxb = __fsub_rn(ec.x, gx1);
+    const float dya = __fsub_rn(ec.y, gy0), dyb = __fsub_rn(ec.y, gy1);
     const float ux0 = __fmul_rn(dxa, dxa), ux1 = __fmul_rn(dxb, dxb);
     const float vy0 = __fmul_rn(dya, dya), vy1 = __fmul_rn(dyb, dyb);
     float d2[kNB];
     d2[0] = __fadd_rn(ux0, vy0); d2[1] = __fadd_rn(ux1, vy0);
     d2[2] = __fadd_rn(ux0, vy1); d2[3] = __fadd_rn(ux1, vy1);
     if (TRACK) {
-      const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)b + 1, 255) << sh : b * shmul + wcode;
+      const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)bc + 1, 255) << sh : bc * shmul + wcode;
 #pragma unroll
       for (int q = 0; q < kNB; ++q) {
         const bool le = d2[q] <= best[q];
@@ -341,6 +363,7 @@ __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsign
 #pragma unroll
       for (int q = 0; q < kNB; ++q) best[q] = fminf(best[q], d2[q]);
     }
+    if (!more) break;
   }
 }
 
@@ -383,7 +406,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #pragma unroll
       for (int q = 0; q < kNB; ++q) {
         const int r = r0 + (q >> 1), c = c0 + (q & 1);
-        if (c < wh && r < wh) blk_slow |= sm.head[r * wh + c] >= 0;
+        if (c < wh && r < wh) blk_slow |= sm.head[r * wh + c] != kNone16;
       }
     }
     float S[kNB];
@@ -431,7 +454,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
             for (int q = 0; q < kNB; ++q) {
               const int r = r0 + (q >> 1), c = c0 + (q & 1);
               if (c < wh && r < wh) {
-                const int hd = any_heavy ? sm.head[r * wh + c] : -1;
+                const int hd = (any_heavy && sm.head[r * wh + c] != kNone16) ? (int)sm.head[r * wh + c] : -1;
                 if (hd >= 0 || ghead >= 0) {
                   const float ss = slow_pixel_score(sm, p0, p1, (q & 1) ? gx1 : gx0, (q >> 1) ? gy1 : gy0, hd, ghead, best[q]);
                   if (ss >= 0.f) { sc[q] = ss; barg[q] = 255u << sh; }
