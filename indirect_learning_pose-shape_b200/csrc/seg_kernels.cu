@@ -54,6 +54,7 @@ struct SegSmem {
   int* lbase;      // [32] exclusive prefix sum of lcount
   int* pptr;       // [36] the part table's CSR pointers (P+1 used)
   int* woff;       // [36] exclusive prefix sum of ceil(lcount / 32): offsets of the parts' survivor words
+  int4* pdesc;     // [32] per part {shared address of its first entry, survivor words, word offset, -}: one load in the hot path
   int* ghead;      // [1]  chain of generic slots, -1 none
   int* nheavy;     // [1]  number of chained heavy entries
   unsigned char* rest;
@@ -91,13 +92,14 @@ __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
   sm.lbase = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.pptr = reinterpret_cast<int*>(raw + off); off += 36 * 4;
   sm.woff = reinterpret_cast<int*>(raw + off); off += 36 * 4;
+  sm.pdesc = reinterpret_cast<int4*>(raw + off); off += 32 * 16;
   sm.ghead = reinterpret_cast<int*>(raw + off);
   sm.nheavy = sm.ghead + 1; off += 16;
   sm.rest = raw + off;
   return sm;
 }
 size_t seg_base_smem(int E, int wh) {
-  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 2 + 15) & ~(size_t)15) + 2 * 32 * 4 + 2 * 36 * 4 + 16;
+  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 2 + 15) & ~(size_t)15) + 2 * 32 * 4 + 2 * 36 * 4 + 32 * 16 + 16;
 }
 
 // Split the sample's part vertices into weight classes (one warp per part, ballot compaction).
@@ -194,6 +196,8 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
     }
     sm.lbase[threadIdx.x] = s - c;
     sm.woff[threadIdx.x] = sw - cw;
+    sm.pdesc[threadIdx.x] = make_int4((int)((uint32_t)__cvta_generic_to_shared(sm.ent) + (uint32_t)sm.pptr[min((int)threadIdx.x, 35)] * 16u),
+                                      cw, sw - cw, 0);
   }
   __syncthreads();
 }
@@ -393,7 +397,6 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   // per-lane staging of one chunk: stage[(sub*4 + q)*32 + lane]  (lane-contiguous: conflict-free, no sync needed)
   float* stage = reinterpret_cast<float*>(sm.rest + (((size_t)nwarps * KW * 4 + 15) & ~(size_t)15)) +
                  (size_t)warp * (8 * kNB * 32) + lane;
-  const uint32_t ent_sa = (uint32_t)__cvta_generic_to_shared(sm.ent);   // shared-window address of entry 0
 
   for (int t = t0 + warp; t < t1; t += nwarps) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
@@ -431,19 +434,22 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
             for (int q = 0; q < kNB; ++q) stage[(sub * kNB + q) * 32] = 0.f;
             continue;
           }
-          const int p0 = sm.pptr[ch - 1], p1 = sm.pptr[ch], nl = sm.lcount[ch - 1];
-          const unsigned* kwp = kw + sm.woff[ch - 1];
+          const int4 pd = sm.pdesc[ch - 1];                          // {entry address, survivor words, word offset}
           const unsigned sh = 8u * (unsigned)s4;
           float best[kNB];
           unsigned barg[kNB];                                        // arg-min code, already shifted to its byte
 #pragma unroll
           for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
           // survivors are visited from the highest index down and replace on <=, so the LOWEST index wins exact ties
-          for (int w = (nl + 31) >> 5; w-- > 0;) {
-            const unsigned m = kwp[w];                               // same address on every lane: broadcast
-            const uint32_t eb = ent_sa + (uint32_t)(p0 + w * 32) * 16u;
-            if (TRACK && w >= 7) scan_word<TRACK, true>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
-            else scan_word<TRACK, false>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
+          if (pd.y == 1) {                                           // at most 32 visible vertices: the common case
+            scan_word<TRACK, false>(kw[pd.z], (uint32_t)pd.x, 0, sh, gx0, gx1, gy0, gy1, best, barg);
+          } else {
+            for (int w = pd.y; w-- > 0;) {
+              const unsigned m = kw[pd.z + w];                       // same address on every lane: broadcast
+              const uint32_t eb = (uint32_t)pd.x + (uint32_t)(w * 32) * 16u;
+              if (TRACK && w >= 7) scan_word<TRACK, true>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
+              else scan_word<TRACK, false>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
+            }
           }
           float sc[kNB];
 #pragma unroll
@@ -456,7 +462,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
               if (c < wh && r < wh) {
                 const int hd = (any_heavy && sm.head[r * wh + c] != kNone16) ? (int)sm.head[r * wh + c] : -1;
                 if (hd >= 0 || ghead >= 0) {
-                  const float ss = slow_pixel_score(sm, p0, p1, (q & 1) ? gx1 : gx0, (q >> 1) ? gy1 : gy0, hd, ghead, best[q]);
+                  const float ss = slow_pixel_score(sm, sm.pptr[ch - 1], sm.pptr[ch], (q & 1) ? gx1 : gx0, (q >> 1) ? gy1 : gy0, hd, ghead, best[q]);
                   if (ss >= 0.f) { sc[q] = ss; barg[q] = 255u << sh; }
                 }
               }
