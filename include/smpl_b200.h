@@ -140,9 +140,10 @@ int smpl_b200_mask_fwd(const float* projects, int N, int Vs, float* mask, void* 
 
 /* ---- projects_to_seg (projects_to_seg.py:9-69) -------------------------------------------------------- */
 /* projects (N,Vs,3), mask (N,Vs) -> seg (N,wh,wh,num_parts+1): channel 0 background, rows flipped.
- * `saved` (nullable) receives what the backward needs instead of a second search: 32 bytes per pixel -- the clip
- * gate (0 <= sum_k s_k <= 1) and the arg-min of every part (index into the part's visible-vertex list; 0xff none,
- * 0xfe re-query) -- in an opaque, kernel-tile order.  Size: smpl_b200_seg_saved_bytes(); 16-byte aligned.
+ * `saved` (nullable) receives what the backward needs instead of a second search: 32 bytes per OUTPUT pixel, laid
+ * out like the segmentation itself ([n][row][col][32]) -- byte 0: bit 0 = the clip gate (0 <= sum_k s_k <= 1);
+ * byte 1+k: the arg-min of part k as (index into the part's visible-vertex list) + 1, 0 = none, 255 = re-query
+ * (heavy / generic winner or index >= 254).  Size: smpl_b200_seg_saved_bytes(); 16-byte aligned.
  * `seg` may be NULL when only `saved` is wanted. */
 size_t smpl_b200_seg_saved_bytes(int N, int img_wh);
 int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs,
