@@ -160,6 +160,19 @@ int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, f
 int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, int Vs, int img_wh,
                              float* g_projects, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the op right after the path: Reshape -> softmax -> categorical focal loss ------------------------------ */
+/* (model.py:119-120, focal_loss.py:10-48)  seg (num_pixels, C) scores, C <= 32; exactly one of
+ * y_true (num_pixels, C) float one-hot / soft labels and labels (num_pixels) uint8 class ids.
+ * loss[i] = sum_c w_c (1 - p_c)^gamma (-y_c log p_c), p = clip(softmax(seg_i), 1e-7, 1 - 1e-7);  class_weights: C device
+ * floats or NULL (ones; focal_loss.py:19-41 when weight_classes).  from_logits = 0: seg already holds probabilities.
+ * bwd: g_seg = g_loss[i] * d loss[i] / d seg (TF autodiff: closed clip interval). */
+int smpl_b200_focal_loss_fwd(const float* seg, const float* y_true, const uint8_t* labels, long long num_pixels,
+                             int num_classes, float gamma, const float* class_weights, int from_logits, float* loss,
+                             void* stream);
+int smpl_b200_focal_loss_bwd(const float* seg, const float* y_true, const uint8_t* labels, const float* g_loss,
+                             long long num_pixels, int num_classes, float gamma, const float* class_weights,
+                             int from_logits, float* g_seg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

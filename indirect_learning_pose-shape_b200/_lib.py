@@ -64,6 +64,10 @@ SIGNATURES = {
                                            C.c_void_p]),
     "smpl_b200_silhouette_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_size_t, C.c_void_p]),
+    "smpl_b200_focal_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_void_p]),
+    "smpl_b200_focal_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float,
+                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lock = threading.Lock()

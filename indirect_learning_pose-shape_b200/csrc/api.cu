@@ -28,7 +28,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // ---- built-in profiler: CUDA-event pairs around every launch, on the launching stream ---------------------------
 static const char* const kKernelNames[KID_COUNT] = {
     "pose_fwd", "blend_fwd", "lbs_fwd", "joints_reg", "lbs_bwd_vertex", "lbs_bwd_joint", "blend_bwd", "pose_bwd",
-    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd"};
+    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd"};
 struct ProfRecord { int kid; cudaEvent_t a, b; };
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mutex;
@@ -616,6 +616,32 @@ int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, i
   if (!projects || !g_sil || !g_projects || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   if (img_wh > 4096) { set_error("silhouette_bwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
   CHECK_LAUNCH(launch_sil_bwd(projects, g_sil, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_focal_loss_fwd(const float* seg, const float* y_true, const uint8_t* labels, long long num_pixels,
+                             int num_classes, float gamma, const float* class_weights, int from_logits, float* loss,
+                             void* stream) {
+  if (num_pixels == 0) return SMPL_B200_OK;
+  if (!seg || !loss || num_pixels < 0 || (!y_true) == (!labels)) {
+    set_error("focal_loss_fwd: null/invalid argument (exactly one of y_true / labels)"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (num_classes < 1 || num_classes > 32) { set_error("focal_loss_fwd: num_classes=%d unsupported (1..32)", num_classes); return SMPL_B200_ERR_UNSUPPORTED; }
+  CHECK_LAUNCH(launch_focal_loss_fwd(seg, y_true, labels, num_pixels, num_classes, gamma, class_weights, from_logits, loss,
+                                     (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_focal_loss_bwd(const float* seg, const float* y_true, const uint8_t* labels, const float* g_loss,
+                             long long num_pixels, int num_classes, float gamma, const float* class_weights,
+                             int from_logits, float* g_seg, void* stream) {
+  if (num_pixels == 0) return SMPL_B200_OK;
+  if (!seg || !g_loss || !g_seg || num_pixels < 0 || (!y_true) == (!labels)) {
+    set_error("focal_loss_bwd: null/invalid argument (exactly one of y_true / labels)"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (num_classes < 1 || num_classes > 32) { set_error("focal_loss_bwd: num_classes=%d unsupported (1..32)", num_classes); return SMPL_B200_ERR_UNSUPPORTED; }
+  CHECK_LAUNCH(launch_focal_loss_bwd(seg, y_true, labels, g_loss, num_pixels, num_classes, gamma, class_weights, from_logits,
+                                     g_seg, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 

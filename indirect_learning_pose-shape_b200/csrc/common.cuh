@@ -24,7 +24,7 @@ void count_launch();
 enum KernelId {
   KID_POSE_FWD = 0, KID_BLEND_FWD, KID_LBS_FWD, KID_JOINTS_REG, KID_LBS_BWD_VERTEX, KID_LBS_BWD_JOINT, KID_BLEND_BWD,
   KID_POSE_BWD, KID_PROJECT_FWD, KID_PROJECT_BWD, KID_MASK, KID_SEG_FWD, KID_SEG_BWD, KID_SIL_FWD, KID_SIL_BWD,
-  KID_COUNT
+  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_COUNT
 };
 // RAII scope around one kernel launch: counts it and, while profiling is enabled, brackets it with CUDA events
 // recorded on the launching stream.
@@ -152,6 +152,12 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
 cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, cudaStream_t st);
 cudaError_t launch_sil_bwd(const float* projects, const float* g_sil, int N, int Vs, int wh, float* g_projects,
                            cudaStream_t st);
+
+cudaError_t launch_focal_loss_fwd(const float* seg, const float* y_true, const uint8_t* labels, long long npix, int C,
+                                  float gamma, const float* class_w, int from_logits, float* loss, cudaStream_t st);
+cudaError_t launch_focal_loss_bwd(const float* seg, const float* y_true, const uint8_t* labels, const float* g_loss,
+                                  long long npix, int C, float gamma, const float* class_w, int from_logits, float* g_seg,
+                                  cudaStream_t st);
 
 // small device helpers
 __device__ __forceinline__ float warp_sum(float v) {

@@ -457,6 +457,78 @@ def load_mean_set_cam_params(smpl, img_wh, mean_params_path: Optional[str] = Non
 
 
 # ------------------------------------------------------------------------------------------------------------
+# the op right after the path: softmax (model.py:119-120) + categorical focal loss
+# ------------------------------------------------------------------------------------------------------------
+def focal_class_weights(num_classes: int = 32) -> np.ndarray:
+    """focal_loss.py:21-38."""
+    w = np.ones(num_classes, np.float32)
+    w[0] = 0.3
+    for c in (1, 2, 3, 4, 10, 12, 14, 15, 16, 17, 23, 25):
+        if c < num_classes:
+            w[c] = 2.0
+    return w
+
+
+class _FocalFn(torch.autograd.Function):
+    """seg scores (N, P, C) + labels -> per-pixel focal loss (N, P); focal_loss.py:12-46 (+ softmax, model.py:120)."""
+
+    @staticmethod
+    def forward(ctx, seg, y_true, labels, gamma: float, class_w, from_logits: bool):
+        lib = _lib.load()
+        seg = _check_cuda_f32(seg, "y_pred")
+        C_ = seg.shape[-1]
+        npix = seg.numel() // C_
+        with torch.cuda.device(seg.device):
+            loss = torch.empty(seg.shape[:-1], dtype=torch.float32, device=seg.device)
+            _lib.check(lib.smpl_b200_focal_loss_fwd(_ptr(seg), _ptr(y_true), _ptr(labels), npix, C_, float(gamma),
+                                                    _ptr(class_w), int(from_logits), _ptr(loss), _stream()),
+                       "smpl_b200_focal_loss_fwd")
+        ctx.gamma, ctx.from_logits = float(gamma), bool(from_logits)
+        ctx.save_for_backward(seg, y_true if y_true is not None else labels, class_w if class_w is not None else seg.new_empty(0))
+        ctx.soft = y_true is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        lib = _lib.load()
+        seg, lab, class_w = ctx.saved_tensors
+        g_loss = _check_cuda_f32(g_loss, "grad loss")
+        C_ = seg.shape[-1]
+        npix = seg.numel() // C_
+        with torch.cuda.device(seg.device):
+            g_seg = torch.empty_like(seg)
+            _lib.check(lib.smpl_b200_focal_loss_bwd(_ptr(seg), _ptr(lab) if ctx.soft else None,
+                                                    None if ctx.soft else _ptr(lab), _ptr(g_loss), npix, C_, ctx.gamma,
+                                                    _ptr(class_w) if class_w.numel() else None, int(ctx.from_logits),
+                                                    _ptr(g_seg), _stream()), "smpl_b200_focal_loss_bwd")
+        return g_seg, None, None, None, None, None
+
+
+def categorical_focal_loss(gamma=2.0, weight_classes=False, from_logits=True):
+    """focal_loss.py:10-48, same factory signature.  The returned ``loss(y_true, y_pred)`` gives the per-pixel loss
+    (N, img_wh^2) like the reference.  ``from_logits=True`` (default) takes the rasteriser's scores and fuses the
+    ``Activation('softmax')`` of model.py:120 into the kernel; ``False`` takes probabilities, like the reference's own
+    ``y_pred``.  ``y_true`` is the reference's one-hot / soft (N, img_wh^2, C) float tensor, or integer class ids
+    (N, img_wh^2) to save the 128-byte label row per pixel."""
+
+    def categorical_focal_loss_fixed(y_true, y_pred):
+        seg = _check_cuda_f32(y_pred, "y_pred")
+        if seg.dim() == 4:                                       # (N, wh, wh, C): the Reshape of model.py:119
+            seg = seg.reshape(seg.shape[0], -1, seg.shape[-1])
+        C_ = seg.shape[-1]
+        if y_true.dtype.is_floating_point:
+            yt = _check_cuda_f32(y_true.reshape(seg.shape), "y_true")
+            lab = None
+        else:
+            yt = None
+            lab = y_true.reshape(seg.shape[:-1]).to(device=seg.device, dtype=torch.uint8).contiguous()
+        cw = torch.as_tensor(focal_class_weights(C_), device=seg.device) if weight_classes else None
+        return _FocalFn.apply(seg, yt, lab, gamma, cw, from_logits)
+
+    return categorical_focal_loss_fixed
+
+
+# ------------------------------------------------------------------------------------------------------------
 # the whole path as one module (model.py:108-118 tail; + train_stage2_silhouette.py:84 silhouette branch)
 # ------------------------------------------------------------------------------------------------------------
 class SmplDecoder(torch.nn.Module):

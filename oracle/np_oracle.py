@@ -294,3 +294,36 @@ def decode(model, params, img_wh, vertex_sampling, part_indices, silhouette_wh=N
     if silhouette_wh:
         out["silhouette"] = projects_to_silhouette(pwd, silhouette_wh)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the op after the path: softmax (model.py:119-120) + categorical focal loss (focal_loss.py:10-48)
+# ---------------------------------------------------------------------------------------------------------------
+KERAS_EPSILON = 1e-7
+
+
+def focal_class_weights(num_classes=32, dt=np.float32):
+    """focal_loss.py:21-38: up-weight hands, elbows, knees, ankles, down-weight the background."""
+    w = np.ones(num_classes, dt)
+    w[0] = 0.3
+    for c in (1, 2, 3, 4, 10, 12, 14, 15, 16, 17, 23, 25):
+        if c < num_classes:        # the reference hard-codes 32 classes; narrower tables keep the same ids
+            w[c] = 2.0
+    return w
+
+
+def softmax_last_axis(x):
+    """model.py:120 Activation('softmax'): exp(x - max) / sum on the last axis (Keras / TF softmax)."""
+    e = np.exp(x - x.max(axis=-1, keepdims=True))
+    return e / e.sum(axis=-1, keepdims=True)
+
+
+def categorical_focal_loss(y_true, y_pred, gamma=2.0, weight_classes=False):
+    """focal_loss.py:12-46.  y_true, y_pred (N, img_wh^2, C); returns (N, img_wh^2)."""
+    dt = y_pred.dtype
+    y_pred = np.clip(y_pred, dt.type(KERAS_EPSILON), dt.type(1.0) - dt.type(KERAS_EPSILON))      # :16
+    cross_entropy = -y_true.astype(dt) * np.log(y_pred)                                           # :17
+    if weight_classes:
+        cross_entropy = cross_entropy * focal_class_weights(y_pred.shape[-1], dt)                 # :19-41
+    focal = np.power(dt.type(1.0) - y_pred, dt.type(gamma)) * cross_entropy                       # :44
+    return focal.sum(axis=2)                                                                      # :45

@@ -163,3 +163,15 @@ def decode(C: TorchSmplConstants, params, img_wh, vertex_sampling, part_indices,
     if silhouette_wh:
         out["silhouette"] = projects_to_silhouette(pwd, silhouette_wh)
     return out
+
+
+def softmax_focal_loss(y_true, seg, gamma=2.0, weight_classes=False, from_logits=True):
+    """model.py:119-120 softmax followed by focal_loss.py:12-46, with torch autograd standing in for TF's
+    (torch.clamp passes the gradient on the closed interval, like tf.clip_by_value)."""
+    dt = seg.dtype
+    y_pred = torch.softmax(seg, dim=-1) if from_logits else seg
+    y_pred = torch.clamp(y_pred, np_oracle.KERAS_EPSILON, 1.0 - np_oracle.KERAS_EPSILON)
+    cross_entropy = -y_true.to(dt) * torch.log(y_pred)
+    if weight_classes:
+        cross_entropy = cross_entropy * torch.as_tensor(np_oracle.focal_class_weights(seg.shape[-1], np.float64), dtype=dt)
+    return (torch.pow(1.0 - y_pred, gamma) * cross_entropy).sum(dim=2)

@@ -404,3 +404,43 @@ def test_errors(pkg, host_model):
     with pytest.raises((IOError, OSError)):
         pkg.SMPLLayer("./does_not_exist.pkl", device=dev()).build()
     assert layer(torch.zeros(0, 86, device=dev())).shape == (0, 6890, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# softmax + categorical focal loss (model.py:119-120, focal_loss.py:10-48)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,weighted,soft,from_logits", [(32, False, False, True), (32, True, True, True),
+                                                          (32, True, False, False), (20, True, True, True)])
+def test_focal_loss_forward_backward(pkg, C, weighted, soft, from_logits):
+    rng = np.random.default_rng(17)
+    n, wh = 3, 12
+    seg = rng.random((n, wh * wh, C)).astype(np.float32)
+    if not from_logits:
+        seg = np_oracle.softmax_last_axis(seg * 8).astype(np.float32)
+        seg[0, 0, :] = 0.0
+        seg[0, 0, 3] = 1.0                                          # saturated probabilities: the clip must gate
+    lab = rng.integers(0, C, (n, wh * wh))
+    if soft:
+        y = (0.9 * np.eye(C)[lab] + 0.1 / C).astype(np.float32)     # label smoothing: every class contributes
+    else:
+        y = np.eye(C, dtype=np.float32)[lab]
+    wgt = rng.standard_normal((n, wh * wh)).astype(np.float32)
+    x64 = torch.tensor(seg.astype(np.float64), requires_grad=True)
+    ref = torch_oracle.softmax_focal_loss(torch.tensor(y.astype(np.float64)), x64, 2.0, weighted, from_logits)
+    (ref * torch.tensor(wgt.astype(np.float64))).sum().backward()
+    if C == 32:                                                     # the reference's weight table is 32 classes wide
+        ref32 = np_oracle.categorical_focal_loss(y, np_oracle.softmax_last_axis(seg) if from_logits else seg, 2.0, weighted)
+    loss_fn = pkg.categorical_focal_loss(gamma=2.0, weight_classes=weighted, from_logits=from_logits)
+    x = t(seg).requires_grad_(True)
+    y_arg = t(y) if soft else torch.as_tensor(lab, device=dev())
+    got = loss_fn(y_arg, x)
+    assert tuple(got.shape) == (n, wh * wh)
+    (got * t(wgt)).sum().backward()
+    g = got.detach().cpu().numpy().astype(np.float64)
+    r = ref.detach().numpy()
+    assert np.abs(g - r).max() <= 2e-6 * max(1.0, np.abs(r).max())
+    if C == 32:
+        assert np.abs(g - ref32).max() <= 2e-6 * max(1.0, np.abs(ref32).max())
+    gg, gr = x.grad.cpu().numpy().astype(np.float64), x64.grad.numpy()
+    assert np.abs(gg - gr).max() <= 3e-6 * max(1.0, np.abs(gr).max())

@@ -157,3 +157,45 @@ def test_golden_vectors_no_drift(host_model, parts_by_vs, smpl_io):
     assert (out["mask"] != z["mask"]).mean() < 2e-3
     assert (out["seg"].argmax(-1) != z["seg_labels"]).mean() < 2e-3
     assert np.abs(out["silhouette"][..., 1] - z["sil"]).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# softmax + categorical focal loss (the op after the path; focal_loss.py:10-48)
+# ---------------------------------------------------------------------------------------------------------------
+def _focal_inputs(n=2, npix=40, C=32, seed=11):
+    rng = np.random.default_rng(seed)
+    seg = rng.random((n, npix, C)).astype(np.float64)           # rasteriser scores live in [0, 1]
+    lab = rng.integers(0, C, (n, npix))
+    y = np.eye(C)[lab]
+    return seg, y, lab
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_focal_loss_closed_form_and_twins(weighted):
+    seg, y, lab = _focal_inputs()
+    p = np_oracle.softmax_last_axis(seg)
+    got = np_oracle.categorical_focal_loss(y, p, 2.0, weighted)
+    # one-hot: only the true class survives the sum (focal_loss.py:45 comment)
+    pt = np.take_along_axis(p, lab[..., None], axis=2)[..., 0]
+    w = np_oracle.focal_class_weights(32, np.float64)[lab] if weighted else 1.0
+    assert np.allclose(got, w * (1 - pt) ** 2 * -np.log(pt), rtol=1e-12, atol=0)
+    tw = torch_oracle.softmax_focal_loss(torch.tensor(y), torch.tensor(seg), 2.0, weighted).numpy()
+    assert np.allclose(tw, got, rtol=1e-12, atol=1e-15)
+    f32 = np_oracle.categorical_focal_loss(y.astype(np.float32), np_oracle.softmax_last_axis(seg.astype(np.float32)), 2.0, weighted)
+    assert f32.dtype == np.float32 and np.allclose(f32, got, rtol=2e-5, atol=1e-6)
+
+
+def test_focal_loss_gradient_matches_finite_differences():
+    seg, y, _ = _focal_inputs(n=1, npix=6, C=8, seed=5)
+    x = torch.tensor(seg, requires_grad=True)
+    wgt = torch.tensor(np.random.default_rng(1).standard_normal((1, 6)))
+    (torch_oracle.softmax_focal_loss(torch.tensor(y), x, 2.0, True) * wgt).sum().backward()
+    g = x.grad.numpy()
+    eps = 1e-6
+    for idx in [(0, 0, 0), (0, 3, 5), (0, 5, 7)]:
+        sp, sm = seg.copy(), seg.copy()
+        sp[idx] += eps
+        sm[idx] -= eps
+        fp = (np_oracle.categorical_focal_loss(y, np_oracle.softmax_last_axis(sp), 2.0, True) * wgt.numpy()).sum()
+        fm = (np_oracle.categorical_focal_loss(y, np_oracle.softmax_last_axis(sm), 2.0, True) * wgt.numpy()).sum()
+        assert abs((fp - fm) / (2 * eps) - g[idx]) <= 1e-6 * max(1.0, abs(g[idx]))

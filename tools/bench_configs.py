@@ -5,6 +5,7 @@
       p50 / p99 over --reps launches (predict_realtime-shaped)
   c3  LBS + orthographic projection fwd+bwd, batch 4096, fp32 (outputs verts + projects, gradient from projects)
   c4  silhouette 256x256 fwd+bwd from projections (N,6890,3), batch --c4-batch (BASELINE: 8192)
+  f1   fused softmax + categorical focal loss fwd+bwd on a (16384,48,48,32) segmentation, uint8 labels
 """
 import argparse
 import importlib
@@ -107,6 +108,26 @@ def main():
             b = 1296616
             print(json.dumps({"config": "C4 silhouette 256x256 fwd+bwd from projections, N=%d" % n, "ms_per_step": ms,
                               "samples_per_s": n / ms * 1e3, "alg_bytes_per_sample": b,
+                              "frac_of_hbm_peak": b * n / (ms * 1e-3) / 1e9 / PEAK}))
+        elif cfg == "f1":
+            n, wh, C = 16384, 48, 32
+            seg = torch.rand((n, wh * wh, C), device=dev)
+            lab = torch.randint(0, C, (n, wh * wh), device=dev, dtype=torch.uint8)
+            loss_fn = pkg.categorical_focal_loss(gamma=2.0, weight_classes=True)
+            gl = torch.full((n, wh * wh), 1.0 / (n * wh * wh), device=dev)
+
+            def step():
+                x = seg.detach().requires_grad_(True)
+                loss_fn(lab, x).backward(gl)
+            ms = timed(step, args.steps, 3)
+            pkg.profile_enable(True); pkg.profile_collect()
+            for _ in range(5):
+                step()
+            pkg.profile_enable(False)
+            kernf = {k: round(t / n_, 3) for k, (n_, t) in pkg.profile_collect().items()}
+            b = wh * wh * (C * 4 + 1 + 4) + wh * wh * (C * 4 + 1 + 4 + C * 4)      # fwd: scores + label + loss; bwd: + g_loss + g_seg
+            print(json.dumps({"config": "F1 softmax + focal loss fwd+bwd, N=16384, 48x48x32, uint8 labels", "ms_per_step": ms,
+                              "samples_per_s": n / ms * 1e3, "alg_bytes_per_sample": b, "kernel_ms": kernf,
                               "frac_of_hbm_peak": b * n / (ms * 1e-3) / 1e9 / PEAK}))
 
 
