@@ -12,6 +12,7 @@ from .layers import (  # noqa: F401
     PartTable,
     SMPLLayer,
     SmplDecoder,
+    categorical_crossentropy,
     categorical_focal_loss,
     compute_mask,
     concat_mean_param,
@@ -26,6 +27,6 @@ from .layers import (  # noqa: F401
 from .sharding import all_gather_outputs, shard_bounds, shard_slice  # noqa: F401
 
 __all__ = ["SMPLLayer", "SmplDecoder", "orthographic_project", "compute_mask", "projects_to_seg",
-           "projects_to_silhouette", "categorical_focal_loss", "concat_mean_param", "set_cam_params", "load_mean_set_cam_params",
+           "projects_to_silhouette", "categorical_focal_loss", "categorical_crossentropy", "concat_mean_param", "set_cam_params", "load_mean_set_cam_params",
            "DeviceModel", "PartTable", "get_device_model", "get_part_table", "smpl_io", "SmplB200Error",
            "launch_count", "load_library", "profile_enable", "profile_collect", "shard_bounds", "shard_slice", "all_gather_outputs"]

@@ -528,6 +528,13 @@ def categorical_focal_loss(gamma=2.0, weight_classes=False, from_logits=True):
     return categorical_focal_loss_fixed
 
 
+def categorical_crossentropy(y_true, y_pred, from_logits=True):
+    """The silhouette branch's loss (train_stage2_silhouette.py:226-228, Keras 'categorical_crossentropy' on the
+    softmax(2) of the silhouette): -sum_c y_c log clip(p_c, eps, 1-eps) per pixel, i.e. the focal kernel with gamma = 0
+    and no class weights.  ``from_logits=True`` fuses the softmax of train_stage2_silhouette.py:85-86."""
+    return categorical_focal_loss(gamma=0.0, weight_classes=False, from_logits=from_logits)(y_true, y_pred)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # the whole path as one module (model.py:108-118 tail; + train_stage2_silhouette.py:84 silhouette branch)
 # ------------------------------------------------------------------------------------------------------------

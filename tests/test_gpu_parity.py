@@ -444,3 +444,22 @@ def test_focal_loss_forward_backward(pkg, C, weighted, soft, from_logits):
         assert np.abs(g - ref32).max() <= 2e-6 * max(1.0, np.abs(ref32).max())
     gg, gr = x.grad.cpu().numpy().astype(np.float64), x64.grad.numpy()
     assert np.abs(gg - gr).max() <= 3e-6 * max(1.0, np.abs(gr).max())
+
+
+@pytest.mark.gpu
+def test_silhouette_crossentropy(pkg):
+    """softmax(2) + Keras categorical_crossentropy on the silhouette (train_stage2_silhouette.py:85-86, 226-228)."""
+    rng = np.random.default_rng(23)
+    n, wh = 2, 16
+    sil = rng.random((n, wh, wh, 2)).astype(np.float32)
+    lab = rng.integers(0, 2, (n, wh * wh))
+    y = np.eye(2, dtype=np.float32)[lab]
+    x64 = torch.tensor(sil.reshape(n, wh * wh, 2).astype(np.float64), requires_grad=True)
+    p = torch.clamp(torch.softmax(x64, -1), 1e-7, 1 - 1e-7)
+    ref = -(torch.tensor(y.astype(np.float64)) * torch.log(p)).sum(-1)              # keras.losses.categorical_crossentropy
+    ref.sum().backward()
+    x = t(sil).requires_grad_(True)
+    got = pkg.categorical_crossentropy(t(y), x)
+    got.sum().backward()
+    assert np.abs(got.detach().cpu().numpy() - ref.detach().numpy()).max() <= 2e-6
+    assert np.abs(x.grad.cpu().numpy().reshape(n, wh * wh, 2) - x64.grad.numpy()).max() <= 3e-6
