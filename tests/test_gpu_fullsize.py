@@ -1,0 +1,90 @@
+"""Full-size runs (BASELINE.json configs C5 and C4) checked through size-independent properties.
+
+The oracle evaluates O(wh^2 V) pairs per sample and cannot run 16384 samples in seconds, so at full size the CUDA
+path is checked against ITSELF at a size the parity tests already pin to the oracle, and against identities of the
+reference arithmetic:
+  * batch invariance  -- every op of the path is per sample, so sample i of the 16384-batch must equal the
+    same sample decoded in a batch of 64 (the regime tests/test_gpu_parity.py compares with the oracle);
+  * linearity of the backward in the upstream gradient -- doubling g doubles every partial sum exactly;
+  * channel identities -- seg[..., 0] = 1 - clip(sum_k seg[..., 1+k], 0, 1) (projects_to_seg.py:61-67),
+    sil[..., 0] + sil[..., 1] = 1 (projects_to_silhouette.py:40-41).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def test_c5_full_batch_properties(pkg, host_model, parts_by_vs, make_params):
+    N, wh, vs = 16384, 48, 5
+    params = torch.as_tensor(make_params(N, wh, seed=0), device=dev())
+    dec = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev())
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    g = torch.randn((N, wh, wh, 32), device=dev(), generator=gen)
+
+    x = params.clone().requires_grad_(True)
+    out = dec(x)
+    seg = out["seg"]
+    seg.backward(g)
+    grad1 = x.grad.clone()
+    seg = seg.detach()
+
+    # channel identity on every pixel of every sample
+    s = seg[..., 1:].sum(-1)
+    bg = 1.0 - s.clamp(0.0, 1.0)
+    assert float((seg[..., 0] - bg).abs().max()) <= 4e-6
+    assert float(seg.min()) >= 0.0 and float(seg.max()) <= 1.0
+    assert bool(torch.isfinite(grad1).all())
+
+    # batch invariance on a strided subset (forward outputs bit-identical: each sample is its own block)
+    idx = torch.arange(0, N, N // 64, device=dev())[:64]
+    xs = params[idx].clone().requires_grad_(True)
+    outs = dec(xs)
+    assert torch.equal(outs["projects"], out["projects"][idx])
+    assert torch.equal(outs["mask"], out["mask"][idx])
+    assert torch.equal(outs["seg"], seg[idx])
+    assert float((outs["verts"] - out["verts"][idx]).abs().max()) <= 1e-6      # the blend GEMM tiles the batch
+    outs["seg"].backward(g[idx])
+    scale = float(grad1[idx].abs().max())
+    assert float((xs.grad - grad1[idx]).abs().max()) <= 2e-5 * scale
+
+    # linearity: g -> 2 g scales every product and partial sum by exactly 2
+    x2 = params.clone().requires_grad_(True)
+    dec(x2)["seg"].backward(2.0 * g)
+    assert float((x2.grad - 2.0 * grad1).abs().max()) <= 1e-6 * float(grad1.abs().max())
+
+
+def test_c4_silhouette_large_batch_properties(pkg, host_model, make_params):
+    wh, n_src, N = 256, 32, 1024                     # BASELINE's batch is 8192; 1024 keeps the round-end GPU tier short
+    dec = pkg.SmplDecoder(host_model, wh, None, device=dev())
+    with torch.no_grad():
+        pr_src = dec(torch.as_tensor(make_params(n_src, wh, seed=5), device=dev()), seg=False)["projects"]
+    pr = pr_src.repeat(N // n_src, 1, 1).contiguous()
+    gen = torch.Generator(device=dev()).manual_seed(4)
+    g = torch.randn((N, wh, wh, 2), device=dev(), generator=gen)
+    x = pr.clone().requires_grad_(True)
+    sil = pkg.projects_to_silhouette(x, wh)
+    sd = sil.detach()
+    assert float((sd[..., 0] + sd[..., 1] - 1.0).abs().max()) <= 1.2e-7
+    assert float(sd.min()) >= 0.0 and float(sd.max()) <= 1.0
+    # replicas of the same sample are bit-identical (per-sample blocks), whatever their position in the batch
+    assert torch.equal(sd[:n_src], sd[N - n_src:])
+    sil.backward(g)
+    g1 = x.grad.clone()
+    sil = sil.detach()
+    assert bool(torch.isfinite(g1).all()) and float(g1[..., 2].abs().max()) == 0.0
+    # batch invariance against a small launch (the tile split over gridDim.y differs below 296 samples)
+    xs = pr[:8].clone().requires_grad_(True)
+    sils = pkg.projects_to_silhouette(xs, wh)
+    assert torch.equal(sils, sil[:8])
+    sils.backward(g[:8])
+    assert float((xs.grad - g1[:8]).abs().max()) <= 1e-5 * float(g1[:8].abs().max())
+    # linearity in the upstream gradient
+    x2 = pr.clone().requires_grad_(True)
+    pkg.projects_to_silhouette(x2, wh).backward(2.0 * g)
+    assert float((x2.grad - 2.0 * g1).abs().max()) <= 1e-6 * float(g1.abs().max())
