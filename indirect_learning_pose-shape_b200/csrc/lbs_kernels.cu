@@ -131,6 +131,76 @@ lbs_fwd_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A
   }
 }
 
+// Warp-independent variant of the forward (the one launched): each warp owns 32 vertices (96 floats = 384 B per sample)
+// and runs its own cp.async ring, so the only block-wide barrier is the one that publishes the group's bone transforms.
+// (The block-synchronous kernel above spent 2.4 of ~11 warp-issue-slots at barriers: three per sample and 3 KB moved
+// between them.)
+constexpr int kWG = 16;          // samples per block
+template <int KW>
+__global__ void __launch_bounds__(kChunk)
+lbs_fwd_warp_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A, const float* __restrict__ params,
+                    int N, int V, const uint8_t* __restrict__ lbs_idx, const float* __restrict__ lbs_w,
+                    float* __restrict__ verts, float* __restrict__ projects, int vs, int Vs) {
+  __shared__ __align__(16) float As[kWG * kARow];
+  __shared__ float cam[kWG * 4];
+  __shared__ __align__(16) float ring[kChunk / 32][kLbsStages][96];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.y * kWG;
+  const int rows = min(kWG, N - n0);
+  const int v = blockIdx.x * kChunk + tid;
+  const bool valid = v < V;
+  const int colw = (blockIdx.x * kChunk + warp * 32) * 3;          // this warp's first column of v_posed / verts
+  auto issue = [&](int s) {
+    if (s < rows && lane < 24) cp_async16(&ring[warp][s % kLbsStages][lane * 4], vp + (size_t)(n0 + s) * LD + colw + lane * 4);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kLbsStages - 1; ++s) issue(s);
+  {
+    const float4* src = reinterpret_cast<const float4*>(A + (size_t)n0 * kARow);
+    float4* dst = reinterpret_cast<float4*>(As);
+    for (int i = tid; i < rows * (kARow / 4); i += kChunk) dst[i] = src[i];
+    if (tid < rows * 4) cam[tid] = params[(size_t)(n0 + (tid >> 2)) * kParams + (tid & 3)];
+  }
+  const Skin<KW> skin = load_skin<KW>(lbs_idx, lbs_w, valid ? v : 0);
+  const bool sampled = valid && projects && (v % vs == 0);
+  const bool need = valid && (verts || sampled);
+  const int q = v / vs;
+  const int lim = (V * 3 - colw) / 2;                              // float2 slots of this warp's slice that exist (V*3, colw even)
+  __syncthreads();                                                 // As / cam published; the only block-wide barrier
+  for (int s = 0; s < rows; ++s) {
+    const int n = n0 + s;
+    issue(s + kLbsStages - 1);                                     // keeps kLbsStages-1 slices in flight behind this one
+    cp_async_wait<kLbsStages - 1>();
+    __syncwarp();                                                  // slice s has landed for the whole warp
+    float* st = ring[warp][s % kLbsStages];
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (need) {
+      const float x = st[lane * 3], y = st[lane * 3 + 1], z = st[lane * 3 + 2];
+      float T[12];
+      blend_T<KW>(skin, As + s * kARow, T);
+      ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+      oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+      oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+      if (sampled) {                                               // projection.py:77-79: multiply, then add (two roundings)
+        float* p = projects + ((size_t)n * Vs + q) * 3;
+        p[0] = __fadd_rn(cam[s * 4 + 2], __fmul_rn(ox, cam[s * 4 + 0]));
+        p[1] = __fadd_rn(cam[s * 4 + 3], __fmul_rn(oy, cam[s * 4 + 1]));
+        p[2] = oz;
+      }
+    }
+    if (verts) {
+      __syncwarp();                                                // every lane has read its input before the slot is reused
+      st[lane * 3] = ox; st[lane * 3 + 1] = oy; st[lane * 3 + 2] = oz;
+      __syncwarp();
+      float2* dst = reinterpret_cast<float2*>(verts + (size_t)n * V * 3 + colw);
+      if (lane < lim) dst[lane] = reinterpret_cast<const float2*>(st)[lane];
+      if (lane < 16 && lane + 32 < lim) dst[lane + 32] = reinterpret_cast<const float2*>(st)[lane + 32];
+    }
+    __syncwarp();                                                  // the issue() of the next iteration overwrites the slot read 1 ring-turn ago
+  }
+}
+
 // Gradient arriving at vertex v of sample n: dense g_verts plus the projection's adjoint at sampled vertices.
 __device__ __forceinline__ void vertex_grad(const float* __restrict__ g_verts, const float* __restrict__ g_projects,
                                             int n, int v, int V, int vs_proj, int Vs_proj, float ku, float kv,
@@ -439,11 +509,11 @@ int lbs_bwd_cam_chunks(int Vp) { return (Vp + kChunk - 1) / kChunk; }
 cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
                            float* verts, float* projects, int vs, cudaStream_t st) {
   const int V = m->V, Vs = (V + vs - 1) / vs;
-  dim3 grid((V + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
+  dim3 grid((V + kChunk - 1) / kChunk, (N + kWG - 1) / kWG);
   LaunchScope scope(KID_LBS_FWD, st);
 #define SMPL_LBS_FWD(KW)                                                                                          \
-  lbs_fwd_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, verts, projects, \
-                                              vs, Vs)
+  lbs_fwd_warp_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, verts,    \
+                                                   projects, vs, Vs)
   if (m->KW == 4) SMPL_LBS_FWD(4);
   else if (m->KW == 8) SMPL_LBS_FWD(8);
   else SMPL_LBS_FWD(24);
