@@ -168,8 +168,11 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
           if (pu >= 0.f && pu <= (float)(wh - 1) && pv >= 0.f && pv <= (float)(wh - 1)) {
             const float xh = __fmul_rn(sqrtf(dist2(h.x, h.y, pu, pv)), h.z);
             if (xh <= kDropX) {
+              // the vertex wins iff xh < sqrt(min_i d2_i); one light vertex with d2 <= xh^2 already settles it (sqrtf is
+              // correctly rounded, so sqrtf(fl(xh*xh)) == xh and the early exit cannot change the comparison)
+              const float xh2 = __fmul_rn(xh, xh);
               float best = CUDART_INF_F;
-              for (int i = 0; i < nl; ++i) {
+              for (int i = 0; i < nl && best > xh2; ++i) {
                 const float4 l = sm.ent[p0 + i];
                 best = fminf(best, dist2(l.x, l.y, pu, pv));
               }
