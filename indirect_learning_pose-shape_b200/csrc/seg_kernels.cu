@@ -43,8 +43,6 @@ namespace {
 constexpr float kHeavyMin = 256.0f;
 constexpr float kDropX = 110.0f;      // exp(-x) == 0 in fp32 (denormals included) for x > 103.98
 constexpr unsigned kNone16 = 0xffffu;
-constexpr int kArgNone = 0xff;        // saved byte: the part has no vertex that reaches this pixel (zero gradient)
-constexpr int kArgSlow = 0xfe;        // saved byte: winner is a heavy/generic vertex or index >= 254: re-query
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct SegSmem {
@@ -75,12 +73,6 @@ __device__ __forceinline__ unsigned head_push(unsigned short* head, int pix, uns
 __device__ __forceinline__ float dist2(float u, float v, float gx, float gy) {
   const float du = __fsub_rn(u, gx), dv = __fsub_rn(v, gy);
   return __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
-}
-
-// exp(-sqrt(d2)) for the light class, fast path (see header).  d2 = +inf (empty part) -> 0.
-__device__ __forceinline__ float score_from_d2(float d2) {
-  const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));            // d2 == 0 -> 0 ; inf*0 is NaN, handled below
-  return (d2 < CUDART_INF_F) ? exp2f(-d * kLog2e) : 0.f;     // exp2f lowers to ex2.approx with a range fix-up
 }
 
 __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
