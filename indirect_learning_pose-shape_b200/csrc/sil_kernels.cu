@@ -163,7 +163,8 @@ __device__ __forceinline__ void warp_argmin(float& d, float& u, float& v) {
   for (int o = 16; o > 0; o >>= 1) {
     const float d2 = __shfl_xor_sync(0xffffffffu, d, o), u2 = __shfl_xor_sync(0xffffffffu, u, o),
                 v2 = __shfl_xor_sync(0xffffffffu, v, o);
-    if (d2 < d) { d = d2; u = u2; v = v2; }
+    // a total order (distance, then coordinates): on exact ties every lane ends with the SAME vertex
+    if (d2 < d || (d2 == d && (u2 < u || (u2 == u && v2 < v)))) { d = d2; u = u2; v = v2; }
   }
 }
 
