@@ -326,43 +326,48 @@ __device__ __forceinline__ void prune_tile(const SegSmem& sm, unsigned* kw, int 
 // its arg-min, (index + 1) << sh.  CLAMP: indices >= 254 do not fit a byte and are recorded as 255 (re-queried by the
 // backward); only words 7 and up can hold them.
 template <bool TRACK, bool CLAMP>
+__device__ __forceinline__ void compare_vertex(float2 e, unsigned b, int w, unsigned sh, unsigned shmul, unsigned wcode,
+                                               float gx0, float gx1, float gy0, float gy1, float (&best)[kNB],
+                                               unsigned (&barg)[kNB]) {
+  const float dxa = __fsub_rn(e.x, gx0), dxb = __fsub_rn(e.x, gx1);
+  const float dya = __fsub_rn(e.y, gy0), dyb = __fsub_rn(e.y, gy1);
+  const float ux0 = __fmul_rn(dxa, dxa), ux1 = __fmul_rn(dxb, dxb);
+  const float vy0 = __fmul_rn(dya, dya), vy1 = __fmul_rn(dyb, dyb);
+  float d2[kNB];
+  d2[0] = __fadd_rn(ux0, vy0); d2[1] = __fadd_rn(ux1, vy0);
+  d2[2] = __fadd_rn(ux0, vy1); d2[3] = __fadd_rn(ux1, vy1);
+  if (TRACK) {
+    const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)b + 1, 255) << sh : b * shmul + wcode;
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) {
+      const bool le = d2[q] <= best[q];
+      barg[q] = le ? vcode : barg[q];
+      best[q] = le ? d2[q] : best[q];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) best[q] = fminf(best[q], d2[q]);
+  }
+}
+
+template <bool TRACK, bool CLAMP>
 __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsigned sh, float gx0, float gx1, float gy0,
                                           float gy1, float (&best)[kNB], unsigned (&barg)[kNB]) {
   const unsigned shmul = 1u << sh, wcode = (unsigned)(w * 32 + 1) << sh;
-  if (!m) return;
-  // software-pipelined: the next survivor's coordinates are in flight while this one is compared
-  unsigned b = bfind_u32(m);
-  m ^= 1u << b;
-  float2 e = lds_f2_nv(eb + b * 16u);
-  for (;;) {
-    const unsigned bc = b;
-    const float2 ec = e;
-    const bool more = m != 0u;
-    if (more) {
-      b = bfind_u32(m);
-      m ^= 1u << b;
-      e = lds_f2_nv(eb + b * 16u);
-    }
-    const float dxa = __fsub_rn(ec.x, gx0), dxb = __fsub_rn(ec.x, gx1);
-    const float dya = __fsub_rn(ec.y, gy0), dyb = __fsub_rn(ec.y, gy1);
-    const float ux0 = __fmul_rn(dxa, dxa), ux1 = __fmul_rn(dxb, dxb);
-    const float vy0 = __fmul_rn(dya, dya), vy1 = __fmul_rn(dyb, dyb);
-    float d2[kNB];
-    d2[0] = __fadd_rn(ux0, vy0); d2[1] = __fadd_rn(ux1, vy0);
-    d2[2] = __fadd_rn(ux0, vy1); d2[3] = __fadd_rn(ux1, vy1);
-    if (TRACK) {
-      const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)bc + 1, 255) << sh : bc * shmul + wcode;
-#pragma unroll
-      for (int q = 0; q < kNB; ++q) {
-        const bool le = d2[q] <= best[q];
-        barg[q] = le ? vcode : barg[q];
-        best[q] = le ? d2[q] : best[q];
-      }
+  // survivors two at a time: both coordinate loads are in flight before either vertex is compared
+  while (m) {
+    const unsigned b0 = bfind_u32(m);
+    m ^= 1u << b0;
+    const float2 e0 = lds_f2_nv(eb + b0 * 16u);
+    if (m) {
+      const unsigned b1 = bfind_u32(m);
+      m ^= 1u << b1;
+      const float2 e1 = lds_f2_nv(eb + b1 * 16u);
+      compare_vertex<TRACK, CLAMP>(e0, b0, w, sh, shmul, wcode, gx0, gx1, gy0, gy1, best, barg);
+      compare_vertex<TRACK, CLAMP>(e1, b1, w, sh, shmul, wcode, gx0, gx1, gy0, gy1, best, barg);
     } else {
-#pragma unroll
-      for (int q = 0; q < kNB; ++q) best[q] = fminf(best[q], d2[q]);
+      compare_vertex<TRACK, CLAMP>(e0, b0, w, sh, shmul, wcode, gx0, gx1, gy0, gy1, best, barg);
     }
-    if (!more) break;
   }
 }
 
