@@ -229,7 +229,6 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
                       float* __restrict__ g_cam) {
   __shared__ __align__(16) float As[kGroup * kARow];
   __shared__ float cam[kGroup * 4];
-  __shared__ float red[kChunk / 32][4];
   const int tid = threadIdx.x;
   const int n0 = blockIdx.y * kGroup;
   const int rows = min(kGroup, N - n0);
@@ -275,20 +274,13 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
         if (g_vp_lo) g_vp_lo[(size_t)n * gvp_ld + c] = 0.f;
       }
     }
+    // per-warp partial sums of the camera gradient go straight to their own plane: no block barrier inside the sample
+    // loop (pose_bwd adds the planes)
 #pragma unroll
     for (int k = 0; k < 4; ++k) c4[k] = warp_sum(c4[k]);
-    if ((tid & 31) == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) red[tid >> 5][k] = c4[k];
-    }
-    __syncthreads();
-    if (tid < 4) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kChunk / 32; ++w) t += red[w][tid];
-      g_cam[((size_t)blockIdx.x * N + n) * 4 + tid] = t;
-    }
-    __syncthreads();
+    if ((tid & 31) == 0)
+      *reinterpret_cast<float4*>(g_cam + (((size_t)blockIdx.x * (kChunk / 32) + (tid >> 5)) * N + n) * 4) =
+          make_float4(c4[0], c4[1], c4[2], c4[3]);
   }
 }
 
@@ -504,7 +496,7 @@ joints_reg_kernel(const float* __restrict__ verts, int N, int V, int R_used, con
 
 }  // namespace
 
-int lbs_bwd_cam_chunks(int Vp) { return (Vp + kChunk - 1) / kChunk; }
+int lbs_bwd_cam_chunks(int Vp) { return ((Vp + kChunk - 1) / kChunk) * (kChunk / 32); }   // one plane per warp of the vertex kernel
 
 cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
                            float* verts, float* projects, int vs, cudaStream_t st) {
@@ -546,7 +538,7 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
 #undef SMPL_LBS_BWD_S
     return cudaGetLastError();
   }
-  *cam_chunks = (Vp + kChunk - 1) / kChunk;
+  *cam_chunks = lbs_bwd_cam_chunks(Vp);
   dim3 grid((Vp + kChunk - 1) / kChunk, (N + kGroup - 1) / kGroup);
   cudaError_t e;
   {
