@@ -310,7 +310,7 @@ def test_full_path_dense_batch(pkg, host_model, parts_by_vs, make_params, n):
 # ---------------------------------------------------------------------------------------------------------------
 # silhouette
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,wh,vs", [(2, 48, None), (2, 64, 5), (1, 256, None), (1, 100, 2)])
+@pytest.mark.parametrize("n,wh,vs", [(2, 48, None), (2, 64, 5), (1, 256, None), (1, 100, 2), (2, 33, 5), (1, 131, 5)])
 def test_silhouette_forward(pkg, host_model, make_params, n, wh, vs):
     p, pr, _ = _oracle_inputs(host_model, make_params, n, wh, vs, seed=51)
     ref = np_oracle.projects_to_silhouette(pr, wh)
@@ -333,7 +333,7 @@ def test_silhouette_scattered_points(pkg):
     assert np.abs(got - ref).max() <= TOL_SCORE
 
 
-@pytest.mark.parametrize("n,wh,vs", [(2, 48, None), (1, 128, 5)])
+@pytest.mark.parametrize("n,wh,vs", [(2, 48, None), (1, 128, 5), (1, 45, 5), (1, 256, None)])
 def test_silhouette_backward(pkg, host_model, make_params, n, wh, vs):
     p, pr, _ = _oracle_inputs(host_model, make_params, n, wh, vs, seed=61)
     g = np.random.default_rng(4).standard_normal((n, wh, wh, 2)).astype(np.float32)
@@ -463,3 +463,30 @@ def test_silhouette_crossentropy(pkg):
     got.sum().backward()
     assert np.abs(got.detach().cpu().numpy() - ref.detach().numpy()).max() <= 2e-6
     assert np.abs(x.grad.cpu().numpy().reshape(n, wh * wh, 2) - x64.grad.numpy()).max() <= 3e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# seg: part tables narrower than 31 parts (channels < 32) and image sizes off every tile / group boundary
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("nparts,wh,vs", [(7, 48, 5), (20, 33, 5), (31, 33, 5), (12, 20, 2), (31, 50, None)])
+def test_seg_narrow_tables_and_odd_sizes(pkg, host_model, parts_by_vs, make_params, nparts, wh, vs):
+    """Forward and backward off the tuned path: fewer than 32 channels (scalar stores, dead lanes in the backward) and
+    widths that are no multiple of the 16x8 tiles or of the backward's 4-pixel groups (wh = 33, 50; wh = 20)."""
+    parts = parts_by_vs[vs][:nparts]
+    p, pr, mask = _oracle_inputs(host_model, make_params, 2, wh, vs, seed=77)
+    ref = np_oracle.projects_to_seg([pr, mask], wh, vs, parts)
+    g = np.random.default_rng(8).standard_normal(ref.shape).astype(np.float32)
+    ref64 = _seg_grad_oracle(pr, mask, wh, vs, parts, g, torch.float64)
+    x = t(pr).requires_grad_(True)
+    out = pkg.projects_to_seg([x, t(mask)], wh, vs, parts=parts)
+    got = out.detach().cpu().numpy()
+    assert got.shape == (2, wh, wh, nparts + 1)
+    assert np.abs(got - ref).max() <= TOL_SCORE
+    assert (_labels(got) != _labels(ref)).mean() <= LABEL_MISMATCH_MAX
+    (out * t(g)).sum().backward()
+    gg = x.grad.cpu().numpy().astype(np.float64)
+    assert np.all(gg[..., 2] == 0)
+    scale = np.abs(ref64).max() + 1e-9
+    bad = np.abs(gg - ref64) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(gg - ref64).max(), scale)
