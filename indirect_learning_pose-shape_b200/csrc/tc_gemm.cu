@@ -20,8 +20,9 @@
 //   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) per K
 //               block into TMEM buffer (block & 1); tcgen05.commit releases the smem stage and publishes the buffer.
 //               Owns the TMEM allocation.
-//   warps 2-5   accumulate + epilogue: tcgen05.ld 32x32b.x16 of the block's partial tile, FADD into BN registers per
-//               thread (one output row each); after the last block add bias, st.global.v8.f32 (full 32-byte sectors)
+//   warps 2-9   accumulate + epilogue, two warps per TMEM lane quadrant (one per half of the columns): all tcgen05.ld
+//               32x32b.x16 of the block's partial half tile in flight, ONE wait, FADD into BN/2 registers per thread (half
+//               an output row each); after the last block add bias, st.global.v8.f32 (full 32-byte sectors)
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -35,8 +36,9 @@ namespace {
 constexpr int kBM = 128;         // rows of an output tile (UMMA M, cta_group::1)
 constexpr int kBK = 32;          // fp32 per K block = one 128-byte swizzle row
 constexpr int kStages = 3;
-constexpr int kThreads = 192;    // 6 warps: TMA, MMA, 4 x epilogue
-constexpr int kTmemCols = 256;   // two partial-tile buffers of up to 128 columns
+constexpr int kThreads = 320;    // 10 warps: TMA, MMA, 2 x 4 accumulate/epilogue (each group owns half of the columns)
+constexpr int kTmemBufs = 4;     // partial-tile buffers in TMEM: the tensor core may run this many K blocks ahead of the adds
+constexpr int kTmemCols = 512;   // kTmemBufs buffers of up to 128 columns = all of TMEM (one CTA per SM)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,6 +94,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // K-major, SWIZZLE_128B operand tile: rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -119,21 +128,21 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                    int tiles_n) {
   constexpr int kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
   constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  constexpr int kAccStride = 128;                      // TMEM columns between the two partial-tile buffers
-  static_assert(BN % 16 == 0 && BN <= 128, "BN registers per epilogue thread");
+  constexpr int kAccStride = 128;                      // TMEM columns between partial-tile buffers
+  static_assert(BN % 16 == 0 && BN <= 128, "BN / 2 registers per epilogue thread");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;                   // partial tile of one K block ready in TMEM buffer b
-  uint64_t* tempty = tfull + 2;                        // TMEM buffer b drained into registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + kTmemBufs;                // TMEM buffer b drained into registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kTmemBufs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < kTmemBufs; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {                                     // TMEM allocation is warp-collective; this warp also frees it
@@ -193,53 +202,55 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           umma_commit(&empty[stage]);                  // frees this smem stage once the MMAs above have read it
           umma_commit(&tfull[buf]);                    // this K block's partial tile is complete
           if (++stage == kStages) { stage = 0; phase ^= 1; }
-          if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+          if (++buf == kTmemBufs) { buf = 0; buf_phase ^= 1; }
         }
       }
     }
   } else {
     // ===== accumulate (fp32 registers, round-to-nearest) + epilogue =====
-    const int q = warp & 3;                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // Eight warps: warp w may only touch TMEM lanes [32*(w%4), +32), so warps 2-5 take columns [0, BN/2) and warps 6-9
+    // columns [BN/2, BN) of the same lanes.  Every thread issues ALL its tcgen05.ld of a K block before the single wait:
+    // the drain of a partial tile was four serialised load->wait round trips per warp and bound the kernel.
+    constexpr int HN = BN / 2;
+    static_assert(HN % 8 == 0, "half rows leave as 32-byte stores");
+    const int q = warp & 3;
+    const int hcol = (warp - 2) >= 4 ? HN : 0;
     int buf = 0;
     uint32_t buf_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
-      float acc[BN];
+      float acc[HN];
 #pragma unroll
-      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int i = 0; i < HN; ++i) acc[i] = 0.f;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&tfull[buf], buf_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride) + (uint32_t)hcol;
+        uint32_t r[HN / 16 + 1][16];
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {             // two x16 loads in flight per wait
-          uint32_t r0[16], r1[16];
-          tmem_ld_32x32b_x16(taddr + c, r0);
-          if (c + 16 < BN) tmem_ld_32x32b_x16(taddr + c + 16, r1);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int e = 0; e < 16; ++e) acc[c + e] += __uint_as_float(r0[e]);
-          if (c + 16 < BN) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) acc[c + 16 + e] += __uint_as_float(r1[e]);
-          }
+        for (int c = 0; c < HN; c += 16) {
+          if (c + 16 <= HN) tmem_ld_32x32b_x16(taddr + c, r[c / 16]);
         }
+        if (HN % 16) tmem_ld_32x32b_x8(taddr + (HN / 16) * 16, r[HN / 16]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < HN; ++c) acc[c] += __uint_as_float(r[c / 16][c % 16]);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        if (++buf == kTmemBufs) { buf = 0; buf_phase ^= 1; }
       }
       const int row = m0 + q * 32 + lane;
       if (row < M) {
-        float* drow = D + (size_t)row * ldd + n0;
+        float* drow = D + (size_t)row * ldd + n0 + hcol;
 #pragma unroll
-        for (int c = 0; c < BN; c += 8) {
+        for (int c = 0; c < HN; c += 8) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = acc[c + e];
           if (BIAS) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + c);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c + 4);
             o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
             o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
           }
