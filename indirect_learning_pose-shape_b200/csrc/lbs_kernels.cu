@@ -46,9 +46,10 @@ __device__ __forceinline__ void blend_T(const Skin<KW>& s, const float* __restri
   for (int e = 0; e < 12; ++e) T[e] = 0.f;
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
+    const float w = s.w[k];
+    if (w == 0.f) continue;      // ELL padding (2.9 of 4 entries are real on average): skipping an exact zero changes nothing
     const float4* a = reinterpret_cast<const float4*>(As + s.j[k] * 12);
     const float4 r0 = a[0], r1 = a[1], r2 = a[2];
-    const float w = s.w[k];
     T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
     T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
     T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
