@@ -30,6 +30,9 @@ __device__ __forceinline__ int cell_of(float u, float v) {
   return (int)pv * kMaskGrid + (int)pu;        // column = u, row = v (meshgrid 'xy', :49-54)
 }
 
+// kPer = vertices per thread kept in registers between the passes (cell and depth key are computed once); launches whose
+// Vs exceeds kPer * blockDim fall back to re-reading (kPer = 0).
+template <int kPer>
 __global__ void __launch_bounds__(1024)
 mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict__ mask) {
   __shared__ unsigned int zmax[kCells];        // 0 = empty (orderable() never returns 0 for a non-NaN float)
@@ -39,17 +42,43 @@ mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict
   const float* p = projects + (size_t)n * Vs * 3;
   for (int i = tid; i < kCells; i += blockDim.x) { zmax[i] = 0u; win[i] = 0xffffffffu; }
   if (tid == 0) occupied = 0;
-  __syncthreads();
-  for (int i = tid; i < Vs; i += blockDim.x) {
-    const float z = p[i * 3 + 2];
-    const int c = cell_of(p[i * 3], p[i * 3 + 1]);
-    if (c >= 0 && z == z) atomicMax(&zmax[c], orderable(z));
+  int cellr[kPer > 0 ? kPer : 1];
+  unsigned keyr[kPer > 0 ? kPer : 1];
+  if (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * blockDim.x;
+      cellr[k] = -1; keyr[k] = 0u;
+      if (i < Vs) {
+        const float z = p[i * 3 + 2];
+        const int c = cell_of(p[i * 3], p[i * 3 + 1]);
+        if (c >= 0 && z == z) { cellr[k] = c; keyr[k] = orderable(z); }
+      }
+    }
   }
   __syncthreads();
-  for (int i = tid; i < Vs; i += blockDim.x) {
-    const float z = p[i * 3 + 2];
-    const int c = cell_of(p[i * 3], p[i * 3 + 1]);
-    if (c >= 0 && z == z && orderable(z) == zmax[c]) atomicMin(&win[c], (unsigned int)i);
+  if (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (cellr[k] >= 0) atomicMax(&zmax[cellr[k]], keyr[k]);
+  } else {
+    for (int i = tid; i < Vs; i += blockDim.x) {
+      const float z = p[i * 3 + 2];
+      const int c = cell_of(p[i * 3], p[i * 3 + 1]);
+      if (c >= 0 && z == z) atomicMax(&zmax[c], orderable(z));
+    }
+  }
+  __syncthreads();
+  if (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (cellr[k] >= 0 && keyr[k] == zmax[cellr[k]]) atomicMin(&win[cellr[k]], (unsigned int)(tid + k * blockDim.x));
+  } else {
+    for (int i = tid; i < Vs; i += blockDim.x) {
+      const float z = p[i * 3 + 2];
+      const int c = cell_of(p[i * 3], p[i * 3 + 1]);
+      if (c >= 0 && z == z && orderable(z) == zmax[c]) atomicMin(&win[c], (unsigned int)i);
+    }
   }
   int occ = 0;
   for (int i = tid; i < kCells; i += blockDim.x) occ += zmax[i] != 0u;
@@ -57,11 +86,24 @@ mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict
   if ((tid & 31) == 0 && occ) atomicAdd(&occupied, occ);
   __syncthreads();
   const bool any_empty = occupied < kCells;
-  for (int i = tid; i < Vs; i += blockDim.x) {
-    const int c = cell_of(p[i * 3], p[i * 3 + 1]);
-    bool vis = (c >= 0) && (win[c] == (unsigned int)i);
-    if (i == 1 && any_empty) vis = true;       // every empty pixel votes for index 1 (:98-99)
-    mask[(size_t)n * Vs + i] = vis ? 1.0f : kMaskInvisible;
+  if (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * blockDim.x;
+      if (i < Vs) {
+        bool vis = (cellr[k] >= 0) && (win[cellr[k]] == (unsigned int)i);
+        if (i == 1 && any_empty) vis = true;     // every empty pixel votes for index 1 (:98-99)
+        mask[(size_t)n * Vs + i] = vis ? 1.0f : kMaskInvisible;
+      }
+    }
+  } else {
+    for (int i = tid; i < Vs; i += blockDim.x) {
+      const int c = cell_of(p[i * 3], p[i * 3 + 1]);
+      const float z = p[i * 3 + 2];
+      bool vis = (c >= 0) && (z == z) && (win[c] == (unsigned int)i);
+      if (i == 1 && any_empty) vis = true;       // every empty pixel votes for index 1 (:98-99)
+      mask[(size_t)n * Vs + i] = vis ? 1.0f : kMaskInvisible;
+    }
   }
 }
 
@@ -69,7 +111,9 @@ mask_kernel(const float* __restrict__ projects, int N, int Vs, float* __restrict
 
 cudaError_t launch_mask_fwd(const float* projects, int N, int Vs, float* mask, cudaStream_t st) {
   LaunchScope scope(KID_MASK, st);
-  mask_kernel<<<N, N < 64 ? 1024 : 256, 0, st>>>(projects, N, Vs, mask);   // few samples: spend threads on each
+  const int threads = N < 64 ? 1024 : 256;    // few samples: spend threads on each
+  if (Vs <= 7 * threads) mask_kernel<7><<<N, threads, 0, st>>>(projects, N, Vs, mask);
+  else mask_kernel<0><<<N, threads, 0, st>>>(projects, N, Vs, mask);
   return cudaGetLastError();
 }
 
