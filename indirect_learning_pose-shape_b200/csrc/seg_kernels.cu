@@ -274,18 +274,27 @@ __device__ __forceinline__ unsigned bfind_u32(unsigned x) {           // index o
 }
 
 // explicit shared-window accesses (a generic pointer into dynamic smem makes the compiler rebuild the window base)
-__device__ __forceinline__ float2 lds_f2(uint32_t a) {
-  float2 r;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
-  return r;
-}
 __device__ __forceinline__ float2 lds_f2_nv(uint32_t a) {            // read-only data: free to be scheduled early
   float2 r;
   asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
   return r;
 }
-__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
-  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+// asynchronous request of [p, p + bytes) into L2 (16-byte aligned, multiple of 16): no register, no scoreboard
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_b64(uint32_t a) {
+  unsigned long long r;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ unsigned long long lds_b64_nv(uint32_t a) {
+  unsigned long long r;
+  asm("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void sts_b64(uint32_t a, unsigned long long v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 
 // Exact pruning of one tile, lane k working on part k: writes the part's survivor words to kw[woff[k] ..].
@@ -322,21 +331,61 @@ __device__ __forceinline__ void prune_tile(const SegSmem& sm, unsigned* kw, int 
   __syncwarp();
 }
 
-// One word of a part's survivor mask against a lane's 2 x 2 pixel block: best[q] = min squared distance, barg[q] = code of
-// its arg-min, (index + 1) << sh.  CLAMP: indices >= 254 do not fit a byte and are recorded as 255 (re-queried by the
-// backward); only words 7 and up can hold them.
-template <bool TRACK, bool CLAMP>
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two fp32 lanes per instruction, each rounded to nearest like the
+// scalar op).  A pair lives in an aligned 64-bit register; ptxas reads a scalar operand as a broadcast (R.F32).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Squared distances of one vertex to a lane's 2 x 2 pixel block, GX = (gx0, gx1), GY = (gy0, gy1):
+// d2[q] = fma(du, du, fl(dv^2)), five packed instructions for the four pixels.
+__device__ __forceinline__ void block_d2(float2 e, f32x2 GX, f32x2 GY, float (&d2)[kNB]) {
+  const f32x2 dx = sub2(pk2(e.x, e.x), GX), dy = sub2(pk2(e.y, e.y), GY);
+  float vy0, vy1;
+  upk2(mul2(dy, dy), vy0, vy1);
+  upk2(fma2(dx, dx, pk2(vy0, vy0)), d2[0], d2[1]);
+  upk2(fma2(dx, dx, pk2(vy1, vy1)), d2[2], d2[3]);
+}
+
+// One survivor against a lane's 2 x 2 pixel block: best[q] = min squared distance, barg[q] = code of its arg-min,
+// (index + 1) << sh.  CLAMP: indices >= 254 do not fit a byte and are recorded as 255 (re-queried by the backward);
+// only words 7 and up can hold them.  FIRST: the block's first candidate of this part: no comparison needed.
+template <bool TRACK, bool CLAMP, bool FIRST>
 __device__ __forceinline__ void compare_vertex(float2 e, unsigned b, int w, unsigned sh, unsigned shmul, unsigned wcode,
-                                               float gx0, float gx1, float gy0, float gy1, float (&best)[kNB],
-                                               unsigned (&barg)[kNB]) {
-  const float dxa = __fsub_rn(e.x, gx0), dxb = __fsub_rn(e.x, gx1);
-  const float dya = __fsub_rn(e.y, gy0), dyb = __fsub_rn(e.y, gy1);
-  const float ux0 = __fmul_rn(dxa, dxa), ux1 = __fmul_rn(dxb, dxb);
-  const float vy0 = __fmul_rn(dya, dya), vy1 = __fmul_rn(dyb, dyb);
+                                               f32x2 GX, f32x2 GY, float (&best)[kNB], unsigned (&barg)[kNB]) {
   float d2[kNB];
-  d2[0] = __fadd_rn(ux0, vy0); d2[1] = __fadd_rn(ux1, vy0);
-  d2[2] = __fadd_rn(ux0, vy1); d2[3] = __fadd_rn(ux1, vy1);
-  if (TRACK) {
+  block_d2(e, GX, GY, d2);
+  if (FIRST) {
+    const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)b + 1, 255) << sh : b * shmul + wcode;
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) { best[q] = d2[q]; if (TRACK) barg[q] = vcode; }
+  } else if (TRACK) {
     const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)b + 1, 255) << sh : b * shmul + wcode;
 #pragma unroll
     for (int q = 0; q < kNB; ++q) {
@@ -350,10 +399,21 @@ __device__ __forceinline__ void compare_vertex(float2 e, unsigned b, int w, unsi
   }
 }
 
-template <bool TRACK, bool CLAMP>
-__device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsigned sh, float gx0, float gx1, float gy0,
-                                          float gy1, float (&best)[kNB], unsigned (&barg)[kNB]) {
+// FRESH: best / barg hold nothing yet: the word's first survivor initialises them (an empty word leaves kBigD2 / 0).
+template <bool TRACK, bool CLAMP, bool FRESH>
+__device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsigned sh, f32x2 GX, f32x2 GY,
+                                          float (&best)[kNB], unsigned (&barg)[kNB]) {
   const unsigned shmul = 1u << sh, wcode = (unsigned)(w * 32 + 1) << sh;
+  if (FRESH) {
+    if (m == 0u) {
+#pragma unroll
+      for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
+      return;
+    }
+    const unsigned b0 = bfind_u32(m);
+    m ^= 1u << b0;
+    compare_vertex<TRACK, CLAMP, true>(lds_f2_nv(eb + b0 * 16u), b0, w, sh, shmul, wcode, GX, GY, best, barg);
+  }
   // survivors two at a time: both coordinate loads are in flight before either vertex is compared
   while (m) {
     const unsigned b0 = bfind_u32(m);
@@ -363,10 +423,10 @@ __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsign
       const unsigned b1 = bfind_u32(m);
       m ^= 1u << b1;
       const float2 e1 = lds_f2_nv(eb + b1 * 16u);
-      compare_vertex<TRACK, CLAMP>(e0, b0, w, sh, shmul, wcode, gx0, gx1, gy0, gy1, best, barg);
-      compare_vertex<TRACK, CLAMP>(e1, b1, w, sh, shmul, wcode, gx0, gx1, gy0, gy1, best, barg);
+      compare_vertex<TRACK, CLAMP, false>(e0, b0, w, sh, shmul, wcode, GX, GY, best, barg);
+      compare_vertex<TRACK, CLAMP, false>(e1, b1, w, sh, shmul, wcode, GX, GY, best, barg);
     } else {
-      compare_vertex<TRACK, CLAMP>(e0, b0, w, sh, shmul, wcode, gx0, gx1, gy0, gy1, best, barg);
+      compare_vertex<TRACK, CLAMP, false>(e0, b0, w, sh, shmul, wcode, GX, GY, best, barg);
     }
   }
 }
@@ -402,6 +462,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int c0 = tx * kTW + lx * 2, r0 = ty * kTH + ly * 2;        // this lane's block origin (grid = (column,row), :26-31)
     const float gx0 = (float)c0, gx1 = (float)(c0 + 1), gy0 = (float)r0, gy1 = (float)(r0 + 1);
+    const f32x2 GX = pk2(gx0, gx1), GY = pk2(gy0, gy1);
     prune_tile(sm, kw, P, lane, (float)(tx * kTW) + kTileHW, (float)(ty * kTH) + kTileHH);
 
     bool blk_slow = ghead >= 0;                                      // any heavy vertex chained to one of my pixels?
@@ -438,17 +499,17 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
           const unsigned sh = 8u * (unsigned)s4;
           float best[kNB];
           unsigned barg[kNB];                                        // arg-min code, already shifted to its byte
-#pragma unroll
-          for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
           // survivors are visited from the highest index down and replace on <=, so the LOWEST index wins exact ties
           if (pd.y == 1) {                                           // at most 32 visible vertices: the common case
-            scan_word<TRACK, false>(kw[pd.z], (uint32_t)pd.x, 0, sh, gx0, gx1, gy0, gy1, best, barg);
+            scan_word<TRACK, false, true>(kw[pd.z], (uint32_t)pd.x, 0, sh, GX, GY, best, barg);
           } else {
+#pragma unroll
+            for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
             for (int w = pd.y; w-- > 0;) {
               const unsigned m = kw[pd.z + w];                       // same address on every lane: broadcast
               const uint32_t eb = (uint32_t)pd.x + (uint32_t)(w * 32) * 16u;
-              if (TRACK && w >= 7) scan_word<TRACK, true>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
-              else scan_word<TRACK, false>(m, eb, w, sh, gx0, gx1, gy0, gy1, best, barg);
+              if (TRACK && w >= 7) scan_word<TRACK, true, false>(m, eb, w, sh, GX, GY, best, barg);
+              else scan_word<TRACK, false, false>(m, eb, w, sh, GX, GY, best, barg);
             }
           }
           float sc[kNB];
@@ -518,6 +579,8 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 // Parts with more than kIL visible vertices spill to a compact overflow list (shared accumulators, atomics; 0.3 % of
 // the entries at vertex_sampling=5).  Heavy / generic winners (code 255) are re-queried from global memory.
 constexpr int kIL = 32;            // interleaved light slots per part
+constexpr int kPF = 16;            // L2 request window of the backward, in 4-pixel groups (8 KB of gradient rows per warp)
+constexpr int kAccRows = kIL + 1;  // accumulator rows per warp: row kIL takes the (discarded) sums of "none" and rare codes
 constexpr unsigned kNoVid = 0xffffu;
 constexpr int kOvPriv = 64;        // private overflow slots per warp; a sample that needs more spills to shared atomics
 
@@ -529,14 +592,14 @@ struct BwdSmem {
   float2* opos;          // [OV]
   float2* oacc;          // [OV]
   unsigned short* ovid;  // [OV]  kNoVid = unused
-  float2* wacc;          // [nwarps][kIL][32]
+  float2* wacc;          // [nwarps][kAccRows][32]
   float2* wov;           // [nwarps][kOvPriv]  private overflow accumulators, slots handed out per sample (odyn)
   int* odyn;             // [32]  exclusive prefix of max(lcount_k - kIL, 0) for THIS sample
 };
 __host__ __device__ __forceinline__ size_t bwd_smem_bytes(int OV, int nwarps) {
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
   const size_t need = 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + ov * 8 * 2 + ov * 2 +
-                      (size_t)nwarps * (kIL * 32 + kOvPriv) * 8;
+                      (size_t)nwarps * (kAccRows * 32 + kOvPriv) * 8;
   const size_t floor_ = 256 + 256 * 256;   // a lane reads lpos row (code - 1) unclamped: rows -1 .. 254 must be mapped
   return need > floor_ ? need : floor_;
 }
@@ -545,7 +608,7 @@ __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* raw, int OV, int nwa
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
   size_t off = 256;
   b.lpos = reinterpret_cast<float2*>(raw + off); off += (size_t)kIL * 32 * 8;
-  b.wacc = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kIL * 32 * 8;
+  b.wacc = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kAccRows * 32 * 8;
   b.wov = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kOvPriv * 8;
   b.opos = reinterpret_cast<float2*>(raw + off); off += ov * 8;
   b.oacc = reinterpret_cast<float2*>(raw + off); off += ov * 8;
@@ -667,11 +730,22 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const BwdSmem b = carve_bwd(raw, OV, nwarps);
+  // Each warp owns a contiguous range of groups of 4 consecutive output pixels (row-major, rows already flipped: grid
+  // row = wh-1-row).  Its first kPF groups of gradient rows (lane 0) and saved rows (lane 1) are requested into L2 now, so
+  // the classification below overlaps their DRAM latency; the main loop keeps the request window kPF groups ahead.
+  const int npx = wh * wh;
+  const int nb = (npx + 3) >> 2;
+  const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
+  constexpr bool kPrefetch = C32 && ALIGNED;                       // 16-byte aligned rows, no partial group
+  const unsigned char* pf_base = (lane == 0) ? reinterpret_cast<const unsigned char*>(g_seg + ((size_t)n * npx + (size_t)b0 * 4) * 32)
+                                             : saved + ((size_t)n * npx + (size_t)b0 * 4) * 32;
+  const uint32_t pf_group = (lane == 0) ? 4u * 128u : 4u * 32u;    // bytes per group
+  if (kPrefetch && lane < 2 && b1 > b0) prefetch_l2_bulk(pf_base, pf_group * (uint32_t)min(kPF, b1 - b0));
   const float* proj_n = projects + (size_t)n * Vs * 3;
   const float* mask_n = mask + (size_t)n * Vs;
   float* out = g_projects + (size_t)n * Vs * 3;
   for (int i = threadIdx.x; i < Vs * 3; i += blockDim.x) out[i] = 0.f;   // z and untouched vertices stay 0
-  for (int i = threadIdx.x; i < nwarps * (kIL * 32 + kOvPriv); i += blockDim.x) b.wacc[i] = make_float2(0.f, 0.f);   // + wov
+  for (int i = threadIdx.x; i < nwarps * (kAccRows * 32 + kOvPriv); i += blockDim.x) b.wacc[i] = make_float2(0.f, 0.f);   // + wov
   for (int i = threadIdx.x; i < 32; i += blockDim.x) reinterpret_cast<float2*>(raw)[i] = make_float2(0.f, 0.f);
   classify_light(b, proj_n, mask_n, ptr, idx, obase, P, OV);
   __syncthreads();
@@ -692,25 +766,25 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int p0 = ptr[k], p1 = ptr[k + 1];
   // column = lane: lane 0 (the gate channel) and dead lanes own harmless columns of their own, so no lane needs masking
   const uint32_t lpos_sa = (uint32_t)__cvta_generic_to_shared(b.lpos) + (uint32_t)lane * 8u;
-  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(b.wacc + (size_t)warp * kIL * 32) + (uint32_t)lane * 8u;
+  const uint32_t wacc_sa = (uint32_t)__cvta_generic_to_shared(b.wacc + (size_t)warp * kAccRows * 32) + (uint32_t)lane * 8u;
   const int ob = b.obase[k], od = b.odyn[k];
   float2* wov_w = b.wov + (size_t)warp * kOvPriv;
-  const int npx = wh * wh;
   const unsigned char* sv = saved + (size_t)n * npx * 32 + lane;
   const float* g_n = g_seg + (size_t)n * npx * C + (lane < C ? lane : 0);
   const bool ld_g = C32 || lane < C;
 
-  // Each warp owns a contiguous range of groups of 4 consecutive output pixels (row-major, rows already flipped: grid
-  // row = wh-1-row); loads run one group ahead in two named register sets (no copies), pointers advance linearly.
+  // Register loads run one group ahead in two named register sets (no copies), pointers advance linearly.
   // ALIGNED (wh % 4 == 0): a group never straddles a row and there is no tail.
-  const int nb = (npx + 3) >> 2;
-  const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
   const unsigned char* svp = sv + (size_t)b0 * 4 * 32;
   const float* gp = g_n + (size_t)b0 * 4 * C;
   int px = b0 * 4;                                                  // first pixel of the group being COMPUTED
   int pxl = px;                                                     // first pixel of the group being LOADED
   int col = px % wh;
-  float gy = (float)(wh - 1 - px / wh);                             // grid row of the group (rows flipped, :68)
+  // (column, grid row) of the group's four pixels as packed pairs (rows flipped, :68); ALIGNED: carried across groups
+  f32x2 GP[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) GP[j] = pk2((float)(col + j), (float)(wh - 1 - px / wh));
+  const f32x2 step_in = pk2(4.0f, 0.0f), step_wrap = pk2((float)(4 - wh), -1.0f);
 #define SEG_LOAD4(code, g)                                                                                             \
   do {                                                                                                                 \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
@@ -722,41 +796,54 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   } while (0)
 #define SEG_COMPUTE4(code, g)                                                                                          \
   do {                                                                                                                 \
-    float gxv[4], gyv[4];                                                                                              \
-    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
-      if (ALIGNED) { gxv[j] = (float)col + (float)j; gyv[j] = gy; }                                                    \
-      else { const int r = (px + j) / wh; gxv[j] = (float)(px + j - r * wh); gyv[j] = (float)(wh - 1 - r); }           \
+    if (!ALIGNED) {                                                                                                    \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                  \
+        const int r = (px + j) / wh;                                                                                   \
+        GP[j] = pk2((float)(px + j - r * wh), (float)(wh - 1 - r));                                                    \
+      }                                                                                                                \
     }                                                                                                                  \
-    float cu[4], cv[4], Gv[4];                                                                                         \
+    f32x2 c2[4];                                                                                                       \
+    float Gv[4];                                                                                                       \
     int li[4];                                                                                                         \
     /* (a) four pixels, mutually independent: the arithmetic of the four chains interleaves */                        \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
       const float t0 = (code[j] & 1) ? g[j] : 0.f;                 /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
       Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                  \
       li[j] = code[j] - 1;                                          /* -1 none, >= kIL overflow, 254 re-query */       \
-      const float2 e = lds_f2_nv(lpos_sa + (uint32_t)(li[j] * 256));   /* rows -1 .. 254 are inside the allocation */   \
-      const float du = __fsub_rn(e.x, gxv[j]), dv = __fsub_rn(e.y, gyv[j]);                                            \
-      const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));                                                \
+      const f32x2 e = lds_b64_nv(lpos_sa + (uint32_t)(li[j] * 256));   /* rows -1 .. 254 are inside the allocation */  \
+      const f32x2 d = sub2(e, GP[j]);                               /* (du, dv) */                                      \
+      float du2, dv2;                                                                                                  \
+      upk2(mul2(d, d), du2, dv2);                                                                                      \
+      const float d2 = __fadd_rn(du2, dv2);                                                                            \
       const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));                                                                \
       const float s = ex2_approx((d2 * rs) * (-kLog2e));                                                               \
       const float coef = (s * Gv[j]) * (-rs);                       /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
-      cu[j] = coef * du; cv[j] = coef * dv;                                                                            \
+      c2[j] = mul2(pk2(coef, coef), d);                                                                                \
     }                                                                                                                  \
-    /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order */            \
-    const bool rare = __any_sync(0xffffffffu, live && max(max(li[0], li[1]), max(li[2], li[3])) >= kIL);                       \
+    /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order; "none" and  */\
+    /* the rare codes add into the discarded row kIL, so the common path has no branch                               */\
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
-      if ((unsigned)li[j] < (unsigned)kIL) {                                                                           \
-        const uint32_t a_sa = wacc_sa + (uint32_t)li[j] * 256u;                                                        \
-        float2 a = lds_f2(a_sa);                                                                                       \
-        a.x += cu[j]; a.y += cv[j];                                                                                    \
-        sts_f2(a_sa, a);                                                                                               \
-      } else if (rare && live && li[j] >= kIL) {                            /* rare: overflow slot, or re-query (code 255) */  \
-        if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxv[j], gyv[j], Gv[j], out);             \
-        else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxv[j], gyv[j], Gv[j]);                                \
+      const uint32_t a_sa = wacc_sa + min((unsigned)li[j], (unsigned)kIL) * 256u;                                      \
+      sts_b64(a_sa, add2(lds_b64(a_sa), c2[j]));                                                                       \
+    }                                                                                                                  \
+    if (__any_sync(0xffffffffu, live && max(max(li[0], li[1]), max(li[2], li[3])) >= kIL)) {                           \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                  \
+        if (live && li[j] >= kIL) {                                 /* rare: overflow slot, or re-query (code 255) */  \
+          float gxj, gyj;                                                                                              \
+          upk2(GP[j], gxj, gyj);                                                                                       \
+          if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxj, gyj, Gv[j], out);                 \
+          else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxj, gyj, Gv[j]);                                    \
+        }                                                                                                              \
       }                                                                                                                \
     }                                                                                                                  \
-    px += 4; col += 4;                                                                                                 \
-    if (ALIGNED && col == wh) { col = 0; gy -= 1.0f; }                                                                 \
+    px += 4;                                                                                                           \
+    if (ALIGNED) {                                                                                                     \
+      col += 4;                                                                                                        \
+      const bool wrap = col == wh;                                                                                     \
+      const f32x2 st2 = wrap ? step_wrap : step_in;                                                                    \
+      col = wrap ? 0 : col;                                                                                            \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) GP[j] = add2(GP[j], st2);                                          \
+    }                                                                                                                  \
   } while (0)
   {
     int codeA[4], codeB[4];
@@ -765,6 +852,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     if (nbw > 0) SEG_LOAD4(codeA, gA);
     for (int i = 0; i < nbw; i += 2) {
       const bool hasB = i + 1 < nbw;
+      if (kPrefetch && lane < 2 && i + kPF < nbw)
+        prefetch_l2_bulk(pf_base + (size_t)(i + kPF) * pf_group, pf_group * (uint32_t)min(2, nbw - i - kPF));
       if (hasB) SEG_LOAD4(codeB, gB);
       SEG_COMPUTE4(codeA, gA);
       if (hasB) {
@@ -781,7 +870,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     const int i = s >> 5, kk = (s & 31) - 1;                       // column = part + 1
     if (kk >= 0 && kk < P && i < b.lcount[kk]) {
       float su = 0.f, sv2 = 0.f;
-      for (int w = 0; w < nwarps; ++w) { const float2 a = b.wacc[(size_t)w * kIL * 32 + s]; su += a.x; sv2 += a.y; }
+      for (int w = 0; w < nwarps; ++w) { const float2 a = b.wacc[(size_t)w * kAccRows * 32 + s]; su += a.x; sv2 += a.y; }
       const int vid = b.lvid[s];
       atomicAdd(&out[vid * 3], su); atomicAdd(&out[vid * 3 + 1], sv2);
     }
