@@ -579,7 +579,6 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 // Parts with more than kIL visible vertices spill to a compact overflow list (shared accumulators, atomics; 0.3 % of
 // the entries at vertex_sampling=5).  Heavy / generic winners (code 255) are re-queried from global memory.
 constexpr int kIL = 32;            // interleaved light slots per part
-constexpr int kPF = 16;            // L2 request window of the backward, in 4-pixel groups (8 KB of gradient rows per warp)
 constexpr int kAccRows = kIL + 1;  // accumulator rows per warp: row kIL takes the (discarded) sums of "none" and rare codes
 constexpr unsigned kNoVid = 0xffffu;
 constexpr int kOvPriv = 64;        // private overflow slots per warp; a sample that needs more spills to shared atomics
@@ -595,10 +594,11 @@ struct BwdSmem {
   float2* wacc;          // [nwarps][kAccRows][32]
   float2* wov;           // [nwarps][kOvPriv]  private overflow accumulators, slots handed out per sample (odyn)
   int* odyn;             // [32]  exclusive prefix of max(lcount_k - kIL, 0) for THIS sample
+  int* next_row;         // [1]   next output row to hand out (ALIGNED schedule)
 };
 __host__ __device__ __forceinline__ size_t bwd_smem_bytes(int OV, int nwarps) {
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
-  const size_t need = 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + ov * 8 * 2 + ov * 2 +
+  const size_t need = 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + 16 + ov * 8 * 2 + ov * 2 +
                       (size_t)nwarps * (kAccRows * 32 + kOvPriv) * 8;
   const size_t floor_ = 256 + 256 * 256;   // a lane reads lpos row (code - 1) unclamped: rows -1 .. 254 must be mapped
   return need > floor_ ? need : floor_;
@@ -615,6 +615,7 @@ __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* raw, int OV, int nwa
   b.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   b.odyn = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   b.obase = reinterpret_cast<int*>(raw + off); off += 36 * 4;
+  b.next_row = reinterpret_cast<int*>(raw + off); off += 16;
   b.lvid = reinterpret_cast<unsigned short*>(raw + off); off += (size_t)kIL * 32 * 2;
   b.ovid = reinterpret_cast<unsigned short*>(raw + off);
   return b;
@@ -730,23 +731,27 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const BwdSmem b = carve_bwd(raw, OV, nwarps);
-  // Each warp owns a contiguous range of groups of 4 consecutive output pixels (row-major, rows already flipped: grid
-  // row = wh-1-row).  Its first kPF groups of gradient rows (lane 0) and saved rows (lane 1) are requested into L2 now, so
-  // the classification below overlaps their DRAM latency; the main loop keeps the request window kPF groups ahead.
+  // ALIGNED (wh % 4 == 0, wh >= 8): output rows (already flipped: grid row = wh-1-row) are handed to the warps on demand
+  // (a shared counter): the scheduler does not run the warps of a block evenly, and with a fixed share per warp a
+  // quarter of the warp-time went into waiting at the final barrier.  A warp walks a row in groups of 4 consecutive
+  // pixels.  The gradient rows (lane 0) and saved rows (lane 1) of a warp's first output row are requested into L2 now,
+  // so the classification below overlaps their DRAM latency; taking row r requests row r + nwarps.
+  // Otherwise: each warp owns a contiguous range of 4-pixel groups of the row-major pixel list, no prefetch.
   const int npx = wh * wh;
   const int nb = (npx + 3) >> 2;
   const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
-  constexpr bool kPrefetch = C32 && ALIGNED;                       // 16-byte aligned rows, no partial group
-  const unsigned char* pf_base = (lane == 0) ? reinterpret_cast<const unsigned char*>(g_seg + ((size_t)n * npx + (size_t)b0 * 4) * 32)
-                                             : saved + ((size_t)n * npx + (size_t)b0 * 4) * 32;
-  const uint32_t pf_group = (lane == 0) ? 4u * 128u : 4u * 32u;    // bytes per group
-  if (kPrefetch && lane < 2 && b1 > b0) prefetch_l2_bulk(pf_base, pf_group * (uint32_t)min(kPF, b1 - b0));
+  constexpr bool kPrefetch = C32 && ALIGNED;                       // 16-byte aligned rows
+  const unsigned char* pf_base = (lane == 0) ? reinterpret_cast<const unsigned char*>(g_seg + (size_t)n * npx * 32)
+                                             : saved + (size_t)n * npx * 32;
+  const uint32_t pf_row = (uint32_t)wh * ((lane == 0) ? 128u : 32u);   // bytes per output row
+  if (kPrefetch && lane < 2 && warp < wh) prefetch_l2_bulk(pf_base + (size_t)warp * pf_row, pf_row);
   const float* proj_n = projects + (size_t)n * Vs * 3;
   const float* mask_n = mask + (size_t)n * Vs;
   float* out = g_projects + (size_t)n * Vs * 3;
   for (int i = threadIdx.x; i < Vs * 3; i += blockDim.x) out[i] = 0.f;   // z and untouched vertices stay 0
   for (int i = threadIdx.x; i < nwarps * (kAccRows * 32 + kOvPriv); i += blockDim.x) b.wacc[i] = make_float2(0.f, 0.f);   // + wov
   for (int i = threadIdx.x; i < 32; i += blockDim.x) reinterpret_cast<float2*>(raw)[i] = make_float2(0.f, 0.f);
+  if (threadIdx.x == 0) *b.next_row = nwarps;                       // rows 0 .. nwarps-1 are the warps' first rows
   classify_light(b, proj_n, mask_n, ptr, idx, obase, P, OV);
   __syncthreads();
   if (threadIdx.x < 32) {                                           // this sample's overflow slots, handed out in part order
@@ -774,17 +779,19 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const bool ld_g = C32 || lane < C;
 
   // Register loads run one group ahead in two named register sets (no copies), pointers advance linearly.
-  // ALIGNED (wh % 4 == 0): a group never straddles a row and there is no tail.
-  const unsigned char* svp = sv + (size_t)b0 * 4 * 32;
-  const float* gp = g_n + (size_t)b0 * 4 * C;
-  int px = b0 * 4;                                                  // first pixel of the group being COMPUTED
-  int pxl = px;                                                     // first pixel of the group being LOADED
-  int col = px % wh;
+  const int px0 = ALIGNED ? warp * wh : b0 * 4;                     // first pixel of this warp
+  const unsigned char* svp = sv + (size_t)px0 * 32;
+  const float* gp = g_n + (size_t)px0 * C;
+  int px = px0;                                                     // first pixel of the group being COMPUTED (!ALIGNED)
+  int pxl = px;                                                     // first pixel of the group being LOADED (!ALIGNED)
+  int rL = warp, gL = 0;                                            // ALIGNED: load cursor (output row, group in the row)
+  int rC = warp, col = 0;                                           // ALIGNED: compute cursor (output row, column)
+  const int G = wh >> 2;
   // (column, grid row) of the group's four pixels as packed pairs (rows flipped, :68); ALIGNED: carried across groups
   f32x2 GP[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) GP[j] = pk2((float)(col + j), (float)(wh - 1 - px / wh));
-  const f32x2 step_in = pk2(4.0f, 0.0f), step_wrap = pk2((float)(4 - wh), -1.0f);
+  for (int j = 0; j < 4; ++j) GP[j] = pk2((float)j, (float)(wh - 1 - rC));
+  const f32x2 step_in = pk2(4.0f, 0.0f);
 #define SEG_LOAD4(code, g)                                                                                             \
   do {                                                                                                                 \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
@@ -837,31 +844,63 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       }                                                                                                                \
     }                                                                                                                  \
     px += 4;                                                                                                           \
-    if (ALIGNED) {                                                                                                     \
+    if (ALIGNED) {                                                  /* next group of the row, or the warp's next row */ \
       col += 4;                                                                                                        \
       const bool wrap = col == wh;                                                                                     \
-      const f32x2 st2 = wrap ? step_wrap : step_in;                                                                    \
       col = wrap ? 0 : col;                                                                                            \
-      _Pragma("unroll") for (int j = 0; j < 4; ++j) GP[j] = add2(GP[j], st2);                                          \
+      if (wrap) {                                                   /* the load cursor is one group ahead: on my next row */ \
+        rC = rL;                                                                                                       \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) GP[j] = pk2((float)j, (float)(wh - 1 - rC));                     \
+      } else {                                                                                                         \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) GP[j] = add2(GP[j], step_in);                                    \
+      }                                                                                                                \
+    }                                                                                                                  \
+  } while (0)
+// ALIGNED: move the load cursor one group on; at a row's end take the next free row and request the row nwarps further
+#define SEG_ADVANCE_LOAD()                                                                                             \
+  do {                                                                                                                 \
+    if (++gL == G && rL < wh) {                                                                                        \
+      gL = 0;                                                                                                          \
+      int r = 0;                                                                                                       \
+      if (lane == 0) r = atomicAdd(b.next_row, 1);                                                                     \
+      rL = __shfl_sync(0xffffffffu, r, 0);                                                                             \
+      svp = sv + (size_t)rL * wh * 32; gp = g_n + (size_t)rL * wh * C;                                                 \
+      if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row); \
     }                                                                                                                  \
   } while (0)
   {
     int codeA[4], codeB[4];
     float gA[4], gB[4];
-    const int nbw = b1 - b0;
-    if (nbw > 0) SEG_LOAD4(codeA, gA);
-    for (int i = 0; i < nbw; i += 2) {
-      const bool hasB = i + 1 < nbw;
-      if (kPrefetch && lane < 2 && i + kPF < nbw)
-        prefetch_l2_bulk(pf_base + (size_t)(i + kPF) * pf_group, pf_group * (uint32_t)min(2, nbw - i - kPF));
-      if (hasB) SEG_LOAD4(codeB, gB);
-      SEG_COMPUTE4(codeA, gA);
-      if (hasB) {
-        if (i + 2 < nbw) SEG_LOAD4(codeA, gA);
-        SEG_COMPUTE4(codeB, gB);
+    if (ALIGNED) {
+      if (rL < wh) {
+        if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row);
+        SEG_LOAD4(codeA, gA);
+        for (;;) {
+          SEG_ADVANCE_LOAD();
+          if (rL < wh) SEG_LOAD4(codeB, gB);
+          SEG_COMPUTE4(codeA, gA);
+          if (rC >= wh) break;
+          SEG_ADVANCE_LOAD();
+          if (rL < wh) SEG_LOAD4(codeA, gA);
+          SEG_COMPUTE4(codeB, gB);
+          if (rC >= wh) break;
+        }
+      }
+    } else {
+      const int nbw = b1 - b0;
+      if (nbw > 0) SEG_LOAD4(codeA, gA);
+      for (int i = 0; i < nbw; i += 2) {
+        const bool hasB = i + 1 < nbw;
+        if (hasB) SEG_LOAD4(codeB, gB);
+        SEG_COMPUTE4(codeA, gA);
+        if (hasB) {
+          if (i + 2 < nbw) SEG_LOAD4(codeA, gA);
+          SEG_COMPUTE4(codeB, gB);
+        }
       }
     }
   }
+#undef SEG_ADVANCE_LOAD
 #undef SEG_LOAD4
 #undef SEG_COMPUTE4
   __syncthreads();
@@ -945,7 +984,7 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
     seg_bwd_kernel<C32, AL><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->obase, \
                                                           p->P, p->ovf, wh, g_projects);                               \
   } while (0)
-  const bool c32 = p->P == 31, al = wh % 4 == 0;
+  const bool c32 = p->P == 31, al = wh % 4 == 0 && wh >= 8;
   if (c32 && al) SMPL_SEG_BWD(true, true);
   else if (c32) SMPL_SEG_BWD(true, false);
   else if (al) SMPL_SEG_BWD(false, true);
