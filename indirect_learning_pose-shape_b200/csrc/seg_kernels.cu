@@ -55,6 +55,7 @@ struct SegSmem {
   int4* pdesc;     // [32] per part {shared address of its first entry, survivor words, word offset, -}: one load in the hot path
   int* ghead;      // [1]  chain of generic slots, -1 none
   int* nheavy;     // [1]  number of chained heavy entries
+  int* next_tile;  // [1]  next tile (in visiting order) to hand out
   unsigned char* rest;
 };
 
@@ -86,7 +87,8 @@ __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
   sm.woff = reinterpret_cast<int*>(raw + off); off += 36 * 4;
   sm.pdesc = reinterpret_cast<int4*>(raw + off); off += 32 * 16;
   sm.ghead = reinterpret_cast<int*>(raw + off);
-  sm.nheavy = sm.ghead + 1; off += 16;
+  sm.nheavy = sm.ghead + 1;
+  sm.next_tile = sm.ghead + 2; off += 16;
   sm.rest = raw + off;
   return sm;
 }
@@ -442,9 +444,6 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const SegSmem sm = carve(raw, E, wh);
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
-  const int ghead = *sm.ghead;
-  const bool any_heavy = *sm.nheavy > 0;
   const int C = P + 1;
   const int tiles_x = (wh + kTW - 1) / kTW, tiles_y = (wh + kTH - 1) / kTH, ntiles = tiles_x * tiles_y;
   const int t0 = (int)(((long long)ntiles * blockIdx.y) / gridDim.y);
@@ -458,8 +457,15 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   float* stage = reinterpret_cast<float*>(sm.rest + (((size_t)nwarps * KW * 4 + 15) & ~(size_t)15)) +
                  (size_t)warp * (8 * kNB * 32) + lane;
 
-  for (int t = t0 + warp; t < t1; t += nwarps) {
-    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  // Tiles are handed to the warps on demand (the first nwarps statically), the image's centre columns first: they hold
+  // the body and cost the most, and a fixed tile -> warp map gave all of them to the same two warps.
+  if (threadIdx.x == 0) *sm.next_tile = t0 + nwarps;                 // ordered before its first use by classify's barriers
+  classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
+  const int ghead = *sm.ghead;
+  const bool any_heavy = *sm.nheavy > 0;
+  for (int ti = t0 + warp; ti < t1;) {
+    const int ci = ti / tiles_y, ty = ti - ci * tiles_y;
+    const int tx = (tiles_x >> 1) + ((ci & 1) ? -((ci + 1) >> 1) : (ci >> 1));
     const int c0 = tx * kTW + lx * 2, r0 = ty * kTH + ly * 2;        // this lane's block origin (grid = (column,row), :26-31)
     const float gx0 = (float)c0, gx1 = (float)(c0 + 1), gy0 = (float)r0, gy1 = (float)(r0 + 1);
     const f32x2 GX = pk2(gx0, gx1), GY = pk2(gy0, gy1);
@@ -567,6 +573,9 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
         }
       }
     }
+    int nt = 0;
+    if (lane == 0) nt = atomicAdd(sm.next_tile, 1);
+    ti = __shfl_sync(0xffffffffu, nt, 0);
   }
 }
 
