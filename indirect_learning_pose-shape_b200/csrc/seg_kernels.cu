@@ -593,7 +593,7 @@ constexpr unsigned kNoVid = 0xffffu;
 constexpr int kOvPriv = 64;        // private overflow slots per warp; a sample that needs more spills to shared atomics
 
 struct BwdSmem {
-  float2* lpos;          // [kIL][32]   (preceded by one readable row: index -1 = "none" reads it)
+  float2* lpos;          // [kAccRows][32]   row kIL = zeros: what "none" and the rare codes read
   unsigned short* lvid;  // [kIL][32]
   int* lcount;           // [32]
   int* obase;            // [36]  overflow offsets of the parts (prefix of max(size_k - kIL, 0))
@@ -607,16 +607,15 @@ struct BwdSmem {
 };
 __host__ __device__ __forceinline__ size_t bwd_smem_bytes(int OV, int nwarps) {
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
-  const size_t need = 256 + (size_t)kIL * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + 16 + ov * 8 * 2 + ov * 2 +
+  const size_t need = 256 + (size_t)kAccRows * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + 16 + ov * 8 * 2 + ov * 2 +
                       (size_t)nwarps * (kAccRows * 32 + kOvPriv) * 8;
-  const size_t floor_ = 256 + 256 * 256;   // a lane reads lpos row (code - 1) unclamped: rows -1 .. 254 must be mapped
-  return need > floor_ ? need : floor_;
+  return need;
 }
 __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* raw, int OV, int nwarps) {
   BwdSmem b;
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
   size_t off = 256;
-  b.lpos = reinterpret_cast<float2*>(raw + off); off += (size_t)kIL * 32 * 8;
+  b.lpos = reinterpret_cast<float2*>(raw + off); off += (size_t)kAccRows * 32 * 8;
   b.wacc = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kAccRows * 32 * 8;
   b.wov = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kOvPriv * 8;
   b.opos = reinterpret_cast<float2*>(raw + off); off += ov * 8;
@@ -759,7 +758,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   float* out = g_projects + (size_t)n * Vs * 3;
   for (int i = threadIdx.x; i < Vs * 3; i += blockDim.x) out[i] = 0.f;   // z and untouched vertices stay 0
   for (int i = threadIdx.x; i < nwarps * (kAccRows * 32 + kOvPriv); i += blockDim.x) b.wacc[i] = make_float2(0.f, 0.f);   // + wov
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) reinterpret_cast<float2*>(raw)[i] = make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) b.lpos[kIL * 32 + i] = make_float2(0.f, 0.f);
   if (threadIdx.x == 0) *b.next_row = nwarps;                       // rows 0 .. nwarps-1 are the warps' first rows
   classify_light(b, proj_n, mask_n, ptr, idx, obase, P, OV);
   __syncthreads();
@@ -821,12 +820,14 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     f32x2 c2[4];                                                                                                       \
     float Gv[4];                                                                                                       \
     int li[4];                                                                                                         \
+    uint32_t row[4];                                                                                                   \
     /* (a) four pixels, mutually independent: the arithmetic of the four chains interleaves */                        \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
       const float t0 = (code[j] & 1) ? g[j] : 0.f;                 /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
       Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                  \
       li[j] = code[j] - 1;                                          /* -1 none, >= kIL overflow, 254 re-query */       \
-      const f32x2 e = lds_b64_nv(lpos_sa + (uint32_t)(li[j] * 256));   /* rows -1 .. 254 are inside the allocation */  \
+      row[j] = min((unsigned)li[j], (unsigned)kIL) * 256u;          /* "none" and the rare codes: row kIL */           \
+      const f32x2 e = lds_b64_nv(lpos_sa + row[j]);                                                                    \
       const f32x2 d = sub2(e, GP[j]);                               /* (du, dv) */                                      \
       float du2, dv2;                                                                                                  \
       upk2(mul2(d, d), du2, dv2);                                                                                      \
@@ -839,7 +840,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order; "none" and  */\
     /* the rare codes add into the discarded row kIL, so the common path has no branch                               */\
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
-      const uint32_t a_sa = wacc_sa + min((unsigned)li[j], (unsigned)kIL) * 256u;                                      \
+      const uint32_t a_sa = wacc_sa + row[j];                                                                          \
       sts_b64(a_sa, add2(lds_b64(a_sa), c2[j]));                                                                       \
     }                                                                                                                  \
     if (__any_sync(0xffffffffu, live && max(max(li[0], li[1]), max(li[2], li[3])) >= kIL)) {                           \
@@ -981,7 +982,7 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
                            const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st) {
   if (Vs >= (int)kNoVid) return cudaErrorInvalidValue;              // vertex ids are kept as 16 bits
   // the largest warp count whose blocks still fit three to an SM; at least 4
-  int warps = 6;
+  int warps = 6;                     // measured: 4 x 5 warps and 4 x 4 warps per SM are slower than 3 x 6; 7 warps spill
   while (warps > 4 && 3 * (bwd_smem_bytes(p->ovf, warps) + 1024) > kMaxSmem + 1024) --warps;
   const size_t smem = bwd_smem_bytes(p->ovf, warps);
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
