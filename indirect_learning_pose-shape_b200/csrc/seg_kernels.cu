@@ -281,10 +281,6 @@ __device__ __forceinline__ float2 lds_f2_nv(uint32_t a) {            // read-onl
   asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
   return r;
 }
-// asynchronous request of [p, p + bytes) into L2 (16-byte aligned, multiple of 16): no register, no scoreboard
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ unsigned long long lds_b64(uint32_t a) {
   unsigned long long r;
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
