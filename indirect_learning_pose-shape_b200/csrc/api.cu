@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace smplb200 {
@@ -262,6 +263,28 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
       }
     CU_TRY(upload(&m->BT_hi, bth));
     CU_TRY(upload(&m->BT_lo, btl));
+    // fp16 split of the same matrix for the forward (twice the tensor rate of TF32): B * 2^e = hi + lo with max |B| 2^e in
+    // [2^13, 2^14), so hi carries 11 bits and lo the next 11 (its own quantisation, 2^-24 / 2^e absolute, is far below
+    // fp32's); products of two fp16 values are exact in the fp32 accumulator.  SMPL_B200_TF32_FWD=1 keeps the TF32 tables.
+    float bmax = 0.f;
+    for (size_t i = 0; i < (size_t)kK * C; ++i) bmax = fmaxf(bmax, fabsf(m->h_Bm[i]));
+    const char* env_tf32 = getenv("SMPL_B200_TF32_FWD");
+    if (bmax > 0.f && std::isfinite(bmax) && !(env_tf32 && env_tf32[0] == '1')) {
+      int ex = 0;
+      frexpf(bmax, &ex);                                   // bmax = f * 2^ex, f in [0.5, 1)
+      m->bt16_scale = ldexpf(1.0f, 14 - ex);
+      std::vector<uint16_t> b16h((size_t)m->LD * kKPad, 0), b16l((size_t)m->LD * kKPad, 0);
+      for (int k = 0; k < kK; ++k)
+        for (size_t c = 0; c < C; ++c) {
+          const float x = m->h_Bm[(size_t)k * C + c] * m->bt16_scale;
+          const __half h = __float2half_rn(x);
+          const __half l = __float2half_rn(x - __half2float(h));
+          b16h[c * kKPad + k] = __half_as_ushort(h);
+          b16l[c * kKPad + k] = __half_as_ushort(l);
+        }
+      CU_TRY(upload(&m->BT16_hi, b16h));
+      CU_TRY(upload(&m->BT16_lo, b16l));
+    }
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     m->num_sms = prop.multiProcessorCount;
@@ -341,7 +364,7 @@ void smpl_b200_model_destroy(SmplB200Model* m) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
-  cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->BT_hi); cudaFree(m->BT_lo); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
+  cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->BT_hi); cudaFree(m->BT_lo); cudaFree(m->BT16_hi); cudaFree(m->BT16_lo); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
   cudaFree(m->jr_ptr); cudaFree(m->jr_vert); cudaFree(m->jr_w);
   for (int i = 0; i < kMaxVsCache; ++i) {
     cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].Bs_hi); cudaFree(m->vst[i].Bs_lo); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w); cudaFree(m->vst[i].csc_q);

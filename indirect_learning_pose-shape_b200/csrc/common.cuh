@@ -70,6 +70,9 @@ struct SmplB200Model {
   float* Bm = nullptr;       // [kKPad][LD]
   float* BT_hi = nullptr;    // [LD][kKPad]  Bm transposed (K-major) for the tensor-core forward, TF32 hi part
   float* BT_lo = nullptr;    // [LD][kKPad]  ... and the exact remainder
+  uint16_t* BT16_hi = nullptr;  // [LD][kKPad] halfs: fp16(B * bt16_scale)            (fp16-split forward; null = use TF32)
+  uint16_t* BT16_lo = nullptr;  // [LD][kKPad] halfs: fp16(B * bt16_scale - hi)
+  float bt16_scale = 1.0f;      // power of two that puts max |B| near 2^14
   int num_sms = 148;
   float* Jt = nullptr;       // [kJ*3]
   float* Jd = nullptr;       // [kJ*3][kBetas]
@@ -104,12 +107,16 @@ const VsTables* get_vs_tables(const SmplB200Model* m, int vs);
 
 // kernels launchers (implemented in the *_kernels.cu files). All return cudaError_t of the launch.
 // X_lo == null: X receives the blend coefficients.  Otherwise X receives their TF32 hi part and X_lo the remainder.
+// X_lo == null: X receives the blend coefficients.  Otherwise the tensor-core split: TF32 hi / remainder as fp32, or
+// (model built with the fp16 tables) [N][kKPad] halfs fp16(64 x) / fp16(64 x - hi).
 cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, float* X, float* X_lo, float* A,
                             float* Jtr, cudaStream_t st);
 cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const float* Xl, int N, float* v_posed,
                                 cudaStream_t st);
 cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const float* gvp_hi, const float* gvp_lo,
                                 size_t gvp_ld, int N, float* g_X, cudaStream_t st);
+constexpr float kXScale16 = 64.0f;     // blend coefficients are scaled by 2^6 before their fp16 split: |x| < 1023 (pose
+                                       // features are bounded by 2, betas by a few units); lo's quantisation is 1e-9 absolute
 constexpr int kDenseBatch = 64;   // from this batch on the blend products run on the tensor cores
 
 // exact split of an fp32 value for the 3xTF32 product: hi keeps the 10 mantissa bits TF32 has, lo = x - hi

@@ -7,6 +7,7 @@
 //   joint regression ................... keras_smpl/batch_smpl.py:106-115  (folded: J = Jt + Jd*beta, exact algebra)
 //   pose_feature ....................... keras_smpl/batch_smpl.py:122
 //   batch_global_rigid_transformation .. keras_smpl/batch_smpl.py:168-228
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace smplb200 {
@@ -147,7 +148,7 @@ __device__ __forceinline__ Chain forward_chain(const float* __restrict__ prm, co
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pose_fwd_kernel(const float* __restrict__ params, int N, const float* __restrict__ Jt, const float* __restrict__ Jd,
-                const TreeInfo tree, float* __restrict__ X, float* __restrict__ Xlo, float* __restrict__ A,
+                const TreeInfo tree, float* __restrict__ X, float* __restrict__ Xlo, int x16, float* __restrict__ A,
                 float* __restrict__ Jtr) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -156,8 +157,14 @@ pose_fwd_kernel(const float* __restrict__ params, int N, const float* __restrict
   const Chain ch = forward_chain(prm, Jt, Jd, tree, lane);
   float* x = X + (size_t)n * kKPad;
   float* xl = Xlo ? Xlo + (size_t)n * kKPad : nullptr;
-  auto put = [&](int i, float v) {              // tensor-core path: exact TF32 split x = hi + lo
-    if (xl) { const float h = tf32_hi(v); x[i] = h; xl[i] = v - h; }
+  __half* x16h = reinterpret_cast<__half*>(X) + (size_t)n * kKPad;
+  __half* x16l = reinterpret_cast<__half*>(Xlo) + (size_t)n * kKPad;
+  auto put = [&](int i, float v) {              // tensor-core path: exact split x = hi + lo (TF32, or fp16 of 64 x)
+    if (x16) {
+      const float sv = v * kXScale16;
+      const __half h = __float2half_rn(sv);
+      x16h[i] = h; x16l[i] = __float2half_rn(sv - __half2float(h));
+    } else if (xl) { const float h = tf32_hi(v); x[i] = h; xl[i] = v - h; }
     else x[i] = v;
   };
   if (lane < kBetas) put(lane, prm[76 + lane]);
@@ -316,7 +323,8 @@ cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, 
                             float* Jtr, cudaStream_t st) {
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
   LaunchScope scope(KID_POSE_FWD, st);
-  pose_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, X, X_lo, A, Jtr);
+  pose_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, X, X_lo,
+                                                         (X_lo && m->BT16_hi) ? 1 : 0, A, Jtr);
   return cudaGetLastError();
 }
 

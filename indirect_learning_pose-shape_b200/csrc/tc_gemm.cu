@@ -74,15 +74,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives on `bar` when all prior MMAs have completed
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  if (F16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -111,21 +123,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                       // [61,64) layout type: SWIZZLE_128B
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+// cute::UMMA::InstrDescriptor for kind::tf32 (operand format 2 = TF32) or kind::f16 (format 0 = F16), fp32 accumulate,
+// both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16) {
   return (1u << 4)                 // [4,6)   c_format = F32
-         | (2u << 7)               // [7,10)  a_format = TF32
-         | (2u << 10)              // [10,13) b_format = TF32
+         | ((f16 ? 0u : 2u) << 7)  // [7,10)  a_format
+         | ((f16 ? 0u : 2u) << 10) // [10,13) b_format
          | ((uint32_t)(N >> 3) << 17)   // [17,23) n_dim
          | ((uint32_t)(M >> 4) << 24);  // [24,29) m_dim
 }
 
-template <int BN, bool BIAS>
+// F16: operands are fp16 hi/lo pairs (64 per 128-byte K block, UMMA K = 16); the accumulated sum is multiplied by
+// out_scale (the inverse of the operands' power-of-two scales) before the bias.
+template <int BN, bool BIAS, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
-tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int kblocks, int tiles_m,
-                   int tiles_n) {
+                   int tiles_n, float out_scale) {
+  constexpr int kBKe = F16 ? 2 * kBK : kBK;            // operand elements per K block (one 128-byte swizzle row)
   constexpr int kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
   constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   constexpr int kAccStride = 128;                      // TMEM columns between partial-tile buffers
@@ -165,10 +181,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
           mbar_expect_tx(&full[stage], kStageBytes);
-          tma_load_2d(st, &tmAh, &full[stage], kb * kBK, m0);
-          tma_load_2d(st + kABytes, &tmAl, &full[stage], kb * kBK, m0);
-          tma_load_2d(st + 2 * kABytes, &tmBh, &full[stage], kb * kBK, n0);
-          tma_load_2d(st + 2 * kABytes + kBBytes, &tmBl, &full[stage], kb * kBK, n0);
+          tma_load_2d(st, &tmAh, &full[stage], kb * kBKe, m0);
+          tma_load_2d(st + kABytes, &tmAl, &full[stage], kb * kBKe, m0);
+          tma_load_2d(st + 2 * kABytes, &tmBh, &full[stage], kb * kBKe, n0);
+          tma_load_2d(st + 2 * kABytes + kBBytes, &tmBl, &full[stage], kb * kBKe, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -176,7 +192,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      constexpr uint32_t idesc = make_idesc(kBM, BN, F16);
       int stage = 0, buf = 0;
       uint32_t phase = 0, buf_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -189,15 +205,15 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint64_t dAh = make_smem_desc(sa), dAl = make_smem_desc(sa + kABytes);
           const uint64_t dBh = make_smem_desc(sa + 2 * kABytes), dBl = make_smem_desc(sa + 2 * kABytes + kBBytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {          // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+          for (int k = 0; k < kBK / 8; ++k) {          // UMMA K = 8 tf32 / 16 f16 = 32 bytes: advance the start address by 2 (x16 B)
             const uint64_t o = (uint64_t)(k * 2);
-            umma_tf32(tmem_d, dAl + o, dBh + o, idesc, k ? 1u : 0u);           // small terms first; fresh per K block
-            umma_tf32(tmem_d, dAh + o, dBl + o, idesc, 1u);
+            umma<F16>(tmem_d, dAl + o, dBh + o, idesc, k ? 1u : 0u);           // small terms first; fresh per K block
+            umma<F16>(tmem_d, dAh + o, dBl + o, idesc, 1u);
           }
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t o = (uint64_t)(k * 2);
-            umma_tf32(tmem_d, dAh + o, dBh + o, idesc, 1u);
+            umma<F16>(tmem_d, dAh + o, dBh + o, idesc, 1u);
           }
           umma_commit(&empty[stage]);                  // frees this smem stage once the MMAs above have read it
           umma_commit(&tfull[buf]);                    // this K block's partial tile is complete
@@ -247,7 +263,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         for (int c = 0; c < HN; c += 8) {
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = acc[c + e];
+          for (int e = 0; e < 8; ++e) o[e] = F16 ? acc[c + e] * out_scale : acc[c + e];
           if (BIAS) {
             const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c);
             const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c + 4);
@@ -281,35 +297,39 @@ cudaError_t load_encode() {
   return cudaSuccess;
 }
 
-// 2-D fp32 tensor [rows][cols] with row pitch ld (floats); box = 32 columns x box_rows, SWIZZLE_128B, zero OOB fill.
-cudaError_t make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+// 2-D tensor [rows][cols] of fp32 (or fp16) with row pitch ld (elements); box = 128 bytes of columns x box_rows,
+// SWIZZLE_128B, zero OOB fill (a K that is not a multiple of the box reads zeros past its end).
+cudaError_t make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, bool f16) {
+  const size_t es = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int BN, bool BIAS>
-cudaError_t launch_gemm(const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb, float* D,
-                        int ldd, const float* bias, int M, int Ntot, int K, int num_sms, cudaStream_t st) {
+template <int BN, bool BIAS, bool F16>
+cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh, const void* Bl, int ldb, float* D,
+                        int ldd, const float* bias, int M, int Ntot, int K, float out_scale, int num_sms, cudaStream_t st) {
   cudaError_t e = load_encode();
   if (e != cudaSuccess) return e;
   CUtensorMap mAh, mAl, mBh, mBl;
-  if ((e = make_map(&mAh, Ah, M, K, lda, kBM)) != cudaSuccess) return e;
-  if ((e = make_map(&mAl, Al, M, K, lda, kBM)) != cudaSuccess) return e;
-  if ((e = make_map(&mBh, Bh, Ntot, K, ldb, BN)) != cudaSuccess) return e;
-  if ((e = make_map(&mBl, Bl, Ntot, K, ldb, BN)) != cudaSuccess) return e;
+  if ((e = make_map(&mAh, Ah, M, K, lda, kBM, F16)) != cudaSuccess) return e;
+  if ((e = make_map(&mAl, Al, M, K, lda, kBM, F16)) != cudaSuccess) return e;
+  if ((e = make_map(&mBh, Bh, Ntot, K, ldb, BN, F16)) != cudaSuccess) return e;
+  if ((e = make_map(&mBl, Bl, Ntot, K, ldb, BN, F16)) != cudaSuccess) return e;
   constexpr int kStageBytes = 2 * kBM * kBK * 4 + 2 * BN * kBK * 4;
   const size_t smem = (size_t)kStages * kStageBytes + 256 + 1024;
-  e = cudaFuncSetAttribute(tf32x3_gemm_kernel<BN, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(split3_gemm_kernel<BN, BIAS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = Ntot / BN;
   const int grid = min(tiles_m * tiles_n, num_sms);
-  tf32x3_gemm_kernel<BN, BIAS><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, K / kBK, tiles_m, tiles_n);
+  constexpr int kBKe = F16 ? 2 * kBK : kBK;
+  split3_gemm_kernel<BN, BIAS, F16><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, (K + kBKe - 1) / kBKe,
+                                                                   tiles_m, tiles_n, out_scale);
   return cudaGetLastError();
 }
 
@@ -319,16 +339,19 @@ cudaError_t launch_gemm(const float* Ah, const float* Al, int lda, const float* 
 cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const float* Xl, int N, float* v_posed,
                                 cudaStream_t st) {
   LaunchScope scope(KID_BLEND_FWD, st);
-  return launch_gemm<128, true>(Xh, Xl, kKPad, m->BT_hi, m->BT_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD, kKPad,
-                                m->num_sms, st);
+  if (m->BT16_hi)   // fp16 split: Xh / Xl hold [N][kKPad] halfs (launch_pose_fwd, xmode 2)
+    return launch_gemm<128, true, true>(Xh, Xl, kKPad, m->BT16_hi, m->BT16_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD,
+                                        kK, 1.0f / (kXScale16 * m->bt16_scale), m->num_sms, st);
+  return launch_gemm<128, true, false>(Xh, Xl, kKPad, m->BT_hi, m->BT_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD, kKPad,
+                                       1.0f, m->num_sms, st);
 }
 
 // g_X[N][224] = g_vp[N][Kp] * Bs[224][Kp]^T   (Kp a multiple of 32)
 cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const float* gvp_hi, const float* gvp_lo,
                                 size_t gvp_ld, int N, float* g_X, cudaStream_t st) {
   LaunchScope scope(KID_BLEND_BWD, st);
-  return launch_gemm<kKPad / 2, false>(gvp_hi, gvp_lo, (int)gvp_ld, t->Bs_hi, t->Bs_lo, t->Kp, g_X, kKPad, nullptr, N,
-                                       kKPad, t->Kp, m->num_sms, st);
+  return launch_gemm<kKPad / 2, false, false>(gvp_hi, gvp_lo, (int)gvp_ld, t->Bs_hi, t->Bs_lo, t->Kp, g_X, kKPad, nullptr,
+                                              N, kKPad, t->Kp, 1.0f, m->num_sms, st);
 }
 
 }  // namespace smplb200
