@@ -283,6 +283,179 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
 }
 
+// ---- forward blend, fp16 split, B panel resident --------------------------------------------------------------------
+// With fp16 operands the tile-per-CTA kernel above is bound by L2 -> shared traffic: every 128 x 128 output tile pulls
+// 128 KB of A and 128 KB of B through TMA (8.4 TB/s at 0.63 ms).  Here a CTA keeps one B panel (128 output columns, the
+// whole K = 4 blocks of 64, hi and lo: 128 KB) in shared memory and streams kPanelRows consecutive A tiles past it, so a
+// tile costs 128 KB + 128 KB / kPanelRows.  Work unit = (column panel, chunk of row tiles); units go to the CTAs
+// round-robin.  Pipeline roles and the per-K-block register accumulation are those of the kernel above.
+constexpr int kPanelKB = 4;          // K blocks of the forward (K = 217 <= 256 halfs)
+constexpr int kPanelRows = 16;       // row tiles per unit
+constexpr int kPanelStages = 3;      // A stages (hi + lo = 32 KB each)
+
+__global__ void __launch_bounds__(kThreads, 1)
+blend_f16_panel_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                       float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int tiles_m, int tiles_n,
+                       float out_scale) {
+  constexpr int BN = 128, kBKe = 2 * kBK;
+  constexpr int kTile = kBM * kBK * 4;                 // one 128-row x 128-byte operand box: 16 KB
+  constexpr int kPanelBytes = kPanelKB * 2 * kTile;    // B panel: [kb][hi, lo]
+  constexpr int kStageBytes = 2 * kTile;               // A stage: hi, lo
+  constexpr int kAccStride = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stages = smem + kPanelBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + kPanelStages * kStageBytes);
+  uint64_t* empty = full + kPanelStages;
+  uint64_t* tfull = empty + kPanelStages;
+  uint64_t* tempty = tfull + kTmemBufs;
+  uint64_t* bfull = tempty + kTmemBufs;                // B panel landed
+  uint64_t* bempty = bfull + 1;                        // every MMA of the unit has read the panel
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks_m = (tiles_m + kPanelRows - 1) / kPanelRows;
+  const int nunits = tiles_n * chunks_m;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPanelStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < kTmemBufs; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    mbar_init(bfull, 1); mbar_init(bempty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, bphase = 0;
+      for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int np = unit / chunks_m, mc = unit - np * chunks_m;
+        const int n0 = np * BN;
+        const int mt0 = mc * kPanelRows, mt1 = min(mt0 + kPanelRows, tiles_m);
+        mbar_wait(bempty, bphase ^ 1);                 // the previous unit's MMAs are done with the panel
+        mbar_expect_tx(bfull, kPanelBytes);
+        for (int kb = 0; kb < kPanelKB; ++kb) {
+          tma_load_2d(smem + (kb * 2) * kTile, &tmBh, bfull, kb * kBKe, n0);
+          tma_load_2d(smem + (kb * 2 + 1) * kTile, &tmBl, bfull, kb * kBKe, n0);
+        }
+        bphase ^= 1;
+        for (int mt = mt0; mt < mt1; ++mt) {
+          for (int kb = 0; kb < kPanelKB; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = stages + stage * kStageBytes;
+            mbar_expect_tx(&full[stage], kStageBytes);
+            tma_load_2d(st, &tmAh, &full[stage], kb * kBKe, mt * kBM);
+            tma_load_2d(st + kTile, &tmAl, &full[stage], kb * kBKe, mt * kBM);
+            if (++stage == kPanelStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN, true);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, buf_phase = 0, bphase = 0;
+      for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int mc = unit % chunks_m;
+        const int mt0 = mc * kPanelRows, mt1 = min(mt0 + kPanelRows, tiles_m);
+        mbar_wait(bfull, bphase);
+        bphase ^= 1;
+        for (int mt = mt0; mt < mt1; ++mt) {
+          for (int kb = 0; kb < kPanelKB; ++kb) {
+            mbar_wait(&tempty[buf], buf_phase ^ 1);
+            mbar_wait(&full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+            const uint32_t sa = smem_u32(stages + stage * kStageBytes);
+            const uint32_t sb = smem_u32(smem + (kb * 2) * kTile);
+            const uint64_t dAh = make_smem_desc(sa), dAl = make_smem_desc(sa + kTile);
+            const uint64_t dBh = make_smem_desc(sb), dBl = make_smem_desc(sb + kTile);
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              umma<true>(tmem_d, dAl + o, dBh + o, idesc, k ? 1u : 0u);
+              umma<true>(tmem_d, dAh + o, dBl + o, idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              umma<true>(tmem_d, dAh + o, dBh + o, idesc, 1u);
+            }
+            umma_commit(&empty[stage]);
+            umma_commit(&tfull[buf]);
+            if (++stage == kPanelStages) { stage = 0; phase ^= 1; }
+            if (++buf == kTmemBufs) { buf = 0; buf_phase ^= 1; }
+          }
+        }
+        umma_commit(bempty);                           // arrives once every MMA above has completed
+      }
+    }
+  } else {
+    // ===== accumulate (fp32 registers, round-to-nearest) + epilogue: as in split3_gemm_kernel =====
+    constexpr int HN = BN / 2;
+    const int q = warp & 3;
+    const int hcol = (warp - 2) >= 4 ? HN : 0;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+      const int np = unit / chunks_m, mc = unit - np * chunks_m;
+      const int n0 = np * BN;
+      const int mt0 = mc * kPanelRows, mt1 = min(mt0 + kPanelRows, tiles_m);
+      for (int mt = mt0; mt < mt1; ++mt) {
+        float acc[HN];
+#pragma unroll
+        for (int i = 0; i < HN; ++i) acc[i] = 0.f;
+        for (int kb = 0; kb < kPanelKB; ++kb) {
+          mbar_wait(&tfull[buf], buf_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride) + (uint32_t)hcol;
+          uint32_t r[HN / 16][16];
+#pragma unroll
+          for (int c = 0; c < HN; c += 16) tmem_ld_32x32b_x16(taddr + c, r[c / 16]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < HN; ++c) acc[c] += __uint_as_float(r[c / 16][c % 16]);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+          if (++buf == kTmemBufs) { buf = 0; buf_phase ^= 1; }
+        }
+        const int row = mt * kBM + q * 32 + lane;
+        if (row < M) {
+          float* drow = D + (size_t)row * ldd + n0 + hcol;
+#pragma unroll
+          for (int c = 0; c < HN; c += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(acc[c + e], out_scale), bb[e]);
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + c), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                         "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                         : "memory");
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -339,9 +512,24 @@ cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh,
 cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const float* Xl, int N, float* v_posed,
                                 cudaStream_t st) {
   LaunchScope scope(KID_BLEND_FWD, st);
-  if (m->BT16_hi)   // fp16 split: Xh / Xl hold [N][kKPad] halfs (launch_pose_fwd, xmode 2)
-    return launch_gemm<128, true, true>(Xh, Xl, kKPad, m->BT16_hi, m->BT16_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD,
-                                        kK, 1.0f / (kXScale16 * m->bt16_scale), m->num_sms, st);
+  if (m->BT16_hi) {   // fp16 split: Xh / Xl hold [N][kKPad] halfs (launch_pose_fwd with the fp16 tables)
+    cudaError_t e = load_encode();
+    if (e != cudaSuccess) return e;
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if ((e = make_map(&mAh, Xh, N, kK, kKPad, kBM, true)) != cudaSuccess) return e;
+    if ((e = make_map(&mAl, Xl, N, kK, kKPad, kBM, true)) != cudaSuccess) return e;
+    if ((e = make_map(&mBh, m->BT16_hi, m->LD, kK, kKPad, 128, true)) != cudaSuccess) return e;
+    if ((e = make_map(&mBl, m->BT16_lo, m->LD, kK, kKPad, 128, true)) != cudaSuccess) return e;
+    constexpr int kTile = kBM * kBK * 4;
+    const size_t smem = (size_t)(kPanelKB * 2 + kPanelStages * 2) * kTile + 256 + 1024;
+    e = cudaFuncSetAttribute(blend_f16_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int tiles_m = (N + kBM - 1) / kBM, tiles_n = m->LD / 128;
+    const int nunits = tiles_n * ((tiles_m + kPanelRows - 1) / kPanelRows);
+    blend_f16_panel_kernel<<<min(nunits, m->num_sms), kThreads, smem, st>>>(mAh, mAl, mBh, mBl, v_posed, m->LD, m->vt_pad, N,
+                                                                           tiles_m, tiles_n, 1.0f / (kXScale16 * m->bt16_scale));
+    return cudaGetLastError();
+  }
   return launch_gemm<128, true, false>(Xh, Xl, kKPad, m->BT_hi, m->BT_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD, kKPad,
                                        1.0f, m->num_sms, st);
 }
