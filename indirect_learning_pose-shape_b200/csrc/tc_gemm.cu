@@ -290,17 +290,16 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 // tile costs 128 KB + 128 KB / kPanelRows.  Work unit = (column panel, chunk of row tiles); units go to the CTAs
 // round-robin.  Pipeline roles and the per-K-block register accumulation are those of the kernel above.
 constexpr int kPanelKB = 4;          // K blocks of the forward (K = 217 <= 256 halfs)
-constexpr int kPanelRows = 16;       // row tiles per unit
-constexpr int kPanelStages = 3;      // A stages (hi + lo = 32 KB each)
-
+template <int BN, int kPanelStages, int kPanelRows>   // output columns per panel, A stages (hi + lo = 32 KB each), row tiles per unit
 __global__ void __launch_bounds__(kThreads, 1)
 blend_f16_panel_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                        float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int tiles_m, int tiles_n,
                        float out_scale) {
-  constexpr int BN = 128, kBKe = 2 * kBK;
+  constexpr int kBKe = 2 * kBK;
   constexpr int kTile = kBM * kBK * 4;                 // one 128-row x 128-byte operand box: 16 KB
-  constexpr int kPanelBytes = kPanelKB * 2 * kTile;    // B panel: [kb][hi, lo]
+  constexpr int kBTile = BN * kBK * 4;                 // one BN-row box of B
+  constexpr int kPanelBytes = kPanelKB * 2 * kBTile;   // B panel: [kb][hi, lo]
   constexpr int kStageBytes = 2 * kTile;               // A stage: hi, lo
   constexpr int kAccStride = 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -344,8 +343,8 @@ blend_f16_panel_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
         mbar_wait(bempty, bphase ^ 1);                 // the previous unit's MMAs are done with the panel
         mbar_expect_tx(bfull, kPanelBytes);
         for (int kb = 0; kb < kPanelKB; ++kb) {
-          tma_load_2d(smem + (kb * 2) * kTile, &tmBh, bfull, kb * kBKe, n0);
-          tma_load_2d(smem + (kb * 2 + 1) * kTile, &tmBl, bfull, kb * kBKe, n0);
+          tma_load_2d(smem + (kb * 2) * kBTile, &tmBh, bfull, kb * kBKe, n0);
+          tma_load_2d(smem + (kb * 2 + 1) * kBTile, &tmBl, bfull, kb * kBKe, n0);
         }
         bphase ^= 1;
         for (int mt = mt0; mt < mt1; ++mt) {
@@ -378,9 +377,9 @@ blend_f16_panel_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
             const uint32_t sa = smem_u32(stages + stage * kStageBytes);
-            const uint32_t sb = smem_u32(smem + (kb * 2) * kTile);
+            const uint32_t sb = smem_u32(smem + (kb * 2) * kBTile);
             const uint64_t dAh = make_smem_desc(sa), dAl = make_smem_desc(sa + kTile);
-            const uint64_t dBh = make_smem_desc(sb), dBl = make_smem_desc(sb + kTile);
+            const uint64_t dBh = make_smem_desc(sb), dBl = make_smem_desc(sb + kBTile);
 #pragma unroll
             for (int k = 0; k < kBK / 8; ++k) {
               const uint64_t o = (uint64_t)(k * 2);
@@ -404,6 +403,7 @@ blend_f16_panel_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
   } else {
     // ===== accumulate (fp32 registers, round-to-nearest) + epilogue: as in split3_gemm_kernel =====
     constexpr int HN = BN / 2;
+    static_assert(HN % 16 == 0, "whole x16 TMEM loads");
     const int q = warp & 3;
     const int hcol = (warp - 2) >= 4 ? HN : 0;
     int buf = 0;
@@ -518,16 +518,18 @@ cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const f
     CUtensorMap mAh, mAl, mBh, mBl;
     if ((e = make_map(&mAh, Xh, N, kK, kKPad, kBM, true)) != cudaSuccess) return e;
     if ((e = make_map(&mAl, Xl, N, kK, kKPad, kBM, true)) != cudaSuccess) return e;
-    if ((e = make_map(&mBh, m->BT16_hi, m->LD, kK, kKPad, 128, true)) != cudaSuccess) return e;
-    if ((e = make_map(&mBl, m->BT16_lo, m->LD, kK, kKPad, 128, true)) != cudaSuccess) return e;
-    constexpr int kTile = kBM * kBK * 4;
-    const size_t smem = (size_t)(kPanelKB * 2 + kPanelStages * 2) * kTile + 256 + 1024;
-    e = cudaFuncSetAttribute(blend_f16_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // measured (N = 16384): <128, 3, 16> 0.55 ms; 2 stages 0.61; 8 rows 0.57; 32 rows 0.60; <96, 4, 16> 0.58; <64, 5, 16> 0.66
+    constexpr int kPanelBN = 128, kPanelStages = 3, kPanelRows = 16;
+    if ((e = make_map(&mBh, m->BT16_hi, m->LD, kK, kKPad, kPanelBN, true)) != cudaSuccess) return e;
+    if ((e = make_map(&mBl, m->BT16_lo, m->LD, kK, kKPad, kPanelBN, true)) != cudaSuccess) return e;
+    const size_t smem = (size_t)kPanelKB * 2 * kPanelBN * 128 + (size_t)kPanelStages * 2 * kBM * 128 + 256 + 1024;
+    e = cudaFuncSetAttribute(blend_f16_panel_kernel<kPanelBN, kPanelStages, kPanelRows>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int tiles_m = (N + kBM - 1) / kBM, tiles_n = m->LD / 128;
+    const int tiles_m = (N + kBM - 1) / kBM, tiles_n = m->LD / kPanelBN;
     const int nunits = tiles_n * ((tiles_m + kPanelRows - 1) / kPanelRows);
-    blend_f16_panel_kernel<<<min(nunits, m->num_sms), kThreads, smem, st>>>(mAh, mAl, mBh, mBl, v_posed, m->LD, m->vt_pad, N,
-                                                                           tiles_m, tiles_n, 1.0f / (kXScale16 * m->bt16_scale));
+    blend_f16_panel_kernel<kPanelBN, kPanelStages, kPanelRows><<<min(nunits, m->num_sms), kThreads, smem, st>>>(
+        mAh, mAl, mBh, mBl, v_posed, m->LD, m->vt_pad, N, tiles_m, tiles_n, 1.0f / (kXScale16 * m->bt16_scale));
     return cudaGetLastError();
   }
   return launch_gemm<128, true, false>(Xh, Xl, kKPad, m->BT_hi, m->BT_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD, kKPad,
