@@ -58,10 +58,11 @@ KERNEL_BYTES = {
 }
 
 
-# DRAM bytes per sample actually moved by each kernel (dram__bytes_read.sum + dram__bytes_write.sum, one ncu capture of
-# tools/prof_step.py --batch 4096, profiles/r1_v22_dram_traffic.csv); scaled by the batch for `roofline.traffic`
+# DRAM bytes per sample actually moved by each kernel (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
+# capture: the seg kernels from profiles/r1_seg_v32_ncu.txt (tools/prof_step.py --batch 2048), the others from
+# profiles/r1_v22_dram_traffic.csv (--batch 4096)); scaled by the batch for `roofline.traffic`
 KERNEL_TRAFFIC = {
-    "seg_fwd": 36.2e3 + 371.4e3, "seg_bwd": 402.8e3 + 24.8e3, "lbs_fwd": 84.3e3 + 85.8e3, "blend_fwd": 29.1e3 + 72.1e3,
+    "seg_fwd": 45.2e3 + 371.0e3, "seg_bwd": 408.6e3 + 26.1e3, "lbs_fwd": 84.3e3 + 85.8e3, "blend_fwd": 29.1e3 + 72.1e3,
     "lbs_bwd_vertex": 100.5e3 + 28.4e3, "blend_bwd": 35.1e3 + 0.0e3, "mask": 16.5e3 + 0.3e3, "pose_fwd": 0.3e3,
     "pose_bwd": 2.4e3,
 }
@@ -333,7 +334,7 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                     "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (KERNEL_TRAFFIC[dom] * B if (dom in KERNEL_TRAFFIC and not args.seg_only) else None),
-                    "traffic_source": "ncu dram__bytes_read+write per sample at batch 4096 (profiles/r1_v22_dram_traffic.csv) x batch",
+                    "traffic_source": "ncu dram__bytes_read+write per sample (profiles/r1_seg_v32_ncu.txt, r1_v22_dram_traffic.csv) x batch",
                     "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": per_kernel[dom]["ms_per_launch"]}
     step_bytes = (BYTES_STEP if not args.seg_only else BYTES_STEP - V * 12 - VS_COUNT * 16)
     step_frac = step_bytes * (B / (ms_step * 1e-3)) / 1e9 / peak

@@ -295,7 +295,8 @@ def test_seg_all_visible_full_resolution(pkg, host_model, parts_by_vs, make_para
 
 @pytest.mark.parametrize("n", [64, 130])
 def test_full_path_dense_batch(pkg, host_model, parts_by_vs, make_params, n):
-    """Batches >= 64 take the tensor-core (tcgen05, 3xTF32) blend path; same tolerances as the small-batch path."""
+    """Batches >= 64 take the tensor-core (tcgen05, fp16-split forward / 3xTF32 backward) blend path; same tolerances as
+    the small-batch path."""
     wh, vs = 48, 5
     p = make_params(n, wh, seed=101)
     ref = np_oracle.decode(host_model, p, wh, vs, parts_by_vs[vs])
@@ -305,6 +306,24 @@ def test_full_path_dense_batch(pkg, host_model, parts_by_vs, make_params, n):
     assert np.abs(out["joints"].cpu().numpy() - ref["J_transformed"]).max() <= TOL_GEOM
     assert np.abs(out["projects"].cpu().numpy() - ref["projects"]).max() <= 2.5 * TOL_GEOM   # see test_projection
     assert (_labels(out["seg"].cpu().numpy()) != _labels(ref["seg"])).mean() <= 5e-3
+
+
+def test_blend_fp16_split_and_tf32_paths_agree(pkg, host_model, make_params, monkeypatch):
+    """The dense-batch forward blend runs as fp16-split tensor-core products (default) or 3xTF32
+    (SMPL_B200_TF32_FWD=1 when the model handle is created): both inside the geometry tolerance, and within 1e-6 of
+    each other."""
+    import copy
+    n, wh = 200, 48
+    p = make_params(n, wh, seed=131)
+    p[0, 76:] = [3.0, -3.0, 2.5, -2.0, 1.5, 3.0, -3.0, 0.1, -0.1, 0.0]        # betas at the sampler's clip
+    ref = np_oracle.smpl_layer_call(host_model, p)
+    got = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SMPL_B200_TF32_FWD", flag)
+        dec = pkg.SmplDecoder(copy.copy(host_model), wh, 5, device=dev())     # a new model handle reads the variable
+        got[flag] = dec(t(p), seg=False)["verts"].cpu().numpy()
+        assert np.abs(got[flag] - ref).max() <= TOL_GEOM, flag
+    assert np.abs(got["0"] - got["1"]).max() <= 1e-6
 
 
 # ---------------------------------------------------------------------------------------------------------------
