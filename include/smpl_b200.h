@@ -81,7 +81,9 @@ int smpl_b200_profile_enable(int on);
 int smpl_b200_profile_collect(SmplB200KernelStat* out, int max_stats, int* num_stats);
 
 /* ---- handles ---------------------------------------------------------------------------------------- */
-/* SMPLLayer.__init__/build (batch_smpl.py:24-94): uploads and repacks the constants on `device`. */
+/* SMPLLayer.__init__/build (batch_smpl.py:24-94): uploads and repacks the constants on `device`.
+ * Environment, read here: SMPL_B200_TF32_FWD=1 builds the handle without the fp16-split blend tables, so the dense-batch
+ * forward blend runs as 3xTF32 instead (same tolerance, slower; blend coefficients beyond |x| < 1023 need it). */
 int smpl_b200_model_create(const SmplB200HostModel* host, int device, SmplB200Model** out);
 void smpl_b200_model_destroy(SmplB200Model* model);
 int smpl_b200_model_num_verts(const SmplB200Model* model);

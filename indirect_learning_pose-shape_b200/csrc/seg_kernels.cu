@@ -6,16 +6,18 @@
 //   out[n, wh-1-r, c, :] = [bg, s_0 .. s_30]          :66-68   (rows flipped)
 //
 // exp, sqrt and the multiply by w are monotone, so  max_i exp(-(d_i w_i)) = exp(-min_i (d_i w_i)): both directions are
-// an exact weighted-nearest-vertex query (arg-min over squared distances computed as fl(fl(du^2)+fl(dv^2)), the same
-// roundings as tf.norm).  Vertices are split by weight once per sample:
+// an exact weighted-nearest-vertex query: the arg-min over fp32 squared distances, computed in the hot loop as
+// fma(du, du, fl(dv^2)) on packed pairs -- one rounding fewer than tf.norm's fl(fl(du^2)+fl(dv^2)), so within one ulp of
+// it; the rare paths (heavy / generic vertices, classification) use the two-rounding form.  Vertices are split by weight
+// once per sample:
 //   light    w == 1        one per occupied z-buffer cell after compute_mask; min over SQUARED distances in the hot loop
 //   heavy    w >= 256      d*w > 128 unless d < 0.5, and exp(-128) is exactly 0 in fp32, so a heavy vertex can only
 //                           reach the one pixel it rounds to: chained per pixel, visited by that pixel alone
 //   generic  anything else evaluated against every pixel (never produced by compute_mask; kept for drop-in inputs)
 //
-// Forward: a warp owns a 16 x 8 pixel tile, a lane a 2 x 2 block of it, so the per-axis squared offsets du^2 and dv^2
-// are shared by the block's pixels.  Once per tile, lane k prunes part k EXACTLY: with i0 the part's vertex nearest the
-// tile centre c, f(g) = d_j^2(g) - d_i0^2(g) is linear in the pixel g, f(g) >= f(c) - 2(|du_j0| hw + |dv_j0| hh) on the
+// Forward: a warp owns a 16 x 8 pixel tile (tiles are taken from a shared counter, the image's centre columns first), a
+// lane a 2 x 2 block of it, so the per-axis squared offsets du^2 and dv^2 are shared by the block's pixels.  Once per
+// tile, lane k prunes part k EXACTLY: with i0 the part's vertex nearest the tile centre c, f(g) = d_j^2(g) - d_i0^2(g) is linear in the pixel g, f(g) >= f(c) - 2(|du_j0| hw + |dv_j0| hh) on the
 // tile, so a vertex whose bound clears a margin (far above the fp32 rounding of the squared distances) can never be the
 // arg-min inside the tile and is dropped from the part's survivor words; the hot loop visits survivors only (about 3
 // per (tile, part) instead of 12).  Eight channels of each pixel are staged per lane and leave as ONE 32-byte store
@@ -26,8 +28,8 @@
 // byte (`saved`, 32 B per pixel, in the layout of the output itself: [n][wh-1-r][c][channel]), so the backward never
 // searches.
 //
-// Backward: lane = channel, a warp walks a contiguous range of output pixels.  The pixel's upstream gradient row is
-// one coalesced 128-byte load and its saved row one 32-byte load; s is recomputed at the recorded arg-min and the
+// Backward: lane = channel, a warp walks output rows (taken from a shared counter) in groups of four pixels.  The
+// pixel's upstream gradient row is one coalesced 128-byte load and its saved row one 32-byte load; s is recomputed at the recorded arg-min and the
 // per-vertex sums accumulate in per-warp PRIVATE shared-memory slots indexed by the part's light slot: lane k is the
 // only writer of part k's slots, so a plain load/add/store replaces atomics (shared fp32 atomicAdd is a CAS loop on
 // sm_100) and no cross-lane reduction is needed.
