@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16384)
-ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=40)   # ~0.3 s: the SM clocks ramp from idle
 args = ap.parse_args()
 pkg = importlib.import_module("indirect_learning_pose-shape_b200")
 synth = importlib.import_module("indirect_learning_pose-shape_b200.synth")
