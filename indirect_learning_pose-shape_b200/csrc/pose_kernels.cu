@@ -226,22 +226,26 @@ pose_bwd_kernel(const float* __restrict__ params, int N, const float* __restrict
   }
 
   // ---- leaves -> root: parents pull from their children, one tree level at a time -------------------------------
+  // A child's whole contribution to its parent, gRG_c R_c^T + gtG_c (x) tl_c  (RG_c = RG_p R_c ; tG_c = RG_p tl_c + tG_p),
+  // is formed in the child's lane, so 12 values cross lanes instead of 24, and a (level, child slot) pair that no lane
+  // uses is skipped altogether (the standard tree uses 12 of the 36).
   for (int d = tree.max_depth; d >= 1; --d) {
+    const M3 a = mul_nt(gRG, ch.rod.R);
+    M3 up;
+    up.m[0] = a.m[0] + gtG.x * ch.tl.x; up.m[1] = a.m[1] + gtG.x * ch.tl.y; up.m[2] = a.m[2] + gtG.x * ch.tl.z;
+    up.m[3] = a.m[3] + gtG.y * ch.tl.x; up.m[4] = a.m[4] + gtG.y * ch.tl.y; up.m[5] = a.m[5] + gtG.y * ch.tl.z;
+    up.m[6] = a.m[6] + gtG.z * ch.tl.x; up.m[7] = a.m[7] + gtG.z * ch.tl.y; up.m[8] = a.m[8] + gtG.z * ch.tl.z;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const int c = tree.child[j][s];
       const bool take = live && c >= 0 && tree.depth[c < 0 ? 0 : c] == d;
+      if (!__any_sync(0xffffffffu, take)) continue;
       const int src = c < 0 ? 0 : c;
-      const M3 cg = shfl_m3(gRG, src);
-      const M3 cR = shfl_m3(ch.rod.R, src);
+      const M3 cu = shfl_m3(up, src);
       const V3 ct = shfl_v3(gtG, src);
-      const V3 cl = shfl_v3(ch.tl, src);
       if (take) {
-        // RG_c = RG_p R_c ; tG_c = RG_p tl_c + tG_p
-        const M3 a = mul_nt(cg, cR);
-        gRG.m[0] += a.m[0] + ct.x * cl.x; gRG.m[1] += a.m[1] + ct.x * cl.y; gRG.m[2] += a.m[2] + ct.x * cl.z;
-        gRG.m[3] += a.m[3] + ct.y * cl.x; gRG.m[4] += a.m[4] + ct.y * cl.y; gRG.m[5] += a.m[5] + ct.y * cl.z;
-        gRG.m[6] += a.m[6] + ct.z * cl.x; gRG.m[7] += a.m[7] + ct.z * cl.y; gRG.m[8] += a.m[8] + ct.z * cl.z;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gRG.m[i] += cu.m[i];
         gtG.x += ct.x; gtG.y += ct.y; gtG.z += ct.z;
       }
     }

@@ -59,6 +59,30 @@ def test_c5_full_batch_properties(pkg, host_model, parts_by_vs, make_params):
     assert float((x2.grad - 2.0 * grad1).abs().max()) <= 1e-6 * float(grad1.abs().max())
 
 
+def test_c5_seg_backward_is_repeatable(pkg, host_model, parts_by_vs, make_params):
+    """The same backward evaluated five times on the same saved state: rows are handed to the warps on demand, so the
+    sums may differ in their last bits, but nothing more.  (An L2 bulk prefetch in this kernel once made ~1 pixel per
+    16384-sample launch read wrong data: differences of the size of a whole vertex gradient, which this test catches.)"""
+    N, wh, vs = 16384, 48, 5
+    dec = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev())
+    with torch.no_grad():
+        out = dec(torch.as_tensor(make_params(N, wh, seed=9), device=dev()))
+    pr, mk = out["projects"].clone(), out["mask"].clone()
+    del out
+    gen = torch.Generator(device=dev()).manual_seed(11)
+    g = torch.randn((N, wh, wh, 32), device=dev(), generator=gen)
+    p = pr.clone().requires_grad_(True)
+    seg = pkg.projects_to_seg([p, mk], wh, vs, parts=parts_by_vs[vs])
+    grads = []
+    for _ in range(5):
+        p.grad = None
+        seg.backward(g, retain_graph=True)
+        grads.append(p.grad.clone())
+    scale = float(grads[0].abs().max())
+    for k in range(1, 5):
+        assert float((grads[k] - grads[0]).abs().max()) <= 2e-6 * scale, k
+
+
 def test_c4_silhouette_large_batch_properties(pkg, host_model, make_params):
     wh, n_src, N = 256, 32, 1024                     # BASELINE's batch is 8192; 1024 keeps the round-end GPU tier short
     dec = pkg.SmplDecoder(host_model, wh, None, device=dev())
