@@ -1,28 +1,36 @@
-// K1 on the 5th-generation tensor cores: error-compensated 3xTF32 GEMM,  D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]).
+// K1 on the 5th-generation tensor cores: error-compensated split-operand GEMMs,  D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]).
 //
 // Both blend products of the SMPL layer are this GEMM (batch_smpl.py:106-108,126-128 forward, their TF autodiff
 // backward):
 //   forward   v_posed[N][LD]  = X[N][224]     * BT[LD][224]^T + v_template      (BT = [shapedirs; posedirs]^T, K-major)
 //   backward  g_X[N][224]     = g_vp[N][Kp]   * Bs[224][Kp]^T
-// fp32 parity (1e-5 on vertices, ~3 ulp on projections) rules out plain TF32, so every operand is supplied as an
-// exact split x = hi + lo with hi = x truncated to TF32 precision (13 low mantissa bits cleared) and lo = x - hi, and
-// the product is accumulated as lo*hi + hi*lo + hi*hi (the dropped lo*lo term is 2^-22 relative).  hi is exactly
-// representable in TF32, so the result does not depend on how the tensor core rounds its inputs.
+// fp32 parity (1e-5 on vertices, ~3 ulp on projections) rules out a plain TF32 or fp16 product, so every operand is
+// supplied as an exact split x = hi + lo and the product is accumulated as lo*hi + hi*lo + hi*hi (the dropped lo*lo
+// term is 2^-22 relative):
+//   backward  3xTF32 (split3_gemm_kernel<.., F16 = false>): hi = x with its 13 low mantissa bits cleared, lo = x - hi;
+//             hi is exactly representable in TF32, so the result does not depend on how the tensor core rounds inputs.
+//             The A operand is the caller's gradient: no fixed scale would keep an fp16 split in range.
+//   forward   fp16 split (blend_f16_panel_kernel; kind::f16 runs at twice the TF32 rate on half the operand bytes): the
+//             blend coefficients are scaled by 2^6 and the blend matrix by the power of two that puts max |B| in
+//             [2^13, 2^14) before hi = fp16(x), lo = fp16(x - hi): 11 + 11 bits, fp16 subnormals bound lo's own error at
+//             1e-9 absolute, fp16 x fp16 products are exact in the fp32 accumulator, and the scales come off exactly in
+//             the epilogue.  SMPL_B200_TF32_FWD=1 at model creation keeps the forward on 3xTF32 (api.cu).
 // The tensor core's own fp32 accumulation is not round-to-nearest, and its error grows with the length of the
 // accumulation chain (measured here: 1.1e-6 on vertices at K=224, 1e-4 relative on gradients at K=4160 when the whole
-// K loop accumulates in TMEM).  So TMEM only ever accumulates ONE K block (32 deep: 12 MMAs); the epilogue warps add
-// each block's partial tile into fp32 REGISTER accumulators with round-to-nearest (Ootomo & Yokota's scheme), while
-// the tensor core works on the next block in the other TMEM buffer.
+// K loop accumulates in TMEM).  So TMEM only ever accumulates ONE K block (128 bytes of K: 12 MMAs); the epilogue warps
+// add each block's partial tile into fp32 REGISTER accumulators with round-to-nearest (Ootomo & Yokota's scheme), while
+// the tensor core works on the next blocks in the other TMEM buffers.
 //
-// Structure (one CTA per SM, persistent over output tiles of 128 x BN, BN = 128 forward / 112 backward):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the four operand boxes (A_hi, A_lo, B_hi, B_lo; 32 fp32 = 128 B
+// Structure of split3_gemm_kernel (one CTA per SM, persistent over output tiles of 128 x BN):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the four operand boxes (A_hi, A_lo, B_hi, B_lo; 128 B of K
 //               wide, SWIZZLE_128B) into a 3-stage ring, completion on a transaction mbarrier
-//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) per K
-//               block into TMEM buffer (block & 1); tcgen05.commit releases the smem stage and publishes the buffer.
+//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma.cta_group::1 (M=128, N=BN, 32 B of K each) per K
+//               block into one of four TMEM buffers; tcgen05.commit releases the smem stage and publishes the buffer.
 //               Owns the TMEM allocation.
 //   warps 2-9   accumulate + epilogue, two warps per TMEM lane quadrant (one per half of the columns): all tcgen05.ld
 //               32x32b.x16 of the block's partial half tile in flight, ONE wait, FADD into BN/2 registers per thread (half
 //               an output row each); after the last block add bias, st.global.v8.f32 (full 32-byte sectors)
+// blend_f16_panel_kernel keeps the same roles and adds a resident B panel (see its own comment).
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cuda.h>
 #include <cudaTypedefs.h>
