@@ -80,7 +80,7 @@ def test_c5_seg_backward_is_repeatable(pkg, host_model, parts_by_vs, make_params
         grads.append(p.grad.clone())
     scale = float(grads[0].abs().max())
     for k in range(1, 5):
-        assert float((grads[k] - grads[0]).abs().max()) <= 2e-6 * scale, k
+        assert float((grads[k] - grads[0]).abs().max()) <= 1e-5 * scale, k     # measured 6e-7; the bug it guards: 0.5
 
 
 def test_c4_silhouette_large_batch_properties(pkg, host_model, make_params):
