@@ -167,6 +167,17 @@ cudaError_t launch_focal_loss_bwd(const float* seg, const float* y_true, const u
                                   cudaStream_t st);
 
 // small device helpers
+// Asynchronous request of [p, p + bytes) into L2 (cp.async.bulk.prefetch: no register, no scoreboard; one thread moves a
+// whole row).  p 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// the same for any byte range: shrunk to its 16-byte aligned interior, so it never leaves the caller's buffer
+__device__ __forceinline__ void prefetch_l2_inner(const void* p, size_t bytes) {
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15;
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(uintptr_t)15;
+  if (e > a) prefetch_l2_bulk(reinterpret_cast<const void*>(a), (uint32_t)(e - a));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

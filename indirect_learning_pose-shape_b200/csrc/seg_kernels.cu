@@ -635,6 +635,10 @@ __device__ void classify_light(const BwdSmem& b, const float* __restrict__ proj,
   if (threadIdx.x < 32) b.lcount[threadIdx.x] = 0;
   if (threadIdx.x < 36) b.obase[threadIdx.x] = obase[min((int)threadIdx.x, P)];
   for (int i = threadIdx.x; i < OV; i += blockDim.x) { b.ovid[i] = (unsigned short)kNoVid; b.oacc[i] = make_float2(0.f, 0.f); }
+  // The initialisation above must be complete before any warp publishes a part's count or overflow entries below.  (This
+  // barrier was missing: a warp held up for a few microseconds -- it took the TMA queue behind the L2 bulk prefetch to do
+  // it -- zeroed a count another warp had already written, and that part's gradient was dropped for the sample.)
+  __syncthreads();
   for (int k = warp; k < P; k += nwarps) {
     const int p0 = ptr[k], p1 = ptr[k + 1], ob = obase[k];
     int nl = 0;
@@ -740,13 +744,17 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   // ALIGNED (wh % 4 == 0, wh >= 8): output rows (already flipped: grid row = wh-1-row) are handed to the warps on demand
   // (a shared counter): the scheduler does not run the warps of a block evenly, and with a fixed share per warp a
   // quarter of the warp-time went into waiting at the final barrier.  A warp walks a row in groups of 4 consecutive
-  // pixels.  Otherwise: each warp owns a contiguous range of 4-pixel groups of the row-major pixel list.
-  // (No L2 prefetch: cp.async.bulk.prefetch.L2 of the next row measured 6 % faster but made the ld.global.nc loads that
-  // follow return wrong data for ~1 .. 20 pixels per launch -- a run-to-run difference of the gradient, found by
-  // tools/determinism_seg.py; prefetch.global.L2 per line is correct and measures no gain at any distance.)
+  // pixels.  The gradient rows (lane 0) and saved rows (lane 1) of a warp's first output row are requested into L2 now,
+  // so the classification below overlaps their DRAM latency; taking row r requests row r + nwarps.
+  // Otherwise: each warp owns a contiguous range of 4-pixel groups of the row-major pixel list, no prefetch.
   const int npx = wh * wh;
   const int nb = (npx + 3) >> 2;
   const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
+  constexpr bool kPrefetch = C32 && ALIGNED;                       // 16-byte aligned rows
+  const unsigned char* pf_base = (lane == 0) ? reinterpret_cast<const unsigned char*>(g_seg + (size_t)n * npx * 32)
+                                             : saved + (size_t)n * npx * 32;
+  const uint32_t pf_row = (uint32_t)wh * ((lane == 0) ? 128u : 32u);   // bytes per output row
+  if (kPrefetch && lane < 2 && warp < wh) prefetch_l2_bulk(pf_base + (size_t)warp * pf_row, pf_row);
   const float* proj_n = projects + (size_t)n * Vs * 3;
   const float* mask_n = mask + (size_t)n * Vs;
   float* out = g_projects + (size_t)n * Vs * 3;
@@ -869,6 +877,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       if (lane == 0) r = atomicAdd(b.next_row, 1);                                                                     \
       rL = __shfl_sync(0xffffffffu, r, 0);                                                                             \
       svp = sv + (size_t)rL * wh * 32; gp = g_n + (size_t)rL * wh * C;                                                 \
+      if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row); \
     }                                                                                                                  \
   } while (0)
   {
@@ -876,6 +885,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     float gA[4], gB[4];
     if (ALIGNED) {
       if (rL < wh) {
+        if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row);
         SEG_LOAD4(codeA, gA);
         for (;;) {
           SEG_ADVANCE_LOAD();
