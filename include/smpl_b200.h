@@ -28,10 +28,12 @@
 extern "C" {
 #endif
 
-#define SMPL_B200_ABI_VERSION 1
+#define SMPL_B200_ABI_VERSION 2
 #define SMPL_B200_NUM_PARAMS 86
 #define SMPL_B200_NUM_JOINTS 24
 #define SMPL_B200_VPOSED_LD(num_verts) ((((num_verts) + 255) / 256) * 768) /* row stride (floats) of the saved v_posed: whole 256-vertex chunks */
+
+#define SMPL_B200_VPS_LD(num_sampled_verts) ((((num_sampled_verts) * 3 + 3) / 4) * 4) /* row stride (floats) of the compact sampled v_posed: 16-byte rows */
 
 typedef enum SmplB200Status {
   SMPL_B200_OK = 0,
@@ -82,8 +84,10 @@ int smpl_b200_profile_collect(SmplB200KernelStat* out, int max_stats, int* num_s
 
 /* ---- handles ---------------------------------------------------------------------------------------- */
 /* SMPLLayer.__init__/build (batch_smpl.py:24-94): uploads and repacks the constants on `device`.
- * Environment, read here: SMPL_B200_TF32_FWD=1 builds the handle without the fp16-split blend tables, so the dense-batch
- * forward blend runs as 3xTF32 instead (same tolerance, slower; blend coefficients beyond |x| < 1023 need it). */
+ * Supported parameter range: for batches of 64 and more the blend products run as fp16-split tensor-core products with
+ * the coefficients scaled by 2^6, exact for |beta| <= 1023 (SMPL shape parameters are O(1)); beyond that the coefficient
+ * saturates at +-1023.5 (finite output) where the reference would extrapolate linearly.  On any error the half-built
+ * handle is released and the caller's current device is restored. */
 int smpl_b200_model_create(const SmplB200HostModel* host, int device, SmplB200Model** out);
 void smpl_b200_model_destroy(SmplB200Model* model);
 int smpl_b200_model_num_verts(const SmplB200Model* model);
@@ -100,7 +104,9 @@ typedef enum SmplB200Op {
   SMPL_B200_OP_DECODE_FWD = 0,
   SMPL_B200_OP_DECODE_BWD = 1,
   SMPL_B200_OP_SILHOUETTE_FWD = 2,
-  SMPL_B200_OP_SILHOUETTE_BWD = 3
+  SMPL_B200_OP_SILHOUETTE_BWD = 3,
+  SMPL_B200_OP_FULL_FWD = 4,
+  SMPL_B200_OP_FULL_BWD = 5
 } SmplB200Op;
 /* bytes of device scratch the op needs for batch N (16-byte aligned buffer); vertex_sampling <= 1 = none */
 size_t smpl_b200_workspace_bytes(const SmplB200Model* model, int op, int N, int img_wh, int vertex_sampling);
@@ -110,22 +116,27 @@ size_t smpl_b200_workspace_bytes(const SmplB200Model* model, int op, int N, int 
  *   joints24     (N,24,3)  J_transformed, the side attribute of batch_smpl.py:131
  *   joints_reg   (N,R,3)   the commented-out cocoplus/LSP regression of batch_smpl.py:147-151 (R = num_reg_joints)
  *   v_posed_save (N,LD)    rest-pose vertices after both blend shapes, row stride LD = SMPL_B200_VPOSED_LD(V);
- *                          the tensor decode_bwd needs (saved-for-backward)
+ *                          the tensor decode_bwd needs when a dense vertex gradient may arrive (saved-for-backward).
+ *                          NULL: v_posed lives in the workspace only (add N*LD*4 bytes, rounded up to 256, to it)
+ *   v_posed_sampled (N, SMPL_B200_VPS_LD(Vs))  compact copy of the rest-pose positions of the SAMPLED vertices (needs
+ *                          `projects`): all decode_bwd needs when the gradient arrives through g_projects only -- 16.5
+ *                          KB instead of 82.9 KB per sample at vertex_sampling = 5, and a coalesced read
  *   projects     (N,Vs,3)  fused orthographic_project (projection.py:54-81) with `vertex_sampling` */
 int smpl_b200_decode_fwd(const SmplB200Model* model, const float* params, int N, float* verts, float* joints24,
-                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* projects,
-                         int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream);
+                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* v_posed_sampled,
+                         float* projects, int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above (TF autodiff of batch_smpl.py:96-153 and projection.py:54-81).
  *   g_verts    (N,V,3)  or NULL
  *   g_projects (N,Vs,3) or NULL (gradient w.r.t. the fused projection output, sampled with vertex_sampling)
  *   g_joints24 (N,24,3) or NULL
  *   g_params   (N,86)   written (not accumulated): camera, pose and shape gradients
- * With g_verts == NULL only the sampled vertices carry gradient and the kernels skip the rest. */
+ * With g_verts == NULL only the sampled vertices carry gradient and the kernels skip the rest; then v_posed_sampled
+ * (if given) is read instead of v_posed_save, which may be NULL. */
 int smpl_b200_decode_bwd(const SmplB200Model* model, const float* params, int N, const float* v_posed_save,
-                         const float* g_verts, const float* g_projects, int vertex_sampling,
-                         const float* g_joints24, float* g_params, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         const float* v_posed_sampled, const float* g_verts, const float* g_projects,
+                         int vertex_sampling, const float* g_joints24, float* g_params, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- orthographic_project (projection.py:54-81), stand-alone ---------------------------------------- */
 int smpl_b200_project_fwd(const float* verts, const float* params, int N, int V, int vertex_sampling,
@@ -154,6 +165,20 @@ int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const f
  * vertices are 0).  projects and mask must be the forward's inputs. */
 int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg,
                       const void* saved, int N, int Vs, int img_wh, float* g_projects, void* stream);
+
+/* ---- the whole path in one call (model.py:108-118: SMPLLayer -> orthographic_project -> compute_mask -> projects_to_seg)
+ * params (N,86) -> projects (N,Vs,3), mask (N,Vs), seg (N,wh,wh,P+1) [+ verts (N,V,3), joints24 (N,24,3); NULL to skip].
+ * `state` (nullable; smpl_b200_full_state_bytes, 16-byte aligned) receives what full_bwd needs: the compact sampled
+ * v_posed and the seg arg-min bytes.  NULL = inference: nothing is saved and the rasteriser skips the arg-min tracking.
+ * Workspace: smpl_b200_workspace_bytes(model, SMPL_B200_OP_FULL_FWD / _BWD, N, img_wh, vertex_sampling).
+ * full_bwd: g_seg (N,wh,wh,P+1) -> g_params (N,86), written; projects and mask are full_fwd's outputs. */
+size_t smpl_b200_full_state_bytes(const SmplB200Model* model, int N, int img_wh, int vertex_sampling);
+int smpl_b200_full_fwd(const SmplB200Model* model, const SmplB200Parts* parts, const float* params, int N, int img_wh,
+                       int vertex_sampling, float* verts, float* joints24, float* projects, float* mask, float* seg,
+                       void* state, void* workspace, size_t workspace_bytes, void* stream);
+int smpl_b200_full_bwd(const SmplB200Model* model, const SmplB200Parts* parts, const float* params, int N, int img_wh,
+                       int vertex_sampling, const float* projects, const float* mask, const float* g_seg,
+                       const void* state, float* g_params, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- projects_to_silhouette (projects_to_silhouette.py:14-44) ------------------------------------------ */
 /* projects (N,Vs,3) -> sil (N,wh,wh,2): channel 0 = 1-s, channel 1 = s, rows flipped. */

@@ -9,6 +9,7 @@ from . import smpl_io  # noqa: F401  (numpy only; safe without the CUDA library)
 from ._lib import SmplB200Error, launch_count, load as load_library, profile_collect, profile_enable  # noqa: F401
 from .layers import (  # noqa: F401
     DeviceModel,
+    GraphedDecoderStep,
     PartTable,
     SMPLLayer,
     SmplDecoder,
@@ -26,7 +27,7 @@ from .layers import (  # noqa: F401
 )
 from .sharding import all_gather_outputs, shard_bounds, shard_slice  # noqa: F401
 
-__all__ = ["SMPLLayer", "SmplDecoder", "orthographic_project", "compute_mask", "projects_to_seg",
+__all__ = ["SMPLLayer", "SmplDecoder", "GraphedDecoderStep", "orthographic_project", "compute_mask", "projects_to_seg",
            "projects_to_silhouette", "categorical_focal_loss", "categorical_crossentropy", "concat_mean_param", "set_cam_params", "load_mean_set_cam_params",
            "DeviceModel", "PartTable", "get_device_model", "get_part_table", "smpl_io", "SmplB200Error",
            "launch_count", "load_library", "profile_enable", "profile_collect", "shard_bounds", "shard_slice", "all_gather_outputs"]

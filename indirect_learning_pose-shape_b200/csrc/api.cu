@@ -77,6 +77,12 @@ static cudaError_t upload(T** dptr, const std::vector<T>& h) {
   return e;
 }
 
+static void free_vs_tables(VsTables* t) {
+  cudaFree(t->BmT); cudaFree(t->Bs_hi); cudaFree(t->Bs_lo); cudaFree(t->csc_ptr); cudaFree(t->csc_vert); cudaFree(t->csc_w);
+  cudaFree(t->csc_q); cudaFree(t->lbs_idx_s); cudaFree(t->lbs_w_s);
+  *t = VsTables();
+}
+
 static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
   const int V = m->V;
   const int Vs = (V + vs - 1) / vs;
@@ -130,8 +136,7 @@ static int build_vs_tables(const SmplB200Model* m, int vs, VsTables* t) {
 
 const VsTables* get_vs_tables(const SmplB200Model* m, int vs) {
   if (vs < 1) vs = 1;
-  for (int i = 0; i < kMaxVsCache; ++i)
-    if (m->vst[i].vs == vs) return &m->vst[i];
+  // always under the mutex (uncontended: ~20 ns): an unlocked fast path would race with build_vs_tables' publication
   std::lock_guard<std::mutex> lk(g_vs_mutex);
   SmplB200Model* mm = const_cast<SmplB200Model*>(m);
   for (int i = 0; i < kMaxVsCache; ++i) {
@@ -141,6 +146,7 @@ const VsTables* get_vs_tables(const SmplB200Model* m, int vs) {
       cudaGetDevice(&dev);
       cudaSetDevice(m->device);
       int rc = build_vs_tables(mm, vs, &mm->vst[i]);
+      if (rc != 0) { free_vs_tables(&mm->vst[i]); }            // a half-built slot is released and stays unused
       cudaSetDevice(dev);
       return rc == 0 ? &mm->vst[i] : nullptr;
     }
@@ -213,6 +219,11 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
   CU_TRY(cudaSetDevice(device));
   const int V = h->num_verts;
   SmplB200Model* m = new SmplB200Model();
+  // every error return below releases the half-built model (device buffers included) and restores the caller's device
+  struct Guard {
+    SmplB200Model* m; int prev;
+    ~Guard() { if (m) smpl_b200_model_destroy(m); cudaSetDevice(prev); }
+  } guard{m, prev};
   m->device = device;
   m->V = V;
   m->LD = SMPL_B200_VPOSED_LD(V);
@@ -222,7 +233,7 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
     int p = (j == 0) ? -1 : h->parents[j];
     if (j > 0 && (p < 0 || p >= j)) {
       set_error("model_create: parents[%d]=%d is not a topologically ordered tree", j, p);
-      delete m; cudaSetDevice(prev); return SMPL_B200_ERR_BAD_ARG;
+      return SMPL_B200_ERR_BAD_ARG;
     }
     m->tree.parent[j] = p;
     m->tree.depth[j] = (j == 0) ? 0 : m->tree.depth[p] + 1;
@@ -235,7 +246,7 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
     while (c < 4 && m->tree.child[p][c] >= 0) ++c;
     if (c == 4) {
       set_error("model_create: joint %d has more than 4 children", p);
-      delete m; cudaSetDevice(prev); return SMPL_B200_ERR_UNSUPPORTED;
+      return SMPL_B200_ERR_UNSUPPORTED;
     }
     m->tree.child[p][c] = j;
   }
@@ -265,11 +276,11 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
     CU_TRY(upload(&m->BT_lo, btl));
     // fp16 split of the same matrix for the forward (twice the tensor rate of TF32): B * 2^e = hi + lo with max |B| 2^e in
     // [2^13, 2^14), so hi carries 11 bits and lo the next 11 (its own quantisation, 2^-24 / 2^e absolute, is far below
-    // fp32's); products of two fp16 values are exact in the fp32 accumulator.  SMPL_B200_TF32_FWD=1 keeps the TF32 tables.
+    // fp32's); products of two fp16 values are exact in the fp32 accumulator.  (A degenerate model -- all-zero or
+    // non-finite blend shapes -- has no such scale and keeps the 3xTF32 tables for the forward too.)
     float bmax = 0.f;
     for (size_t i = 0; i < (size_t)kK * C; ++i) bmax = fmaxf(bmax, fabsf(m->h_Bm[i]));
-    const char* env_tf32 = getenv("SMPL_B200_TF32_FWD");
-    if (bmax > 0.f && std::isfinite(bmax) && !(env_tf32 && env_tf32[0] == '1')) {
+    if (bmax > 0.f && std::isfinite(bmax)) {
       int ex = 0;
       frexpf(bmax, &ex);                                   // bmax = f * 2^ex, f in [0.5, 1)
       m->bt16_scale = ldexpf(1.0f, 14 - ex);
@@ -290,7 +301,7 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
     m->num_sms = prop.multiProcessorCount;
     if (prop.major != 10) {
       set_error("model_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
-      delete m; cudaSetDevice(prev); return SMPL_B200_ERR_NO_DEVICE;
+      return SMPL_B200_ERR_NO_DEVICE;
     }
   }
   // folded joint regression: J = Jt + Jd * beta   (exact algebra of batch_smpl.py:106-115, evaluated in fp64)
@@ -351,10 +362,10 @@ int smpl_b200_model_create(const SmplB200HostModel* h, int device, SmplB200Model
   const int eager[3] = {1, 2, 5};
   for (int i = 0; i < 3; ++i) {
     int rc = build_vs_tables(m, eager[i], &m->vst[i]);
-    if (rc != 0) { cudaSetDevice(prev); return rc; }
+    if (rc != 0) return rc;
   }
   CU_TRY(cudaDeviceSynchronize());
-  cudaSetDevice(prev);
+  guard.m = nullptr;                 // success: the caller owns the model now (the guard still restores the device)
   *out = m;
   return SMPL_B200_OK;
 }
@@ -366,10 +377,7 @@ void smpl_b200_model_destroy(SmplB200Model* m) {
   cudaSetDevice(m->device);
   cudaFree(m->vt_pad); cudaFree(m->Bm); cudaFree(m->BT_hi); cudaFree(m->BT_lo); cudaFree(m->BT16_hi); cudaFree(m->BT16_lo); cudaFree(m->Jt); cudaFree(m->Jd); cudaFree(m->lbs_idx); cudaFree(m->lbs_w);
   cudaFree(m->jr_ptr); cudaFree(m->jr_vert); cudaFree(m->jr_w);
-  for (int i = 0; i < kMaxVsCache; ++i) {
-    cudaFree(m->vst[i].BmT); cudaFree(m->vst[i].Bs_hi); cudaFree(m->vst[i].Bs_lo); cudaFree(m->vst[i].csc_ptr); cudaFree(m->vst[i].csc_vert); cudaFree(m->vst[i].csc_w); cudaFree(m->vst[i].csc_q);
-    cudaFree(m->vst[i].lbs_idx_s); cudaFree(m->vst[i].lbs_w_s);
-  }
+  for (int i = 0; i < kMaxVsCache; ++i) free_vs_tables(&m->vst[i]);
   free(m->h_Bm); free(m->h_W);
   cudaSetDevice(prev);
   delete m;
@@ -410,6 +418,10 @@ int smpl_b200_parts_create(int device, int num_parts, const int32_t* part_ptr, c
   cudaGetDevice(&prev);
   CU_TRY(cudaSetDevice(device));
   SmplB200Parts* p = new SmplB200Parts();
+  struct Guard {
+    SmplB200Parts* p; int prev;
+    ~Guard() { if (p) smpl_b200_parts_destroy(p); cudaSetDevice(prev); }
+  } guard{p, prev};
   p->device = device; p->P = num_parts; p->E = E; p->Vs = num_sampled_verts; p->max_part = max_part;
   CU_TRY(upload(&p->ptr, ptr));
   CU_TRY(upload(&p->idx, idx));
@@ -419,7 +431,7 @@ int smpl_b200_parts_create(int device, int num_parts, const int32_t* part_ptr, c
   p->ovf = ob[num_parts];
   CU_TRY(upload(&p->obase, ob));
   CU_TRY(cudaDeviceSynchronize());
-  cudaSetDevice(prev);
+  guard.p = nullptr;
   *out = p;
   return SMPL_B200_OK;
 }
@@ -474,6 +486,10 @@ size_t smpl_b200_workspace_bytes(const SmplB200Model* m, int op, int N, int img_
     case SMPL_B200_OP_DECODE_BWD: return decode_ws(m, N, true, vs == 1, vs, nullptr).bytes;
     case SMPL_B200_OP_SILHOUETTE_FWD:
     case SMPL_B200_OP_SILHOUETTE_BWD: return 256;
+    case SMPL_B200_OP_FULL_FWD:      // decode scratch + the transient v_posed
+      return decode_ws(m, N, false, false, 1, nullptr).bytes + ru((size_t)N * m->LD * sizeof(float), 256);
+    case SMPL_B200_OP_FULL_BWD:      // decode scratch (sampled gradient) + g_projects
+      return decode_ws(m, N, true, false, vs, nullptr).bytes + ru((size_t)N * ((m->V + vs - 1) / vs) * 3 * sizeof(float), 256);
     default: return 0;
   }
 }
@@ -488,8 +504,8 @@ size_t smpl_b200_workspace_bytes(const SmplB200Model* m, int op, int N, int img_
   } while (0)
 
 int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, float* verts, float* joints24,
-                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* projects,
-                         int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream) {
+                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* v_posed_sampled,
+                         float* projects, int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!m || !params || N < 0 || (!verts && !projects)) { set_error("decode_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
@@ -501,6 +517,7 @@ int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, flo
     return SMPL_B200_ERR_BAD_ARG;
   }
   if (joints_reg && !verts) { set_error("decode_fwd: joints_reg needs verts"); return SMPL_B200_ERR_BAD_ARG; }
+  if (v_posed_sampled && !projects) { set_error("decode_fwd: v_posed_sampled needs projects"); return SMPL_B200_ERR_BAD_ARG; }
   // v_posed must live somewhere: the caller's save buffer, else the tail of the workspace
   DecodeWs w = decode_ws(m, N, false, false, 1, workspace);
   size_t need = w.bytes + (v_posed_save ? 0 : ru((size_t)N * m->LD * sizeof(float), 256));
@@ -513,19 +530,25 @@ int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, flo
   CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, dense ? w.Xlo : nullptr, w.A, joints24 ? joints24 : w.Jtr, st));
   if (dense) CHECK_LAUNCH(launch_blend_fwd_tc(m, w.X, w.Xlo, N, vp, st));
   else CHECK_LAUNCH(launch_blend_fwd(m, w.X, N, vp, st));
-  CHECK_LAUNCH(launch_lbs_fwd(m, vp, w.A, params, N, verts, projects, vs, st));
+  const int Vs = (m->V + vs - 1) / vs;
+  CHECK_LAUNCH(launch_lbs_fwd(m, vp, w.A, params, N, verts, projects, vs, v_posed_sampled, SMPL_B200_VPS_LD(Vs), st));
   if (joints_reg) CHECK_LAUNCH(launch_joints_reg_fwd(m, verts, N, num_reg_joints_used, joints_reg, st));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, const float* v_posed_save,
-                         const float* g_verts, const float* g_projects, int vertex_sampling,
-                         const float* g_joints24, float* g_params, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+                         const float* v_posed_sampled, const float* g_verts, const float* g_projects,
+                         int vertex_sampling, const float* g_joints24, float* g_params, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
-  if (!m || !params || !v_posed_save || !g_params || N < 0) { set_error("decode_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  if (!m || !params || !g_params || N < 0) { set_error("decode_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   const int vs_in = vertex_sampling < 1 ? 1 : vertex_sampling;
   const bool full = (g_verts != nullptr) || !g_projects;     // dense vertex gradient (or none at all): every vertex
+  if (!v_posed_save && (full || !v_posed_sampled)) {
+    set_error("decode_bwd: v_posed_save is required unless the gradient arrives through g_projects only and "
+              "v_posed_sampled is given");
+    return SMPL_B200_ERR_BAD_ARG;
+  }
   const int vs_t = full ? 1 : vs_in;
   const VsTables* t = get_vs_tables(m, vs_t);
   if (!t) return SMPL_B200_ERR_CUDA;
@@ -539,7 +562,8 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, nullptr, w.A, w.Jtr, st));   // recompute A (cheap) instead of saving it
   int cam_chunks = w.cam_chunks;
   CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp,
-                              dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, &cam_chunks, st));
+                              dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, &cam_chunks,
+                              full ? nullptr : v_posed_sampled, SMPL_B200_VPS_LD(t->Vs), st));
   if (dense) CHECK_LAUNCH(launch_blend_bwd_tc(m, t, w.gvp, w.gvplo, w.gvp_ld, N, w.gX, st));
   else CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
   CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, cam_chunks, N, g_params, st));
@@ -620,6 +644,79 @@ int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const f
   }
   CHECK_LAUNCH(e);
   return SMPL_B200_OK;
+}
+
+// ---- the whole path in one call (model.py:108-118) ---------------------------------------------------------------
+static size_t full_vps_bytes(const SmplB200Model* m, int N, int vs) {
+  const int Vs = (m->V + vs - 1) / vs;
+  return ru((size_t)N * SMPL_B200_VPS_LD(Vs) * sizeof(float), 256);
+}
+
+size_t smpl_b200_full_state_bytes(const SmplB200Model* m, int N, int img_wh, int vertex_sampling) {
+  if (!m || N < 0 || img_wh < 0) return 0;
+  const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
+  return full_vps_bytes(m, N, vs) + seg_saved_bytes(N, img_wh);
+}
+
+int smpl_b200_full_fwd(const SmplB200Model* m, const SmplB200Parts* parts, const float* params, int N, int img_wh,
+                       int vertex_sampling, float* verts, float* joints24, float* projects, float* mask, float* seg,
+                       void* state, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return SMPL_B200_OK;
+  if (!m || !parts || !params || !projects || !mask || !seg || N < 0) { set_error("full_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
+  const int Vs = (m->V + vs - 1) / vs;
+  int rc = seg_check(parts, projects, mask, N, Vs, img_wh, "full_fwd");
+  if (rc) return rc;
+  if (!aligned(seg, 16) || (state && !aligned(state, 16)) || !aligned(workspace, 16) || (verts && !aligned(verts, 8))) {
+    set_error("full_fwd: misaligned buffer (seg/state/workspace 16B, verts 8B)"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  const size_t need = smpl_b200_workspace_bytes(m, SMPL_B200_OP_FULL_FWD, N, img_wh, vs);
+  if (!workspace || workspace_bytes < need) {
+    set_error("full_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return SMPL_B200_ERR_WORKSPACE;
+  }
+  float* vps = state ? (float*)state : nullptr;
+  unsigned char* saved = state ? (unsigned char*)state + full_vps_bytes(m, N, vs) : nullptr;
+  rc = smpl_b200_decode_fwd(m, params, N, verts, joints24, nullptr, 0, nullptr, vps, projects, vs, workspace,
+                            workspace_bytes, stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CHECK_LAUNCH(launch_mask_fwd(projects, N, Vs, mask, st));
+  cudaError_t e = launch_seg_fwd(parts, projects, mask, N, Vs, img_wh, seg, saved, st);
+  if (e == cudaErrorInvalidConfiguration) {
+    set_error("full_fwd: part table (%d entries) and img_wh=%d need more than 227 KB of shared memory", parts->E, img_wh);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  CHECK_LAUNCH(e);
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_full_bwd(const SmplB200Model* m, const SmplB200Parts* parts, const float* params, int N, int img_wh,
+                       int vertex_sampling, const float* projects, const float* mask, const float* g_seg,
+                       const void* state, float* g_params, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return SMPL_B200_OK;
+  if (!m || !parts || !params || !projects || !mask || !g_seg || !state || !g_params || N < 0) {
+    set_error("full_bwd: null/invalid argument (full_fwd must have been given a `state` buffer)"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
+  const int Vs = (m->V + vs - 1) / vs;
+  int rc = seg_check(parts, projects, mask, N, Vs, img_wh, "full_bwd");
+  if (rc) return rc;
+  const size_t need = smpl_b200_workspace_bytes(m, SMPL_B200_OP_FULL_BWD, N, img_wh, vs);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 16)) {
+    set_error("full_bwd: workspace too small or misaligned (%zu < %zu bytes)", workspace_bytes, need); return SMPL_B200_ERR_WORKSPACE;
+  }
+  const size_t dbytes = decode_ws(m, N, true, false, vs, nullptr).bytes;
+  float* g_proj = (float*)((char*)workspace + dbytes);
+  const float* vps = (const float*)state;
+  const unsigned char* saved = (const unsigned char*)state + full_vps_bytes(m, N, vs);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = launch_seg_bwd(parts, projects, mask, g_seg, saved, N, Vs, img_wh, g_proj, st);
+  if (e == cudaErrorInvalidConfiguration) {
+    set_error("full_bwd: part table (%d entries), Vs=%d and img_wh=%d need more than 227 KB of shared memory", parts->E, Vs, img_wh);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  CHECK_LAUNCH(e);
+  return smpl_b200_decode_bwd(m, params, N, nullptr, vps, nullptr, g_proj, vs, nullptr, g_params, workspace, dbytes, stream);
 }
 
 int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,

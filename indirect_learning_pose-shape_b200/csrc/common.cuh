@@ -128,8 +128,9 @@ __host__ __device__ __forceinline__ float tf32_hi(float x) {
 #endif
 }
 cudaError_t launch_blend_fwd(const SmplB200Model* m, const float* X, int N, float* v_posed, cudaStream_t st);
+// vps (nullable): compact copy [N][vps_ld] of the rest-pose positions of the sampled vertices (the sampled backward's input)
 cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
-                           float* verts, float* projects, int vs, cudaStream_t st);
+                           float* verts, float* projects, int vs, float* vps, int vps_ld, cudaStream_t st);
 cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, int N, int R_used, float* joints,
                                   cudaStream_t st);
 // t = tables of the PROCESSING stride (1 = every vertex, g_vp rows [LD]; >1 = sampled vertices only, g_vp rows
@@ -138,7 +139,9 @@ cudaError_t launch_joints_reg_fwd(const SmplB200Model* m, const float* verts, in
 cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
                            const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
                            float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, int* cam_chunks,
+                           const float* vps, int vps_ld,
                            cudaStream_t st);   // cam_chunks: how many [N][4] partial-sum planes of g_cam were written
+                                               // vps (nullable): launch_lbs_fwd's compact copy; v_posed may then be null
 cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
                              float* g_X, cudaStream_t st);
 // g_cam = [cam_chunks][N][4] partial camera-gradient sums from launch_lbs_bwd (or null)

@@ -74,74 +74,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int kLbsStages = 4;   // v_posed slices in flight per block (cp.async ring)
 
-template <int KW>
-__global__ void __launch_bounds__(kChunk)
-lbs_fwd_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A, const float* __restrict__ params,
-               int N, int V, const uint8_t* __restrict__ lbs_idx, const float* __restrict__ lbs_w,
-               float* __restrict__ verts, float* __restrict__ projects, int vs, int Vs) {
-  __shared__ __align__(16) float As[kGroup * kARow];
-  __shared__ float cam[kGroup * 4];
-  __shared__ __align__(16) float stage[kLbsStages][kChunk * 3];
-  const int tid = threadIdx.x;
-  const int n0 = blockIdx.y * kGroup;
-  const int rows = min(kGroup, N - n0);
-  const int v = blockIdx.x * kChunk + tid;
-  const bool valid = v < V;
-  const int col0 = blockIdx.x * kChunk * 3;
-  // the group's v_posed slices stream through a cp.async ring: kLbsStages x 3 KB in flight per block, no register staging
-  auto issue = [&](int s) {
-    if (s < rows && tid < kChunk * 3 / 4) cp_async16(&stage[s % kLbsStages][tid * 4], vp + (size_t)(n0 + s) * LD + col0 + tid * 4);
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int s = 0; s < kLbsStages - 1; ++s) issue(s);
-  load_group_A(As, cam, A, params, n0, rows);
-  const Skin<KW> skin = load_skin<KW>(lbs_idx, lbs_w, valid ? v : 0);
-  const bool sampled = valid && projects && (v % vs == 0);
-  const bool need = valid && (verts || sampled);
-  const int q = v / vs;
-  for (int s = 0; s < rows; ++s) {
-    const int n = n0 + s;
-    issue(s + kLbsStages - 1);                     // keeps kLbsStages-1 slices in flight behind the one consumed now
-    cp_async_wait<kLbsStages - 1>();               // slice s has landed (for this thread's copies) ...
-    __syncthreads();                               // ... and for everyone's; also publishes As/cam on the first pass
-    float* st = stage[s % kLbsStages];
-    if (need) {
-      const float x = st[tid * 3], y = st[tid * 3 + 1], z = st[tid * 3 + 2];
-      float T[12];
-      blend_T<KW>(skin, As + s * kARow, T);
-      const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
-      const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
-      const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
-      st[tid * 3] = ox; st[tid * 3 + 1] = oy; st[tid * 3 + 2] = oz;
-      if (sampled) {                               // projection.py:77-79: multiply, then add (two roundings)
-        float* p = projects + ((size_t)n * Vs + q) * 3;
-        p[0] = __fadd_rn(cam[s * 4 + 2], __fmul_rn(ox, cam[s * 4 + 0]));
-        p[1] = __fadd_rn(cam[s * 4 + 3], __fmul_rn(oy, cam[s * 4 + 1]));
-        p[2] = oz;
-      }
-    }
-    __syncthreads();
-    if (verts) {
-      float2* dst = reinterpret_cast<float2*>(verts + (size_t)n * V * 3 + col0);
-      const int lim = (V * 3 - col0) / 2;          // V*3 and col0 are even
-      for (int i = tid; i < kChunk * 3 / 2; i += kChunk)
-        if (i < lim) dst[i] = reinterpret_cast<const float2*>(st)[i];
-    }
-    __syncthreads();                               // the next iteration's issue() overwrites the slot consumed before this one
-  }
-}
-
-// Warp-independent variant of the forward (the one launched): each warp owns 32 vertices (96 floats = 384 B per sample)
-// and runs its own cp.async ring, so the only block-wide barrier is the one that publishes the group's bone transforms.
-// (The block-synchronous kernel above spent 2.4 of ~11 warp-issue-slots at barriers: three per sample and 3 KB moved
-// between them.)
+// Forward: each warp owns 32 vertices (96 floats = 384 B per sample) and runs its own cp.async ring, so the only
+// block-wide barrier is the one that publishes the group's bone transforms.  (A block-synchronous predecessor spent 2.4
+// of ~11 warp-issue-slots at barriers: three per sample and 3 KB moved between them.)
 constexpr int kWG = 16;          // samples per block
 template <int KW>
 __global__ void __launch_bounds__(kChunk)
 lbs_fwd_warp_kernel(const float* __restrict__ vp, int LD, const float* __restrict__ A, const float* __restrict__ params,
                     int N, int V, const uint8_t* __restrict__ lbs_idx, const float* __restrict__ lbs_w,
-                    float* __restrict__ verts, float* __restrict__ projects, int vs, int Vs) {
+                    float* __restrict__ verts, float* __restrict__ projects, int vs, int Vs,
+                    float* __restrict__ vps, int vps_ld) {
   __shared__ __align__(16) float As[kWG * kARow];
   __shared__ float cam[kWG * 4];
   __shared__ __align__(16) float ring[kChunk / 32][kLbsStages][96];
@@ -188,6 +130,10 @@ lbs_fwd_warp_kernel(const float* __restrict__ vp, int LD, const float* __restric
         p[0] = __fadd_rn(cam[s * 4 + 2], __fmul_rn(ox, cam[s * 4 + 0]));
         p[1] = __fadd_rn(cam[s * 4 + 3], __fmul_rn(oy, cam[s * 4 + 1]));
         p[2] = oz;
+        if (vps) {                                                 // compact rest-pose copy: all the sampled backward reads
+          float* o = vps + (size_t)n * vps_ld + (size_t)q * 3;
+          o[0] = x; o[1] = y; o[2] = z;
+        }
       }
     }
     if (verts) {
@@ -338,7 +284,7 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
                        const float* __restrict__ sw, const int* __restrict__ csc_ptr, const int* __restrict__ csc_q,
                        const float* __restrict__ csc_w, const float* __restrict__ g_projects,
                        float* __restrict__ g_vp, float* __restrict__ g_vp_lo, int gvp_ld, int Kp,
-                       float* __restrict__ g_A, float* __restrict__ g_cam) {
+                       float* __restrict__ g_A, float* __restrict__ g_cam, const float* __restrict__ vps, int vps_ld) {
   extern __shared__ __align__(16) float sm[];
   float* As = sm;                         // [24][12]
   float* sg = As + kARow;                 // [Vs][3] gradient at the sampled vertices   (STAGE only; otherwise phase 2
@@ -347,22 +293,24 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // The sampled vertices sit 12 bytes in every 12 * vs of the v_posed row: the gather below touches every 64-byte DRAM
   // burst of the row anyway, so request the row (and the gradient row) into L2 as two streaming transfers first
-  // (0.52 -> 0.50 ms).
-  if (tid == 0) prefetch_l2_inner(vp + (size_t)n * LD, (size_t)min(LD, Vs * vs * 3) * 4);
+  // (0.52 -> 0.50 ms).  With the forward's compact copy `vps` (rows of Vs*3 floats) the gather is a plain coalesced read of
+  // 12*Vs bytes instead: ncu showed 2.46x the algorithmic DRAM bytes for the strided gather.
+  const int step3 = vps ? 3 : vs * 3;                               // floats between consecutive sampled vertices
+  const float* vrow = vps ? vps + (size_t)n * vps_ld : vp + (size_t)n * LD;
+  if (tid == 0) prefetch_l2_inner(vrow, vps ? (size_t)Vs * 12 : (size_t)min(LD, Vs * vs * 3) * 4);
   else if (tid == 32) prefetch_l2_inner(g_projects + (size_t)n * Vs * 3, (size_t)Vs * 12);
   for (int i = tid; i < kARow / 4; i += blockDim.x)
     reinterpret_cast<float4*>(As)[i] = reinterpret_cast<const float4*>(A + (size_t)n * kARow)[i];
   const float ku = params[(size_t)n * kParams], kv = params[(size_t)n * kParams + 1];
   __syncthreads();
   const float* gp = g_projects + (size_t)n * Vs * 3;
-  const float* vrow = vp + (size_t)n * LD;
   float* orow = g_vp + (size_t)n * gvp_ld;
   float* lrow = g_vp_lo ? g_vp_lo + (size_t)n * gvp_ld : nullptr;
   float c4[4] = {0.f, 0.f, 0.f, 0.f};
   for (int q = tid; q < Vs; q += blockDim.x) {
     const Skin<KW> skin = load_skin<KW>(sidx, sw, q);
     const float gu = gp[q * 3], gv = gp[q * 3 + 1], gz = gp[q * 3 + 2];
-    const float x = vrow[(size_t)q * vs * 3], y = vrow[(size_t)q * vs * 3 + 1], z = vrow[(size_t)q * vs * 3 + 2];
+    const float x = vrow[(size_t)q * step3], y = vrow[(size_t)q * step3 + 1], z = vrow[(size_t)q * step3 + 2];
     const float gx = gu * ku, gy = gv * kv;                       // u = u0 + x k_u, v = v0 + y k_v (projection.py:77-78)
     float T[12];
     blend_T<KW>(skin, As, T);
@@ -413,7 +361,7 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
         x = sp[q * 3]; y = sp[q * 3 + 1]; z = sp[q * 3 + 2];
       } else {
         gx = gp[q * 3] * ku * w; gy = gp[q * 3 + 1] * kv * w; gz = gp[q * 3 + 2] * w;
-        x = vrow[(size_t)q * vs * 3]; y = vrow[(size_t)q * vs * 3 + 1]; z = vrow[(size_t)q * vs * 3 + 2];
+        x = vrow[(size_t)q * step3]; y = vrow[(size_t)q * step3 + 1]; z = vrow[(size_t)q * step3 + 2];
       }
       acc[0] = fmaf(gx, x, acc[0]); acc[1] = fmaf(gx, y, acc[1]); acc[2] = fmaf(gx, z, acc[2]); acc[3] += gx;
       acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
@@ -505,13 +453,13 @@ joints_reg_kernel(const float* __restrict__ verts, int N, int V, int R_used, con
 int lbs_bwd_cam_chunks(int Vp) { return ((Vp + kChunk - 1) / kChunk) * (kChunk / 32); }   // one plane per warp of the vertex kernel
 
 cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const float* A, const float* params, int N,
-                           float* verts, float* projects, int vs, cudaStream_t st) {
+                           float* verts, float* projects, int vs, float* vps, int vps_ld, cudaStream_t st) {
   const int V = m->V, Vs = (V + vs - 1) / vs;
   dim3 grid((V + kChunk - 1) / kChunk, (N + kWG - 1) / kWG);
   LaunchScope scope(KID_LBS_FWD, st);
 #define SMPL_LBS_FWD(KW)                                                                                          \
   lbs_fwd_warp_kernel<KW><<<grid, kChunk, 0, st>>>(v_posed, m->LD, A, params, N, V, m->lbs_idx, m->lbs_w, verts,    \
-                                                   projects, vs, Vs)
+                                                   projects, vs, Vs, projects ? vps : nullptr, vps_ld)
   if (m->KW == 4) SMPL_LBS_FWD(4);
   else if (m->KW == 8) SMPL_LBS_FWD(8);
   else SMPL_LBS_FWD(24);
@@ -522,7 +470,7 @@ cudaError_t launch_lbs_fwd(const SmplB200Model* m, const float* v_posed, const f
 cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_proj, const float* v_posed,
                            const float* A, const float* params, const float* g_verts, const float* g_projects, int N,
                            float* g_vp, float* g_vp_lo, size_t gvp_ld, float* g_A, float* g_cam, int* cam_chunks,
-                           cudaStream_t st) {
+                           const float* vps, int vps_ld, cudaStream_t st) {
   const int V = m->V, Vp = t->Vs, Vs_proj = (V + vs_proj - 1) / vs_proj;
   if (!g_verts && g_projects && t->vs == vs_proj) {
     // gradient arrives through the projection only: one fused kernel, one block per sample
@@ -536,7 +484,7 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
     if (e != cudaSuccess) return e;                                                                                \
     lbs_bwd_sampled_kernel<KW, ST><<<N, 256, smem, st>>>(v_posed, m->LD, A, params, N, t->vs, Vp, t->lbs_idx_s,      \
                                                          t->lbs_w_s, t->csc_ptr, t->csc_q, t->csc_w, g_projects, g_vp, \
-                                                         g_vp_lo, (int)gvp_ld, t->Kp, g_A, g_cam);                  \
+                                                         g_vp_lo, (int)gvp_ld, t->Kp, g_A, g_cam, vps, vps_ld);     \
   } while (0)
     if (m->KW == 4) { if (stage) SMPL_LBS_BWD_S(4, true); else SMPL_LBS_BWD_S(4, false); }
     else if (m->KW == 8) { if (stage) SMPL_LBS_BWD_S(8, true); else SMPL_LBS_BWD_S(8, false); }

@@ -161,7 +161,9 @@ pose_fwd_kernel(const float* __restrict__ params, int N, const float* __restrict
   __half* x16l = reinterpret_cast<__half*>(Xlo) + (size_t)n * kKPad;
   auto put = [&](int i, float v) {              // tensor-core path: exact split x = hi + lo (TF32, or fp16 of 64 x)
     if (x16) {
-      const float sv = v * kXScale16;
+      // |64 x| beyond fp16's range (|beta| > 1023: a diverged regressor) saturates to a finite value instead of
+      // overflowing to inf / NaN vertices; the supported range is documented in smpl_b200.h
+      const float sv = fminf(fmaxf(v * kXScale16, -65504.0f), 65504.0f);
       const __half h = __float2half_rn(sv);
       x16h[i] = h; x16l[i] = __float2half_rn(sv - __half2float(h));
     } else if (xl) { const float h = tf32_hi(v); x[i] = h; xl[i] = v - h; }

@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(192, 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
                const int* __restrict__ idx, const int* __restrict__ obase, int P, int OV, int wh,
-               float* __restrict__ g_projects) {
+               float* __restrict__ g_projects, int pf_ok) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -750,7 +750,9 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int npx = wh * wh;
   const int nb = (npx + 3) >> 2;
   const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
-  constexpr bool kPrefetch = C32 && ALIGNED;                       // 16-byte aligned rows
+  // cp.async.bulk.prefetch needs 16-byte aligned addresses: the rows are multiples of 16 bytes here, and the launcher
+  // clears pf_ok when the caller's g_seg / saved base pointers are not (a contiguous autograd view with an odd offset)
+  const bool kPrefetch = C32 && ALIGNED && pf_ok;
   const unsigned char* pf_base = (lane == 0) ? reinterpret_cast<const unsigned char*>(g_seg + (size_t)n * npx * 32)
                                              : saved + (size_t)n * npx * 32;
   const uint32_t pf_row = (uint32_t)wh * ((lane == 0) ? 128u : 32u);   // bytes per output row
@@ -994,9 +996,10 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
     cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
     seg_bwd_kernel<C32, AL><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->obase, \
-                                                          p->P, p->ovf, wh, g_projects);                               \
+                                                          p->P, p->ovf, wh, g_projects, pf_ok);                        \
   } while (0)
   const bool c32 = p->P == 31, al = wh % 4 == 0 && wh >= 8;
+  const int pf_ok = (reinterpret_cast<uintptr_t>(g_seg) % 16 == 0 && reinterpret_cast<uintptr_t>(saved) % 16 == 0) ? 1 : 0;
   if (c32 && al) SMPL_SEG_BWD(true, true);
   else if (c32) SMPL_SEG_BWD(true, false);
   else if (al) SMPL_SEG_BWD(false, true);

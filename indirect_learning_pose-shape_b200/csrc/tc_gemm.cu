@@ -14,7 +14,7 @@
 //             blend coefficients are scaled by 2^6 and the blend matrix by the power of two that puts max |B| in
 //             [2^13, 2^14) before hi = fp16(x), lo = fp16(x - hi): 11 + 11 bits, fp16 subnormals bound lo's own error at
 //             1e-9 absolute, fp16 x fp16 products are exact in the fp32 accumulator, and the scales come off exactly in
-//             the epilogue.  SMPL_B200_TF32_FWD=1 at model creation keeps the forward on 3xTF32 (api.cu).
+//             the epilogue.  A degenerate model (no finite non-zero blend shape) keeps the forward on 3xTF32 (api.cu).
 // The tensor core's own fp32 accumulation is not round-to-nearest, and its error grows with the length of the
 // accumulation chain (measured here: 1.1e-6 on vertices at K=224, 1e-4 relative on gradients at K=4160 when the whole
 // K loop accumulates in TMEM).  So TMEM only ever accumulates ONE K block (128 bytes of K: 12 MMAs); the epilogue warps
@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <mutex>
 #include "common.cuh"
 
 namespace smplb200 {
@@ -480,7 +481,28 @@ cudaError_t load_encode() {
 
 // 2-D tensor [rows][cols] of fp32 (or fp16) with row pitch ld (elements); box = 128 bytes of columns x box_rows,
 // SWIZZLE_128B, zero OOB fill (a K that is not a multiple of the box reads zeros past its end).
+// The encoding is a pure function of its arguments, and a training loop presents the same few (pointer, shape) tuples
+// step after step (torch's caching allocator hands the same blocks back): a small ring of recent encodings replaces
+// the eight driver calls per step with eight 40-byte compares.
+struct MapKey {
+  const void* base; int rows, cols, ld, box_rows, f16;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && f16 == o.f16;
+  }
+};
+constexpr int kMapCache = 32;
+std::mutex g_map_mutex;
+MapKey g_map_keys[kMapCache];
+CUtensorMap g_map_vals[kMapCache];
+int g_map_used = 0, g_map_next = 0;
+
 cudaError_t make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, bool f16) {
+  const MapKey key{base, rows, cols, ld, box_rows, f16 ? 1 : 0};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    for (int i = 0; i < g_map_used; ++i)
+      if (g_map_keys[i] == key) { *map = g_map_vals[i]; return cudaSuccess; }
+  }
   const size_t es = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * es};
@@ -489,7 +511,13 @@ cudaError_t make_map(CUtensorMap* map, const void* base, int rows, int cols, int
   CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  g_map_keys[g_map_next] = key;
+  g_map_vals[g_map_next] = *map;
+  g_map_next = (g_map_next + 1) % kMapCache;
+  g_map_used = g_map_used < kMapCache ? g_map_used + 1 : kMapCache;
+  return cudaSuccess;
 }
 
 template <int BN, bool BIAS, bool F16>

@@ -31,7 +31,7 @@ NUM_PARTS = 31
 SMPL_PARENTS = np.array([-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21], np.int32)
 
 # The reference's own data files (part tables, mean-parameter h5 bytes, template geometry of the PLY), extracted by
-# tools/make_golden_fixtures.py; used when the CWD-relative files the reference opens are not present.
+# tools/extract_reference_data.py; used when the CWD-relative files the reference opens are not present.
 _GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ref_fixtures.npz")
 
 
@@ -240,7 +240,6 @@ def make_synthetic_smpl(seed: int = 0, v_template: Optional[np.ndarray] = None, 
     if v_template is None:
         v_template = golden_fixtures()["v_template"].astype(np.float64).copy()
         v_template[:, 1] -= 0.18           # PLY origin -> SMPL-like origin (pelvis near y=-0.22)
-        v_template[:, 1] += 0.0
     v_template = np.asarray(v_template, np.float64)
     V = v_template.shape[0]
     joints = _APPROX_JOINTS.copy()

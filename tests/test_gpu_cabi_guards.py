@@ -51,9 +51,11 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     params.view(torch.float32, (n, 86)).copy_(torch.from_numpy(p_np))
     verts, joints = Guarded(n * V * 12, dev), Guarded(n * 24 * 12, dev)
     vposed, proj = Guarded(n * LD * 4, dev), Guarded(n * Vs * 12, dev)
+    vps_ld = (Vs * 3 + 3) // 4 * 4                       # SMPL_B200_VPS_LD
+    vps = Guarded(n * vps_ld * 4, dev)
     ws_f = Guarded(dm.workspace_bytes(binding.OP_DECODE_FWD, n), dev)
-    binding.check(lib.smpl_b200_decode_fwd(dm.handle, params.ptr, n, verts.ptr, joints.ptr, None, 0, vposed.ptr, proj.ptr, vs,
-                                           ws_f.ptr, ws_f.n, stream), "decode_fwd")
+    binding.check(lib.smpl_b200_decode_fwd(dm.handle, params.ptr, n, verts.ptr, joints.ptr, None, 0, vposed.ptr, vps.ptr,
+                                           proj.ptr, vs, ws_f.ptr, ws_f.n, stream), "decode_fwd")
     mask = Guarded(n * Vs * 4, dev)
     binding.check(lib.smpl_b200_mask_fwd(proj.ptr, n, Vs, mask.ptr, stream), "mask_fwd")
     seg = Guarded(n * wh * wh * 32 * 4, dev)
@@ -70,15 +72,35 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     binding.check(lib.smpl_b200_silhouette_bwd(proj.ptr, g_sil.ptr, n, Vs, wh, g_proj2.ptr, None, 0, stream), "sil_bwd")
     g_params = Guarded(n * 86 * 4, dev)
     ws_b = Guarded(dm.workspace_bytes(binding.OP_DECODE_BWD, n, 0, vs), dev)
-    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, None, g_proj.ptr, vs, None, g_params.ptr,
-                                           ws_b.ptr, ws_b.n, stream), "decode_bwd")
+    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, None, None, g_proj.ptr, vs, None,
+                                           g_params.ptr, ws_b.ptr, ws_b.n, stream), "decode_bwd")
+    # the same backward from the compact sampled copy alone (no full v_posed): same arithmetic, same bits
+    g_params_c = Guarded(n * 86 * 4, dev)
+    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, None, vps.ptr, None, g_proj.ptr, vs, None,
+                                           g_params_c.ptr, ws_b.ptr, ws_b.n, stream), "decode_bwd compact")
+    assert lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, None, None, None, g_proj.ptr, vs, None, g_params_c.ptr,
+                                    ws_b.ptr, ws_b.n, stream) == -1          # neither copy: SMPL_B200_ERR_BAD_ARG
     # dense-gradient variant (g_verts given) needs the full-size workspace
     g_verts = Guarded(n * V * 12, dev)
     g_verts.view(torch.float32, (n, V, 3)).normal_()
     g_params2 = Guarded(n * 86 * 4, dev)
     ws_b2 = Guarded(dm.workspace_bytes(binding.OP_DECODE_BWD, n, 0, 1), dev)
-    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, g_verts.ptr, g_proj.ptr, vs, None,
+    binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, vps.ptr, g_verts.ptr, g_proj.ptr, vs, None,
                                            g_params2.ptr, ws_b2.ptr, ws_b2.n, stream), "decode_bwd dense")
+    # the whole path in one call each way (smpl_b200_full_fwd / _bwd): same kernels, so the same bits as the chain above
+    f_verts, f_joints, f_proj = Guarded(n * V * 12, dev), Guarded(n * 24 * 12, dev), Guarded(n * Vs * 12, dev)
+    f_mask, f_seg, f_gp = Guarded(n * Vs * 4, dev), Guarded(n * wh * wh * 32 * 4, dev), Guarded(n * 86 * 4, dev)
+    f_state = Guarded(lib.smpl_b200_full_state_bytes(dm.handle, n, wh, vs), dev)
+    ws_ff = Guarded(dm.workspace_bytes(binding.OP_FULL_FWD, n, wh, vs), dev)
+    ws_fb = Guarded(dm.workspace_bytes(binding.OP_FULL_BWD, n, wh, vs), dev)
+    binding.check(lib.smpl_b200_full_fwd(dm.handle, table.handle, params.ptr, n, wh, vs, f_verts.ptr, f_joints.ptr,
+                                         f_proj.ptr, f_mask.ptr, f_seg.ptr, f_state.ptr, ws_ff.ptr, ws_ff.n, stream), "full_fwd")
+    binding.check(lib.smpl_b200_full_bwd(dm.handle, table.handle, params.ptr, n, wh, vs, f_proj.ptr, f_mask.ptr, g_seg.ptr,
+                                         f_state.ptr, f_gp.ptr, ws_fb.ptr, ws_fb.n, stream), "full_bwd")
+    # inference form: no state, verts / joints skipped
+    f_seg2, f_proj2, f_mask2 = Guarded(n * wh * wh * 32 * 4, dev), Guarded(n * Vs * 12, dev), Guarded(n * Vs * 4, dev)
+    binding.check(lib.smpl_b200_full_fwd(dm.handle, table.handle, params.ptr, n, wh, vs, None, None, f_proj2.ptr,
+                                         f_mask2.ptr, f_seg2.ptr, None, ws_ff.ptr, ws_ff.n, stream), "full_fwd inference")
     # stand-alone projection
     proj_s, g_verts_s, g_params_s = Guarded(n * Vs * 12, dev), Guarded(n * V * 12, dev), Guarded(n * 86 * 4, dev)
     binding.check(lib.smpl_b200_project_fwd(verts.ptr, params.ptr, n, V, vs, proj_s.ptr, stream), "project_fwd")
@@ -88,7 +110,9 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     for name, g in dict(params=params, verts=verts, joints=joints, vposed=vposed, proj=proj, ws_f=ws_f, mask=mask, seg=seg,
                         saved=saved, g_seg=g_seg, g_proj=g_proj, sil=sil, g_sil=g_sil, g_proj2=g_proj2, g_params=g_params,
                         ws_b=ws_b, g_verts=g_verts, g_params2=g_params2, ws_b2=ws_b2, proj_s=proj_s, g_verts_s=g_verts_s,
-                        g_params_s=g_params_s).items():
+                        g_params_s=g_params_s, vps=vps, g_params_c=g_params_c, f_verts=f_verts, f_joints=f_joints,
+                        f_proj=f_proj, f_mask=f_mask, f_seg=f_seg, f_gp=f_gp, f_state=f_state, ws_ff=ws_ff, ws_fb=ws_fb,
+                        f_seg2=f_seg2, f_proj2=f_proj2, f_mask2=f_mask2).items():
         assert g.intact(), "guard band damaged around %s" % name
     # and the results are the real thing
     ref = np_oracle.smpl_layer_call(host_model, p_np)
@@ -96,3 +120,11 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     assert np.array_equal(proj.view(torch.float32, (n, Vs, 3)).cpu().numpy(), proj_s.view(torch.float32, (n, Vs, 3)).cpu().numpy())
     assert torch.isfinite(g_params.view(torch.float32, (n, 86))).all() and torch.isfinite(g_params2.view(torch.float32, (n, 86))).all()
     assert float(seg.view(torch.float32, (n, wh, wh, 32)).sum(-1).min()) > 0.99
+    f32 = lambda g, shape: g.view(torch.float32, shape)      # noqa: E731
+    assert torch.equal(f32(g_params_c, (n, 86)), f32(g_params, (n, 86)))
+    assert torch.equal(f32(f_verts, (n, V, 3)), f32(verts, (n, V, 3)))
+    assert torch.equal(f32(f_proj, (n, Vs, 3)), f32(proj, (n, Vs, 3))) and torch.equal(f32(f_mask, (n, Vs)), f32(mask, (n, Vs)))
+    assert torch.equal(f32(f_seg, (n, wh, wh, 32)), f32(seg, (n, wh, wh, 32)))
+    assert torch.equal(f32(f_seg2, (n, wh, wh, 32)), f32(seg, (n, wh, wh, 32)))
+    ga, gb = f32(f_gp, (n, 86)), f32(g_params, (n, 86))
+    assert float((ga - gb).abs().max()) <= 1e-5 * float(gb.abs().max())     # the seg backward sums rows in on-demand order

@@ -293,10 +293,54 @@ def test_seg_all_visible_full_resolution(pkg, host_model, parts_by_vs, make_para
     assert bad.mean() <= 2e-3, (bad.mean(), np.abs(gg - ref64).max(), scale)
 
 
+def _explain_full_path(out, ref, tag):
+    """Full-path comparison with every deviation accounted for (returns the measured rates; also written to
+    gpurun_out/parity_rates.jsonl when that directory exists).
+
+    The kernel's projections differ from the fp32 oracle's by dp <= 2.5e-5 (both sit ~1e-5 from the fp64 value, see
+    test_projection).  Consequences, and nothing else, may differ downstream:
+      * a vertex within dp of a .5 pixel boundary may round into the neighbouring z-buffer cell: a MASK FLIP; scores
+        around that vertex then change by O(1), so samples with a flipped mask are compared on labels only, loosely;
+      * on samples with identical masks every score moves by at most |ds| <= |dd| <= sqrt(2) dp (exp(-d) is
+        1-Lipschitz in d), so a label (arg-max over channels) can only flip at a pixel whose two best oracle scores
+        are closer than 2 sqrt(2) dp + 2 * 2e-6 (the score tolerance): every mismatch must be such a pixel.
+    """
+    import json
+    import os
+    got_p, ref_p = out["projects"].cpu().numpy(), ref["projects"]
+    dp = float(np.abs(got_p - ref_p).max())
+    got_m, ref_m = out["mask"].cpu().numpy(), ref["mask"]
+    seg, rseg = out["seg"].cpu().numpy(), ref["seg"]
+    same = (got_m == ref_m).all(axis=1)
+    lab, rlab = _labels(seg), _labels(rseg)
+    mism = lab != rlab
+    top2 = np.sort(rseg, axis=-1)[..., -2:]
+    gap = top2[..., 1] - top2[..., 0]
+    bound = 2.0 * np.sqrt(2.0) * dp + 4e-6
+    unexplained = int((mism & (gap > bound) & same[:, None, None]).sum())
+    rates = {"case": tag, "n": int(got_p.shape[0]), "max_abs_dprojects": dp, "mask_flip_vertex_rate": float((got_m != ref_m).mean()),
+             "samples_with_mask_flip": int((~same).sum()),
+             "label_mismatch_rate_same_mask": float(mism[same].mean()) if same.any() else None,
+             "label_mismatch_rate_all": float(mism.mean()), "unexplained_label_mismatches": unexplained,
+             "max_abs_dseg_same_mask": float(np.abs(seg[same] - rseg[same]).max()) if same.any() else None,
+             "tie_gap_bound": float(bound)}
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_rates.jsonl"), "a") as f:
+            f.write(json.dumps(rates) + "\n")
+    assert dp <= 2.5 * TOL_GEOM, rates                       # see test_projection for the 1e-5-vs-fp64 statement
+    assert same.any(), rates
+    assert unexplained == 0, rates                           # every label flip is a near-tie of the oracle's own scores
+    assert rates["label_mismatch_rate_same_mask"] <= LABEL_MISMATCH_MAX, rates       # the stated <= 0.1 %
+    assert rates["max_abs_dseg_same_mask"] <= np.sqrt(2.0) * dp + TOL_SCORE + 1e-6, rates
+    assert rates["mask_flip_vertex_rate"] <= 2e-3, rates     # a flip moves <= 2 vertices (loser / winner of one cell)
+    return rates
+
+
 @pytest.mark.parametrize("n", [64, 130])
 def test_full_path_dense_batch(pkg, host_model, parts_by_vs, make_params, n):
     """Batches >= 64 take the tensor-core (tcgen05, fp16-split forward / 3xTF32 backward) blend path; same tolerances as
-    the small-batch path."""
+    the small-batch path, every downstream deviation explained (see _explain_full_path)."""
     wh, vs = 48, 5
     p = make_params(n, wh, seed=101)
     ref = np_oracle.decode(host_model, p, wh, vs, parts_by_vs[vs])
@@ -304,26 +348,30 @@ def test_full_path_dense_batch(pkg, host_model, parts_by_vs, make_params, n):
     out = dec(t(p))
     assert np.abs(out["verts"].cpu().numpy() - ref["verts"]).max() <= TOL_GEOM
     assert np.abs(out["joints"].cpu().numpy() - ref["J_transformed"]).max() <= TOL_GEOM
-    assert np.abs(out["projects"].cpu().numpy() - ref["projects"]).max() <= 2.5 * TOL_GEOM   # see test_projection
-    assert (_labels(out["seg"].cpu().numpy()) != _labels(ref["seg"])).mean() <= 5e-3
+    _explain_full_path(out, ref, "dense n=%d vs=5" % n)
+    # the fused entry (smpl_b200_full_fwd) runs the same kernels: identical bits
+    fout = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev(), fused=True)(t(p))
+    for k in ("verts", "joints", "projects", "mask", "seg"):
+        assert torch.equal(fout[k], out[k]), k
 
 
-def test_blend_fp16_split_and_tf32_paths_agree(pkg, host_model, make_params, monkeypatch):
-    """The dense-batch forward blend runs as fp16-split tensor-core products (default) or 3xTF32
-    (SMPL_B200_TF32_FWD=1 when the model handle is created): both inside the geometry tolerance, and within 1e-6 of
-    each other."""
-    import copy
+def test_dense_batch_blend_coefficient_range(pkg, host_model, make_params):
+    """The dense-batch forward blend runs as fp16-split tensor-core products with the coefficients scaled by 2^6: exact
+    (inside the geometry tolerance) for every |beta| <= 1023, saturating -- finite, never inf/NaN -- beyond that
+    (include/smpl_b200.h, smpl_b200_model_create)."""
     n, wh = 200, 48
     p = make_params(n, wh, seed=131)
     p[0, 76:] = [3.0, -3.0, 2.5, -2.0, 1.5, 3.0, -3.0, 0.1, -0.1, 0.0]        # betas at the sampler's clip
+    p[1, 76:] = [40.0, -25.0, 10.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 100.0]      # far outside any plausible shape
     ref = np_oracle.smpl_layer_call(host_model, p)
-    got = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("SMPL_B200_TF32_FWD", flag)
-        dec = pkg.SmplDecoder(copy.copy(host_model), wh, 5, device=dev())     # a new model handle reads the variable
-        got[flag] = dec(t(p), seg=False)["verts"].cpu().numpy()
-        assert np.abs(got[flag] - ref).max() <= TOL_GEOM, flag
-    assert np.abs(got["0"] - got["1"]).max() <= 1e-6
+    dec = pkg.SmplDecoder(host_model, wh, 5, device=dev())
+    got = dec(t(p), seg=False)["verts"].cpu().numpy()
+    scale = np.maximum(1.0, np.abs(ref).max(axis=(1, 2), keepdims=True))      # sample 1's vertices are O(10)
+    assert (np.abs(got - ref) / scale).max() <= TOL_GEOM
+    p[2, 76] = 5000.0                                                           # a diverged regressor
+    got = dec(t(p), seg=False)["verts"].cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got[3:] - ref[3:]).max() <= TOL_GEOM
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -379,14 +427,7 @@ def test_full_path_forward(pkg, host_model, parts_by_vs, make_params, n, vs):
     dec = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev())
     out = dec(t(p))
     assert np.abs(out["verts"].cpu().numpy() - ref["verts"]).max() <= TOL_GEOM
-    assert np.abs(out["projects"].cpu().numpy() - ref["projects"]).max() <= 2.5 * TOL_GEOM   # see test_projection
-    # projections differ by ~1e-6, so a vertex within that of a .5 boundary may change pixel: allow a tiny mismatch
-    assert (out["mask"].cpu().numpy() != ref["mask"]).mean() <= 2e-3
-    seg = out["seg"].cpu().numpy()
-    assert (_labels(seg) != _labels(ref["seg"])).mean() <= 5e-3
-    same = (out["mask"].cpu().numpy() == ref["mask"]).all(axis=1)
-    if same.any():
-        assert np.abs(seg[same] - ref["seg"][same]).max() <= 1e-4      # |ds| <= |dd| ~ 1e-5 * few
+    _explain_full_path(out, ref, "small n=%d vs=%s" % (n, vs))
 
 
 def test_full_path_backward_runs_and_matches(pkg, host_model, parts_by_vs, tconst64, make_params):
@@ -410,6 +451,83 @@ def test_full_path_backward_runs_and_matches(pkg, host_model, parts_by_vs, tcons
     err = (np.abs(got - ref) / scale)[same_mask]
     assert err.max() <= 2e-2, err.max()       # thousands of arg-min terms per parameter; a few flip at fp32 ties
     assert np.median(err) <= 1e-4
+
+
+def test_fused_decoder_backward_matches_modular(pkg, host_model, parts_by_vs, make_params):
+    """SmplDecoder(fused=True) (smpl_b200_full_fwd/_bwd, compact sampled v_posed as backward state) against the modular
+    autograd chain: same kernels, so identical up to the seg backward's on-demand row order."""
+    n, wh, vs = 70, 48, 5
+    p = make_params(n, wh, seed=83)
+    g = torch.randn((n, wh, wh, 32), device=dev(), generator=torch.Generator(device=dev()).manual_seed(5))
+    grads = {}
+    for fused in (False, True):
+        dec = pkg.SmplDecoder(host_model, wh, vs, need_verts=False, parts=parts_by_vs[vs], device=dev(), fused=fused)
+        x = t(p).requires_grad_(True)
+        dec(x)["seg"].backward(g)
+        grads[fused] = x.grad.clone()
+    scale = float(grads[False].abs().max())
+    assert float((grads[True] - grads[False]).abs().max()) <= 1e-5 * scale
+    # CUDA-graph replay of the same step (GraphedDecoderStep): same numbers again
+    dec = pkg.SmplDecoder(host_model, wh, vs, need_verts=False, parts=parts_by_vs[vs], device=dev(), fused=True)
+    gs = pkg.GraphedDecoderStep(dec, n, device=dev())
+    got = gs(t(p), g).clone()
+    assert gs.launches_per_step >= 8
+    assert float((got - grads[False]).abs().max()) <= 1e-5 * scale
+    got2 = gs(t(p) * 1.0, 2.0 * g).clone()                               # new inputs through the static buffers
+    assert float((got2 - 2.0 * grads[False]).abs().max()) <= 2e-5 * scale
+
+
+def test_seg_duplicate_entries_tie_gradient(pkg):
+    """Exact ties of the max (SURVEY 3.3 / hard part 5).  TF's reduce_max gradient is split EVENLY among equal maxima;
+    the kernels give it all to the first arg-max.  Two kinds of exact tie exist:
+      (a) the same vertex listed twice in a part -- `index // vertex_sampling` collisions of projects_to_seg.py:36-37
+          (the vs=5 table holds such duplicates): tf.gather's adjoint adds the halves back onto the one vertex, so both
+          rules give that vertex the same total -- checked here against the amax-based torch twin, to rounding;
+      (b) two DIFFERENT vertices at identical coordinates: TF gives each half, the kernel gives the lower index all of
+          it; the SUM over the pair is the same (and it is what reaches d/d params when the two move together)."""
+    rng = np.random.default_rng(29)
+    wh, Vs = 24, 40
+    pr = np.concatenate([rng.random((2, Vs, 2)) * 22 + 1, rng.standard_normal((2, Vs, 1))], 2).astype(np.float32)
+    pr[:, 7, :2] = pr[:, 3, :2]                                           # (b): vertices 3 and 7 coincide exactly
+    mask = np.ones((2, Vs), np.float32)
+    parts = [[0, 1, 1, 2, 2, 2], [3, 7, 4], [5, 5, 6, 8, 9], [10, 11, 12, 13, 13]] + [[14 + k] for k in range(27)]
+    g = rng.standard_normal((2, wh, wh, 32)).astype(np.float32)
+    ref64 = _seg_grad_oracle(pr, mask, wh, None, parts, g, torch.float64)   # torch.amax: TF's even split
+    x = t(pr).requires_grad_(True)
+    out = pkg.projects_to_seg([x, t(mask)], wh, None, parts=parts)
+    assert np.abs(out.detach().cpu().numpy() - np_oracle.projects_to_seg([pr, mask], wh, None, parts)).max() <= TOL_SCORE
+    (out * t(g)).sum().backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    scale = np.abs(ref64).max()
+    others = [v for v in range(Vs) if v not in (3, 7)]
+    bad = np.abs(got[:, others] - ref64[:, others]) > 2e-4 * scale         # (a): duplicates included, same totals
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(got[:, others] - ref64[:, others]).max(), scale)
+    for v in (1, 2, 5, 13):
+        assert np.abs(got[:, v] - ref64[:, v]).max() <= 2e-4 * scale, v
+    pair_got, pair_ref = got[:, 3] + got[:, 7], ref64[:, 3] + ref64[:, 7]
+    assert np.abs(pair_got - pair_ref).max() <= 2e-4 * scale               # (b): the pair's total
+    assert np.all(got[:, 7] == 0) and np.abs(ref64[:, 3] - ref64[:, 7]).max() <= 1e-12 * scale   # first arg-max vs even split
+
+
+def test_seg_backward_misaligned_upstream_gradient(pkg, host_model, parts_by_vs, make_params):
+    """A contiguous upstream gradient whose storage offset is 4 bytes off 16-byte alignment (e.g. a slice of a cat's
+    backward): the backward must not issue its 16-byte bulk L2 prefetch on it, and the result must not change."""
+    n, wh, vs = 3, 48, 5
+    p, pr, mask = _oracle_inputs(host_model, make_params, n, wh, vs, seed=43)
+    gen = torch.Generator(device=dev()).manual_seed(12)
+    flat = torch.randn((n * wh * wh * 32 + 1,), device=dev(), generator=gen)
+    g_off = flat[1:].view(n, wh, wh, 32)
+    assert g_off.is_contiguous() and g_off.data_ptr() % 16 == 4
+    g_al = g_off.clone()
+    assert g_al.data_ptr() % 16 == 0
+    grads = []
+    for g in (g_al, g_off):
+        x = t(pr).requires_grad_(True)
+        pkg.projects_to_seg([x, t(mask)], wh, vs, parts=parts_by_vs[vs]).backward(g)
+        grads.append(x.grad.clone())
+    torch.cuda.synchronize()
+    scale = float(grads[0].abs().max())
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * scale
 
 
 def test_errors(pkg, host_model):
@@ -478,7 +596,7 @@ def test_silhouette_crossentropy(pkg):
     ref = -(torch.tensor(y.astype(np.float64)) * torch.log(p)).sum(-1)              # keras.losses.categorical_crossentropy
     ref.sum().backward()
     x = t(sil).requires_grad_(True)
-    got = pkg.categorical_crossentropy(t(y), x)
+    got = pkg.categorical_crossentropy(t(y), x, from_logits=True)
     got.sum().backward()
     assert np.abs(got.detach().cpu().numpy() - ref.detach().numpy()).max() <= 2e-6
     assert np.abs(x.grad.cpu().numpy().reshape(n, wh * wh, 2) - x64.grad.numpy()).max() <= 3e-6

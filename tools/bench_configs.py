@@ -113,7 +113,7 @@ def main():
             n, wh, C = 16384, 48, 32
             seg = torch.rand((n, wh * wh, C), device=dev)
             lab = torch.randint(0, C, (n, wh * wh), device=dev, dtype=torch.uint8)
-            loss_fn = pkg.categorical_focal_loss(gamma=2.0, weight_classes=True)
+            loss_fn = pkg.categorical_focal_loss(gamma=2.0, weight_classes=True, from_logits=True)
             gl = torch.full((n, wh * wh), 1.0 / (n * wh * wh), device=dev)
 
             def step():

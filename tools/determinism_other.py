@@ -53,7 +53,7 @@ for wh in (64, 256):
     rep("silhouette fwd+bwd %dx%d, N=%d" % (wh, wh, pr.shape[0]), sil, reps=3)
 seg = torch.rand((2048, 48, 48, 32), device=dev)
 lab = torch.randint(0, 32, (2048, 48, 48), device=dev, dtype=torch.uint8)
-loss_fn = pkg.categorical_focal_loss(gamma=2.0)
+loss_fn = pkg.categorical_focal_loss(gamma=2.0, from_logits=True)
 
 
 def focal():
