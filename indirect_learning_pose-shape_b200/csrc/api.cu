@@ -465,7 +465,7 @@ static DecodeWs decode_ws(const SmplB200Model* m, int N, bool bwd, bool full_gra
   w.Jtr = take((size_t)N * kJ * 3);
   if (bwd) {
     w.gA = take((size_t)N * kJ * 12);
-    w.gX = take((size_t)N * kKPad);
+    w.gX = take((size_t)N * kKPad * (N >= kDenseBatch ? kMaxBlendBwdSplit : 1));   // K-split planes of the tensor-core product
     const int Vs = (m->V + vs - 1) / vs;
     w.cam_chunks = lbs_bwd_cam_chunks(Vs);
     w.gcam = take((size_t)N * 4 * w.cam_chunks);
@@ -564,9 +564,10 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp,
                               dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, &cam_chunks,
                               full ? nullptr : v_posed_sampled, SMPL_B200_VPS_LD(t->Vs), st));
-  if (dense) CHECK_LAUNCH(launch_blend_bwd_tc(m, t, w.gvp, w.gvplo, w.gvp_ld, N, w.gX, st));
+  int gx_planes = 1;
+  if (dense) CHECK_LAUNCH(launch_blend_bwd_tc(m, t, w.gvp, w.gvplo, w.gvp_ld, N, w.gX, &gx_planes, st));
   else CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
-  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, g_joints24, w.gcam, cam_chunks, N, g_params, st));
+  CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, gx_planes, g_joints24, w.gcam, cam_chunks, N, g_params, st));
   return SMPL_B200_OK;
 }
 

@@ -113,8 +113,10 @@ cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, 
                             float* Jtr, cudaStream_t st);
 cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const float* Xl, int N, float* v_posed,
                                 cudaStream_t st);
+constexpr int kMaxBlendBwdSplit = 8;   // K slices of the tensor-core backward blend product = planes of g_X (workspace size)
+// g_X: [*planes][N][kKPad] partial sums (planes <= kMaxBlendBwdSplit), added in fixed order by launch_pose_bwd
 cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const float* gvp_hi, const float* gvp_lo,
-                                size_t gvp_ld, int N, float* g_X, cudaStream_t st);
+                                size_t gvp_ld, int N, float* g_X, int* planes, cudaStream_t st);
 constexpr float kXScale16 = 64.0f;     // blend coefficients are scaled by 2^6 before their fp16 split: |x| < 1023 (pose
                                        // features are bounded by 2, betas by a few units); lo's quantisation is 1e-9 absolute
 constexpr int kDenseBatch = 64;   // from this batch on the blend products run on the tensor cores
@@ -145,9 +147,10 @@ cudaError_t launch_lbs_bwd(const SmplB200Model* m, const VsTables* t, int vs_pro
 cudaError_t launch_blend_bwd(const SmplB200Model* m, const VsTables* t, const float* g_vp, size_t gvp_ld, int N,
                              float* g_X, cudaStream_t st);
 // g_cam = [cam_chunks][N][4] partial camera-gradient sums from launch_lbs_bwd (or null)
+// g_X = [gx_planes][N][kKPad] partial sums of the blend backward (1 plane unless the tensor-core product was K-split)
 cudaError_t launch_pose_bwd(const SmplB200Model* m, const float* params, const float* g_A, const float* g_X,
-                            const float* g_Jtr, const float* g_cam, int cam_chunks, int N, float* g_params,
-                            cudaStream_t st);
+                            int gx_planes, const float* g_Jtr, const float* g_cam, int cam_chunks, int N,
+                            float* g_params, cudaStream_t st);
 int lbs_bwd_cam_chunks(int num_processed_verts);
 cudaError_t launch_project_fwd(const float* verts, const float* params, int N, int V, int vs, float* projects,
                                cudaStream_t st);

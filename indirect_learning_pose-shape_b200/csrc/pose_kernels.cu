@@ -193,9 +193,10 @@ pose_fwd_kernel(const float* __restrict__ params, int N, const float* __restrict
 //   g_cam is [cam_chunks][N][4] partial sums written by the LBS backward (summed here in fixed order), or null.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pose_bwd_kernel(const float* __restrict__ params, int N, const float* __restrict__ Jt, const float* __restrict__ Jd,
-                const TreeInfo tree, const float* __restrict__ gA, const float* __restrict__ gX,
+                const TreeInfo tree, const float* __restrict__ gA, const float* __restrict__ gX, int gx_planes,
                 const float* __restrict__ gJtr, const float* __restrict__ gcam, int cam_chunks,
                 float* __restrict__ gparams) {
+  const size_t gx_stride = (size_t)N * kKPad;            // between the K-split planes of gX (added in fixed order)
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -267,8 +268,15 @@ pose_bwd_kernel(const float* __restrict__ params, int N, const float* __restrict
   }
   if (live && j >= 1 && gX) {                             // pose_feature = R_j - I
     const float* g = gX + (size_t)n * kKPad + kBetas + (j - 1) * 9;
+    float t9[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) gR.m[i] += g[i];
+    for (int i = 0; i < 9; ++i) t9[i] = g[i];
+    for (int pl = 1; pl < gx_planes; ++pl) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) t9[i] += g[(size_t)pl * gx_stride + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) gR.m[i] += t9[i];
   }
 
   // ---- Rodrigues backward (autodiff of batch_smpl.py:265-275) --------------------------------------------------
@@ -312,7 +320,11 @@ pose_bwd_kernel(const float* __restrict__ params, int N, const float* __restrict
     float v = 0.f;
 #pragma unroll
     for (int k = 0; k < kBetas; ++k) if (k == lane) v = gb[k];
-    if (gX) v += gX[(size_t)n * kKPad + lane];
+    if (gX) {
+      float t = gX[(size_t)n * kKPad + lane];
+      for (int pl = 1; pl < gx_planes; ++pl) t += gX[(size_t)pl * gx_stride + (size_t)n * kKPad + lane];
+      v += t;
+    }
     gparams[(size_t)n * kParams + 76 + lane] = v;
   }
   if (lane < 4) {
@@ -335,12 +347,12 @@ cudaError_t launch_pose_fwd(const SmplB200Model* m, const float* params, int N, 
 }
 
 cudaError_t launch_pose_bwd(const SmplB200Model* m, const float* params, const float* g_A, const float* g_X,
-                            const float* g_Jtr, const float* g_cam, int cam_chunks, int N, float* g_params,
-                            cudaStream_t st) {
+                            int gx_planes, const float* g_Jtr, const float* g_cam, int cam_chunks, int N,
+                            float* g_params, cudaStream_t st) {
   const int blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
   LaunchScope scope(KID_POSE_BWD, st);
-  pose_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, g_A, g_X, g_Jtr, g_cam,
-                                                         cam_chunks, g_params);
+  pose_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(params, N, m->Jt, m->Jd, m->tree, g_A, g_X, max(gx_planes, 1),
+                                                         g_Jtr, g_cam, cam_chunks, g_params);
   return cudaGetLastError();
 }
 

@@ -149,7 +149,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int kblocks, int tiles_m,
-                   int tiles_n, float out_scale) {
+                   int tiles_n, float out_scale, int ksplit, size_t plane_stride) {
+  // Work unit = (output tile, K slice s of ksplit): slice s covers K blocks [s kblocks / ksplit, (s+1) kblocks / ksplit)
+  // and writes its partial tile to plane s of D (D + s * plane_stride); the consumer adds the planes in fixed order
+  // (deterministic, unlike atomics).  ksplit = 1: the plain GEMM.  The backward blend product has only 2 N / 128 output
+  // tiles of K = 4160: without the split a 2048-sample shard kept 32 of 148 SMs busy.
   constexpr int kBKe = F16 ? 2 * kBK : kBK;            // operand elements per K block (one 128-byte swizzle row)
   constexpr int kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
   constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
@@ -163,7 +167,7 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   uint64_t* tempty = tfull + kTmemBufs;                // TMEM buffer b drained into registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kTmemBufs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = tiles_m * tiles_n;
+  const int ntiles = tiles_m * tiles_n * ksplit;       // work units
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -184,9 +188,11 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < ntiles; unit += gridDim.x) {
+        const int tile = unit / ksplit, ks = unit - tile * ksplit;
         const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb0 = (int)(((long long)kblocks * ks) / ksplit), kb1 = (int)(((long long)kblocks * (ks + 1)) / ksplit);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
           mbar_expect_tx(&full[stage], kStageBytes);
@@ -204,8 +210,10 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       constexpr uint32_t idesc = make_idesc(kBM, BN, F16);
       int stage = 0, buf = 0;
       uint32_t phase = 0, buf_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int kb = 0; kb < kblocks; ++kb) {
+      for (int unit = blockIdx.x; unit < ntiles; unit += gridDim.x) {
+        const int ks = unit % ksplit;
+        const int kb0 = (int)(((long long)kblocks * ks) / ksplit), kb1 = (int)(((long long)kblocks * (ks + 1)) / ksplit);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&tempty[buf], buf_phase ^ 1);      // the accumulate warps have drained this TMEM buffer
           mbar_wait(&full[stage], phase);              // TMA has landed this stage
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -242,12 +250,14 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int hcol = (warp - 2) >= 4 ? HN : 0;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < ntiles; unit += gridDim.x) {
+      const int tile = unit / ksplit, ks = unit - tile * ksplit;
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+      const int kb0 = (int)(((long long)kblocks * ks) / ksplit), kb1 = (int)(((long long)kblocks * (ks + 1)) / ksplit);
       float acc[HN];
 #pragma unroll
       for (int i = 0; i < HN; ++i) acc[i] = 0.f;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&tfull[buf], buf_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride) + (uint32_t)hcol;
@@ -267,13 +277,13 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
       const int row = m0 + q * 32 + lane;
       if (row < M) {
-        float* drow = D + (size_t)row * ldd + n0 + hcol;
+        float* drow = D + (size_t)ks * plane_stride + (size_t)row * ldd + n0 + hcol;
 #pragma unroll
         for (int c = 0; c < HN; c += 8) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = F16 ? acc[c + e] * out_scale : acc[c + e];
-          if (BIAS) {
+          if (BIAS && ks == 0) {
             const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c);
             const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + hcol + c + 4);
             o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
@@ -299,12 +309,12 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 // tile costs 128 KB + 128 KB / kPanelRows.  Work unit = (column panel, chunk of row tiles); units go to the CTAs
 // round-robin.  Pipeline roles and the per-K-block register accumulation are those of the kernel above.
 constexpr int kPanelKB = 4;          // K blocks of the forward (K = 217 <= 256 halfs)
-template <int BN, int kPanelStages, int kPanelRows>   // output columns per panel, A stages (hi + lo = 32 KB each), row tiles per unit
+template <int BN, int kPanelStages>   // output columns per panel, A stages (hi + lo = 32 KB each)
 __global__ void __launch_bounds__(kThreads, 1)
 blend_f16_panel_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                        float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int tiles_m, int tiles_n,
-                       float out_scale) {
+                       float out_scale, int kPanelRows) {   // kPanelRows: row tiles per unit, chosen by the launcher
   constexpr int kBKe = 2 * kBK;
   constexpr int kTile = kBM * kBK * 4;                 // one 128-row x 128-byte operand box: 16 KB
   constexpr int kBTile = BN * kBK * 4;                 // one BN-row box of B
@@ -522,7 +532,8 @@ cudaError_t make_map(CUtensorMap* map, const void* base, int rows, int cols, int
 
 template <int BN, bool BIAS, bool F16>
 cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh, const void* Bl, int ldb, float* D,
-                        int ldd, const float* bias, int M, int Ntot, int K, float out_scale, int num_sms, cudaStream_t st) {
+                        int ldd, const float* bias, int M, int Ntot, int K, float out_scale, int num_sms, cudaStream_t st,
+                        int ksplit = 1, size_t plane_stride = 0) {
   cudaError_t e = load_encode();
   if (e != cudaSuccess) return e;
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -535,10 +546,10 @@ cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh,
   e = cudaFuncSetAttribute(split3_gemm_kernel<BN, BIAS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = Ntot / BN;
-  const int grid = min(tiles_m * tiles_n, num_sms);
+  const int grid = min(tiles_m * tiles_n * ksplit, num_sms);
   constexpr int kBKe = F16 ? 2 * kBK : kBK;
   split3_gemm_kernel<BN, BIAS, F16><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, (K + kBKe - 1) / kBKe,
-                                                                   tiles_m, tiles_n, out_scale);
+                                                                   tiles_m, tiles_n, out_scale, ksplit, plane_stride);
   return cudaGetLastError();
 }
 
@@ -554,30 +565,62 @@ cudaError_t launch_blend_fwd_tc(const SmplB200Model* m, const float* Xh, const f
     CUtensorMap mAh, mAl, mBh, mBl;
     if ((e = make_map(&mAh, Xh, N, kK, kKPad, kBM, true)) != cudaSuccess) return e;
     if ((e = make_map(&mAl, Xl, N, kK, kKPad, kBM, true)) != cudaSuccess) return e;
-    // measured (N = 16384): <128, 3, 16> 0.55 ms; 2 stages 0.61; 8 rows 0.57; 32 rows 0.60; <96, 4, 16> 0.58; <64, 5, 16> 0.66
-    constexpr int kPanelBN = 128, kPanelStages = 3, kPanelRows = 16;
+    // measured (N = 16384): <128, 3> with 16 rows per unit 0.55 ms; 2 stages 0.61; 8 rows 0.57; 32 rows 0.60; <96, 4> 0.58;
+    // <64, 5> 0.66
+    constexpr int kPanelBN = 128, kPanelStages = 3;
     if ((e = make_map(&mBh, m->BT16_hi, m->LD, kK, kKPad, kPanelBN, true)) != cudaSuccess) return e;
     if ((e = make_map(&mBl, m->BT16_lo, m->LD, kK, kKPad, kPanelBN, true)) != cudaSuccess) return e;
     const size_t smem = (size_t)kPanelKB * 2 * kPanelBN * 128 + (size_t)kPanelStages * 2 * kBM * 128 + 256 + 1024;
-    e = cudaFuncSetAttribute(blend_f16_panel_kernel<kPanelBN, kPanelStages, kPanelRows>,
+    e = cudaFuncSetAttribute(blend_f16_panel_kernel<kPanelBN, kPanelStages>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int tiles_m = (N + kBM - 1) / kBM, tiles_n = m->LD / kPanelBN;
-    const int nunits = tiles_n * ((tiles_m + kPanelRows - 1) / kPanelRows);
-    blend_f16_panel_kernel<kPanelBN, kPanelStages, kPanelRows><<<min(nunits, m->num_sms), kThreads, smem, st>>>(
-        mAh, mAl, mBh, mBl, v_posed, m->LD, m->vt_pad, N, tiles_m, tiles_n, 1.0f / (kXScale16 * m->bt16_scale));
+    // Row tiles per unit: units go to the CTAs round-robin, so the launch takes ceil(units / SMs) rounds of (rows + the
+    // unit's exposed panel load, ~0.85 of a row tile: 128 KB against 32 KB + the MMAs).  16 rows minimise that at 16384
+    // samples (9 rounds of 16); a 2048-sample shard (16 row tiles) would run 2 rounds of 16 with 14 CTAs in the second.
+    int rows = 16;
+    {
+      double best = 1e30;
+      for (int r = 1; r <= 32; ++r) {
+        const int chunks = (tiles_m + r - 1) / r;
+        const int rr = (tiles_m + chunks - 1) / chunks;            // the even split with that many chunks
+        const long long units = (long long)tiles_n * chunks;
+        const double cost = (double)((units + m->num_sms - 1) / m->num_sms) * (rr + 0.85);
+        if (cost < best - 1e-9) { best = cost; rows = rr; }
+      }
+    }
+    const int nunits = tiles_n * ((tiles_m + rows - 1) / rows);
+    blend_f16_panel_kernel<kPanelBN, kPanelStages><<<min(nunits, m->num_sms), kThreads, smem, st>>>(
+        mAh, mAl, mBh, mBl, v_posed, m->LD, m->vt_pad, N, tiles_m, tiles_n, 1.0f / (kXScale16 * m->bt16_scale), rows);
     return cudaGetLastError();
   }
   return launch_gemm<128, true, false>(Xh, Xl, kKPad, m->BT_hi, m->BT_lo, kKPad, v_posed, m->LD, m->vt_pad, N, m->LD, kKPad,
                                        1.0f, m->num_sms, st);
 }
 
-// g_X[N][224] = g_vp[N][Kp] * Bs[224][Kp]^T   (Kp a multiple of 32)
+// K slices of the backward blend product for batch N and depth Kp: 2 ceil(N / 128) output tiles of Kp / 32 K blocks each
+// go to the CTAs round-robin; a slice costs its K blocks plus ~8 K-block times of pipeline fill, epilogue and plane sum
+// (measured: 16384 samples 0.168 ms unsplit / 0.176 in 4 slices; 2048 samples 0.080 unsplit / 0.033 in 4 slices).
+int blend_bwd_ksplit(const SmplB200Model* m, int N, int Kp) {
+  const int tiles = 2 * ((N + kBM - 1) / kBM), kblocks = (Kp + kBK - 1) / kBK;
+  int best_s = 1;
+  double best = 1e30;
+  for (int s = 1; s <= kMaxBlendBwdSplit; ++s) {
+    const long long units = (long long)tiles * s;
+    const double cost = (double)((units + m->num_sms - 1) / m->num_sms) * ((kblocks + s - 1) / s + 8.0);
+    if (cost < best - 1e-9) { best = cost; best_s = s; }
+  }
+  return best_s;
+}
+
+// g_X[s][N][224] (s < ksplit planes, summed by pose_bwd) = g_vp[N][Kp] * Bs[224][Kp]^T   (Kp a multiple of 32)
 cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const float* gvp_hi, const float* gvp_lo,
-                                size_t gvp_ld, int N, float* g_X, cudaStream_t st) {
+                                size_t gvp_ld, int N, float* g_X, int* planes, cudaStream_t st) {
   LaunchScope scope(KID_BLEND_BWD, st);
+  const int ks = blend_bwd_ksplit(m, N, t->Kp);
+  *planes = ks;
   return launch_gemm<kKPad / 2, false, false>(gvp_hi, gvp_lo, (int)gvp_ld, t->Bs_hi, t->Bs_lo, t->Kp, g_X, kKPad, nullptr,
-                                              N, kKPad, t->Kp, 1.0f, m->num_sms, st);
+                                              N, kKPad, t->Kp, 1.0f, m->num_sms, st, ks, (size_t)N * kKPad);
 }
 
 }  // namespace smplb200

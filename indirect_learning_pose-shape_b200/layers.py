@@ -377,6 +377,7 @@ class _FullFn(torch.autograd.Function):
                                               _ptr(joints), _ptr(proj), _ptr(mask), _ptr(seg), _ptr(state), _ptr(ws),
                                               ws.numel(), _stream()), "smpl_b200_full_fwd")
         ctx.dm, ctx.table, ctx.img_wh, ctx.vs, ctx.have_state = dm, table, img_wh, vs, need_grad
+        ctx.set_materialize_grads(False)      # or autograd memsets a dense zero gradient for every unused output (1.6 GB at 16384)
         if need_grad:
             ctx.save_for_backward(params, proj, mask, state)
         ctx.mark_non_differentiable(joints, proj, mask)

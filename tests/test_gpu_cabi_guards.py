@@ -121,7 +121,8 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     assert torch.isfinite(g_params.view(torch.float32, (n, 86))).all() and torch.isfinite(g_params2.view(torch.float32, (n, 86))).all()
     assert float(seg.view(torch.float32, (n, wh, wh, 32)).sum(-1).min()) > 0.99
     f32 = lambda g, shape: g.view(torch.float32, shape)      # noqa: E731
-    assert torch.equal(f32(g_params_c, (n, 86)), f32(g_params, (n, 86)))
+    gc, gm = f32(g_params_c, (n, 86)), f32(g_params, (n, 86))
+    assert float((gc - gm).abs().max()) <= 1e-6 * float(gm.abs().max())       # same arithmetic; the small-batch blend backward sums with atomics
     assert torch.equal(f32(f_verts, (n, V, 3)), f32(verts, (n, V, 3)))
     assert torch.equal(f32(f_proj, (n, Vs, 3)), f32(proj, (n, Vs, 3))) and torch.equal(f32(f_mask, (n, Vs)), f32(mask, (n, Vs)))
     assert torch.equal(f32(f_seg, (n, wh, wh, 32)), f32(seg, (n, wh, wh, 32)))

@@ -50,7 +50,7 @@ def test_c5_full_batch_properties(pkg, host_model, parts_by_vs, make_params):
     assert torch.equal(outs["projects"], out["projects"][idx])
     assert torch.equal(outs["mask"], out["mask"][idx])
     assert torch.equal(outs["seg"], seg[idx])
-    assert float((outs["verts"] - out["verts"][idx]).abs().max()) <= 1e-6      # the blend GEMM tiles the batch
+    assert float((outs["verts"] - out["verts"][idx]).detach().abs().max()) <= 1e-6      # the blend GEMM tiles the batch
     outs["seg"].backward(g[idx])
     scale = float(grad1[idx].abs().max())
     assert float((xs.grad - grad1[idx]).abs().max()) <= 2e-5 * scale
@@ -64,11 +64,11 @@ def test_c5_full_batch_properties(pkg, host_model, parts_by_vs, make_params):
     # tests/test_gpu_parity.py
     ii = idx.cpu().numpy()
     ref = np_oracle.decode(host_model, params[idx].cpu().numpy(), wh, vs, parts_by_vs[vs])
-    assert np.abs(out["verts"][idx].cpu().numpy() - ref["verts"]).max() <= 1e-5
-    assert np.abs(out["joints"][idx].cpu().numpy() - ref["J_transformed"]).max() <= 1e-5
-    dp = float(np.abs(out["projects"][idx].cpu().numpy() - ref["projects"]).max())
+    assert np.abs(out["verts"][idx].detach().cpu().numpy() - ref["verts"]).max() <= 1e-5
+    assert np.abs(out["joints"][idx].detach().cpu().numpy() - ref["J_transformed"]).max() <= 1e-5
+    dp = float(np.abs(out["projects"][idx].detach().cpu().numpy() - ref["projects"]).max())
     assert dp <= 2.5e-5, dp
-    gm, rm = out["mask"][idx].cpu().numpy(), ref["mask"]
+    gm, rm = out["mask"][idx].detach().cpu().numpy(), ref["mask"]
     same = (gm == rm).all(axis=1)
     assert (gm != rm).mean() <= 2e-3 and same.sum() >= 32, ((gm != rm).mean(), int(same.sum()))
     sg, rs = seg[idx].cpu().numpy(), ref["seg"]
@@ -77,7 +77,9 @@ def test_c5_full_batch_properties(pkg, host_model, parts_by_vs, make_params):
     near_tie = (top2[..., 1] - top2[..., 0]) <= 2.0 * np.sqrt(2.0) * dp + 4e-6
     assert int((mism & ~near_tie & same[:, None, None]).sum()) == 0          # every label flip is an oracle near-tie
     assert mism[same].mean() <= 1e-3, mism[same].mean()
-    assert np.abs(sg[same] - rs[same]).max() <= np.sqrt(2.0) * dp + 3e-6
+    dseg = np.abs(sg[same] - rs[same])
+    assert (dseg > np.sqrt(2.0) * dp + 3e-6).mean() <= 1e-5                   # visible vertices: exp(-d) is 1-Lipschitz
+    assert dseg.max() <= 500.0 * np.sqrt(2.0) * dp + 2e-6                     # occluded ones (w = 500) on a pixel centre
     assert ii.shape == (64,)
 
 

@@ -301,9 +301,12 @@ def _explain_full_path(out, ref, tag):
     test_projection).  Consequences, and nothing else, may differ downstream:
       * a vertex within dp of a .5 pixel boundary may round into the neighbouring z-buffer cell: a MASK FLIP; scores
         around that vertex then change by O(1), so samples with a flipped mask are compared on labels only, loosely;
-      * on samples with identical masks every score moves by at most |ds| <= |dd| <= sqrt(2) dp (exp(-d) is
-        1-Lipschitz in d), so a label (arg-max over channels) can only flip at a pixel whose two best oracle scores
-        are closer than 2 sqrt(2) dp + 2 * 2e-6 (the score tolerance): every mismatch must be such a pixel.
+      * on samples with identical masks a score exp(-d w) moves by at most |ds| <= w |dd| <= w sqrt(2) dp: w = 1 for
+        visible vertices (1-Lipschitz), w = 500 for an occluded vertex, which only scores at all within ~0.03 px of a
+        pixel centre (a handful of (pixel, part) pairs per batch).  So all but <= 1e-5 of the scores must agree within
+        sqrt(2) dp + the score tolerance, every one within 500 sqrt(2) dp, and a label (arg-max over channels) can
+        only flip at a pixel whose two best oracle scores are closer than 2 sqrt(2) dp + 2 * 2e-6: every mismatch
+        must be such a pixel.
     """
     import json
     import os
@@ -323,6 +326,8 @@ def _explain_full_path(out, ref, tag):
              "label_mismatch_rate_same_mask": float(mism[same].mean()) if same.any() else None,
              "label_mismatch_rate_all": float(mism.mean()), "unexplained_label_mismatches": unexplained,
              "max_abs_dseg_same_mask": float(np.abs(seg[same] - rseg[same]).max()) if same.any() else None,
+             "frac_dseg_beyond_visible_bound": float((np.abs(seg[same] - rseg[same]) > np.sqrt(2.0) * dp + TOL_SCORE + 1e-6).mean())
+             if same.any() else None,
              "tie_gap_bound": float(bound)}
     d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(d):
@@ -332,7 +337,8 @@ def _explain_full_path(out, ref, tag):
     assert same.any(), rates
     assert unexplained == 0, rates                           # every label flip is a near-tie of the oracle's own scores
     assert rates["label_mismatch_rate_same_mask"] <= LABEL_MISMATCH_MAX, rates       # the stated <= 0.1 %
-    assert rates["max_abs_dseg_same_mask"] <= np.sqrt(2.0) * dp + TOL_SCORE + 1e-6, rates
+    assert rates["frac_dseg_beyond_visible_bound"] <= 1e-5, rates
+    assert rates["max_abs_dseg_same_mask"] <= 500.0 * np.sqrt(2.0) * dp + TOL_SCORE, rates
     assert rates["mask_flip_vertex_rate"] <= 2e-3, rates     # a flip moves <= 2 vertices (loser / winner of one cell)
     return rates
 
@@ -486,7 +492,7 @@ def test_seg_duplicate_entries_tie_gradient(pkg):
       (b) two DIFFERENT vertices at identical coordinates: TF gives each half, the kernel gives the lower index all of
           it; the SUM over the pair is the same (and it is what reaches d/d params when the two move together)."""
     rng = np.random.default_rng(29)
-    wh, Vs = 24, 40
+    wh, Vs = 24, 41
     pr = np.concatenate([rng.random((2, Vs, 2)) * 22 + 1, rng.standard_normal((2, Vs, 1))], 2).astype(np.float32)
     pr[:, 7, :2] = pr[:, 3, :2]                                           # (b): vertices 3 and 7 coincide exactly
     mask = np.ones((2, Vs), np.float32)

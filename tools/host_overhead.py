@@ -46,8 +46,13 @@ def main():
                 step()
                 hs.append(time.perf_counter() - t1)
                 torch.cuda.synchronize()
+            pkg.profile_enable(True); pkg.profile_collect()
+            for _ in range(10):
+                step()
+            pkg.profile_enable(False)
+            kern = {k: round(t / n_, 4) for k, (n_, t) in pkg.profile_collect().items()}
             res[name] = {"ms_per_step": t_total * 1e3, "host_issue_ms_back_to_back": t_issue * 1e3,
-                         "host_ms_per_step_idle_gpu": sorted(hs)[len(hs) // 2] * 1e3}
+                         "host_ms_per_step_idle_gpu": sorted(hs)[len(hs) // 2] * 1e3, "kernel_ms": kern}
         dec = pkg.SmplDecoder(host, 48, 5, parts=parts, device=dev, fused=True)
         gs = pkg.GraphedDecoderStep(dec, B, device=dev)
         gs.params.copy_(p); gs.g_seg.copy_(g)
