@@ -166,6 +166,20 @@ int smpl_b200_seg_fwd(const SmplB200Parts* parts, const float* projects, const f
 int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_seg,
                       const void* saved, int N, int Vs, int img_wh, float* g_projects, void* stream);
 
+/* ---- projects_to_seg fused with the op after it: Reshape -> softmax -> categorical focal loss -------------------------
+ * (model.py:119-120, focal_loss.py:10-48.)  Integer labels only: labels (N,wh,wh) uint8 class ids in the OUTPUT's pixel
+ * order (rows flipped, i.e. the order of y_true).  loss (N, wh*wh) per pixel, as the reference's loss function returns
+ * it.  `seg` may be NULL: a training step never materialises the 128-byte score row per pixel, and the backward reads a
+ * 16-byte record per pixel from `state` (smpl_b200_seg_loss_state_bytes, 16-byte aligned) instead of an upstream
+ * gradient row.  class_weights: num_parts+1 device floats or NULL (ones).  g_loss (N, wh*wh): upstream gradient of the
+ * per-pixel loss.  g_projects (N,Vs,3) fully written. */
+size_t smpl_b200_seg_loss_state_bytes(int N, int img_wh);
+int smpl_b200_seg_loss_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs,
+                           int img_wh, const uint8_t* labels, float gamma, const float* class_weights, float* seg,
+                           float* loss, void* state, void* stream);
+int smpl_b200_seg_loss_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_loss,
+                           const void* state, int N, int Vs, int img_wh, float* g_projects, void* stream);
+
 /* ---- the whole path in one call (model.py:108-118: SMPLLayer -> orthographic_project -> compute_mask -> projects_to_seg)
  * params (N,86) -> projects (N,Vs,3), mask (N,Vs), seg (N,wh,wh,P+1) [+ verts (N,V,3), joints24 (N,24,3); NULL to skip].
  * `state` (nullable; smpl_b200_full_state_bytes, 16-byte aligned) receives what full_bwd needs: the compact sampled
@@ -181,7 +195,10 @@ int smpl_b200_full_bwd(const SmplB200Model* model, const SmplB200Parts* parts, c
                        const void* state, float* g_params, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- projects_to_silhouette (projects_to_silhouette.py:14-44) ------------------------------------------ */
-/* projects (N,Vs,3) -> sil (N,wh,wh,2): channel 0 = 1-s, channel 1 = s, rows flipped. */
+/* projects (N,Vs,3) -> sil (N,wh,wh,2): channel 0 = 1-s, channel 1 = s, rows flipped.
+ * workspace (nullable; smpl_b200_workspace_bytes(model, SMPL_B200_OP_SILHOUETTE_FWD, N, wh, 0) = 2 bytes per pixel): the
+ * forward records every pixel's arg-min vertex there; handed to silhouette_bwd with the same projections, the backward
+ * streams instead of repeating the nearest-vertex search.  NULL on either side: the backward searches. */
 int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,
                              size_t workspace_bytes, void* stream);
 int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, int Vs, int img_wh,

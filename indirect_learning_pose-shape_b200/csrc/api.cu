@@ -484,8 +484,8 @@ size_t smpl_b200_workspace_bytes(const SmplB200Model* m, int op, int N, int img_
   switch (op) {
     case SMPL_B200_OP_DECODE_FWD: return decode_ws(m, N, false, false, 1, nullptr).bytes;
     case SMPL_B200_OP_DECODE_BWD: return decode_ws(m, N, true, vs == 1, vs, nullptr).bytes;
-    case SMPL_B200_OP_SILHOUETTE_FWD:
-    case SMPL_B200_OP_SILHOUETTE_BWD: return 256;
+    case SMPL_B200_OP_SILHOUETTE_FWD:      // the arg-min map the forward hands to the backward: 2 bytes per pixel
+    case SMPL_B200_OP_SILHOUETTE_BWD: return ru((size_t)N * img_wh * img_wh * 2, 256);
     case SMPL_B200_OP_FULL_FWD:      // decode scratch + the transient v_posed
       return decode_ws(m, N, false, false, 1, nullptr).bytes + ru((size_t)N * m->LD * sizeof(float), 256);
     case SMPL_B200_OP_FULL_BWD:      // decode scratch (sampled gradient) + g_projects
@@ -647,6 +647,53 @@ int smpl_b200_seg_bwd(const SmplB200Parts* parts, const float* projects, const f
   return SMPL_B200_OK;
 }
 
+// ---- projects_to_seg + Reshape -> softmax -> categorical focal loss, fused (integer labels) ----------------------------
+size_t smpl_b200_seg_loss_state_bytes(int N, int img_wh) {
+  if (N < 0 || img_wh < 0) return 0;
+  return seg_saved_bytes(N, img_wh) + (size_t)N * img_wh * img_wh * 16;
+}
+
+int smpl_b200_seg_loss_fwd(const SmplB200Parts* parts, const float* projects, const float* mask, int N, int Vs,
+                           int img_wh, const uint8_t* labels, float gamma, const float* class_weights, float* seg,
+                           float* loss, void* state, void* stream) {
+  if (N == 0) return SMPL_B200_OK;
+  int rc = seg_check(parts, projects, mask, N, Vs, img_wh, "seg_loss_fwd");
+  if (rc) return rc;
+  if (!labels || !loss || !state) { set_error("seg_loss_fwd: null labels / loss / state"); return SMPL_B200_ERR_BAD_ARG; }
+  if ((seg && !aligned(seg, 16)) || !aligned(state, 16) || !aligned(loss, 4)) {
+    set_error("seg_loss_fwd: seg/state must be 16-byte aligned"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  unsigned char* saved = (unsigned char*)state;
+  void* aux = saved + seg_saved_bytes(N, img_wh);
+  cudaError_t e = launch_seg_loss_fwd(parts, projects, mask, N, Vs, img_wh, labels, gamma, class_weights, seg, loss, saved,
+                                      aux, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) {
+    set_error("seg_loss_fwd: part table (%d entries) and img_wh=%d need more than 227 KB of shared memory", parts->E, img_wh);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  CHECK_LAUNCH(e);
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_seg_loss_bwd(const SmplB200Parts* parts, const float* projects, const float* mask, const float* g_loss,
+                           const void* state, int N, int Vs, int img_wh, float* g_projects, void* stream) {
+  if (N == 0) return SMPL_B200_OK;
+  int rc = seg_check(parts, projects, mask, N, Vs, img_wh, "seg_loss_bwd");
+  if (rc) return rc;
+  if (!g_loss || !state || !g_projects) { set_error("seg_loss_bwd: null g_loss / state / g_projects"); return SMPL_B200_ERR_BAD_ARG; }
+  if (!aligned(state, 16)) { set_error("seg_loss_bwd: state must be 16-byte aligned"); return SMPL_B200_ERR_BAD_ARG; }
+  const unsigned char* saved = (const unsigned char*)state;
+  const void* aux = saved + seg_saved_bytes(N, img_wh);
+  cudaError_t e = launch_seg_loss_bwd(parts, projects, mask, g_loss, saved, aux, N, Vs, img_wh, g_projects,
+                                      (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) {
+    set_error("seg_loss_bwd: part table (%d entries), Vs=%d and img_wh=%d need more than 227 KB of shared memory", parts->E, Vs, img_wh);
+    return SMPL_B200_ERR_UNSUPPORTED;
+  }
+  CHECK_LAUNCH(e);
+  return SMPL_B200_OK;
+}
+
 // ---- the whole path in one call (model.py:108-118) ---------------------------------------------------------------
 static size_t full_vps_bytes(const SmplB200Model* m, int N, int vs) {
   const int Vs = (m->V + vs - 1) / vs;
@@ -723,20 +770,28 @@ int smpl_b200_full_bwd(const SmplB200Model* m, const SmplB200Parts* parts, const
 int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,
                              size_t workspace_bytes, void* stream) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
-  (void)workspace; (void)workspace_bytes;
   if (!projects || !sil || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   if (img_wh > 4096) { set_error("silhouette_fwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
-  CHECK_LAUNCH(launch_sil_fwd(projects, N, Vs, img_wh, sil, (cudaStream_t)stream));
+  if (workspace && (workspace_bytes < (size_t)N * img_wh * img_wh * 2 || !aligned(workspace, 2))) {
+    set_error("silhouette_fwd: arg-min workspace too small (%zu < %zu bytes)", workspace_bytes, (size_t)N * img_wh * img_wh * 2);
+    return SMPL_B200_ERR_WORKSPACE;
+  }
+  CHECK_LAUNCH(launch_sil_fwd(projects, N, Vs, img_wh, sil, (unsigned short*)workspace, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 
 int smpl_b200_silhouette_bwd(const float* projects, const float* g_sil, int N, int Vs, int img_wh, float* g_projects,
                              void* workspace, size_t workspace_bytes, void* stream) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
-  (void)workspace; (void)workspace_bytes;
   if (!projects || !g_sil || !g_projects || N < 0 || Vs < 1 || img_wh < 1) { set_error("silhouette_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   if (img_wh > 4096) { set_error("silhouette_bwd: img_wh=%d unsupported", img_wh); return SMPL_B200_ERR_UNSUPPORTED; }
-  CHECK_LAUNCH(launch_sil_bwd(projects, g_sil, N, Vs, img_wh, g_projects, (cudaStream_t)stream));
+  if (workspace && (workspace_bytes < (size_t)N * img_wh * img_wh * 2 || !aligned(workspace, 2))) {
+    set_error("silhouette_bwd: arg-min workspace too small (%zu < %zu bytes)", workspace_bytes, (size_t)N * img_wh * img_wh * 2);
+    return SMPL_B200_ERR_WORKSPACE;
+  }
+  cudaError_t e = launch_sil_bwd(projects, g_sil, N, Vs, img_wh, g_projects, (const unsigned short*)workspace, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) { set_error("silhouette_bwd: Vs=%d needs more than 227 KB of shared memory", Vs); return SMPL_B200_ERR_UNSUPPORTED; }
+  CHECK_LAUNCH(e);
   return SMPL_B200_OK;
 }
 

@@ -162,9 +162,19 @@ cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const 
                            float* seg, unsigned char* saved, cudaStream_t st);
 cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
                            const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st);
-cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, cudaStream_t st);
+// projects_to_seg fused with Reshape -> softmax -> categorical focal loss on integer labels (model.py:119-120,
+// focal_loss.py:10-48).  labels [N][wh][wh] in the output's pixel order; aux = [N][wh*wh] float4 (see seg_kernels.cu);
+// seg may be null (training never materialises it).
+cudaError_t launch_seg_loss_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
+                                const unsigned char* labels, float gamma, const float* class_w, float* seg, float* loss,
+                                unsigned char* saved, void* aux, cudaStream_t st);
+cudaError_t launch_seg_loss_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_loss,
+                                const unsigned char* saved, const void* aux, int N, int Vs, int wh, float* g_projects,
+                                cudaStream_t st);
+// saved (nullable): [N][wh][wh] uint16 arg-min vertex of every output pixel; given to both, the backward does not search
+cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, unsigned short* saved, cudaStream_t st);
 cudaError_t launch_sil_bwd(const float* projects, const float* g_sil, int N, int Vs, int wh, float* g_projects,
-                           cudaStream_t st);
+                           const unsigned short* saved, cudaStream_t st);
 
 cudaError_t launch_focal_loss_fwd(const float* seg, const float* y_true, const uint8_t* labels, long long npix, int C,
                                   float gamma, const float* class_w, int from_logits, float* loss, cudaStream_t st);

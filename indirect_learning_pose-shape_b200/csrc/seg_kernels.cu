@@ -431,13 +431,32 @@ __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsign
   }
 }
 
+// Fused Reshape -> softmax -> categorical focal loss (model.py:119-120, focal_loss.py:10-48) with integer labels: what the
+// LOSS variants of the two kernels exchange per OUTPUT pixel (16 bytes instead of the 128-byte upstream gradient row).
+//   x = al * q_l      al = w_l [gamma (1-p_l)^(gamma-1) log p_l - (1-p_l)^gamma / p_l] where the clip passes, else 0
+//   y = x / Z         Z = sum_c exp(s_c): the gradient w.r.t. score c is  g_loss * (x [c == l] - y exp(s_c))
+//   z = gate * (x [l == 0] - y exp(s_0))   the background channel's share, routed to every part through 1 - clip(sum)
+//   w = the label, as a float
+struct SegLossArgs {
+  const unsigned char* labels;   // [N][wh][wh] class ids in OUTPUT pixel order (rows flipped, like y_true)
+  const float* class_w;          // [32] or null (ones)
+  float gamma;
+  float* loss;                   // [N][wh*wh]
+  float4* aux;                   // [N][wh*wh]
+};
+constexpr float kKerasEps = 1e-7f;          // K.epsilon(), focal_loss.py:15
+__device__ __forceinline__ float pow_gamma(float x, float gamma) { return gamma == 2.0f ? x * x : powf(x, gamma); }
+
 // saved layout: 32 bytes per OUTPUT pixel, [n][wh-1-r][c][32].  byte 0: bit 0 = clip gate.  byte 1+k (part k): 0 none,
 // 1..254 light index + 1, 255 re-query (heavy / generic winner or light index >= 254).
-template <bool TRACK>
-__global__ void __launch_bounds__(256, 3)
+// (The LOSS variant carries twelve more live values through the part loop -- softmax denominators, the label's
+// numerator, the labels -- and spilled them at the 80 registers of four blocks per SM: it is compiled without that cap
+// and runs three 6-warp blocks per SM.)
+template <bool TRACK, bool LOSS>
+__global__ void __launch_bounds__(LOSS ? 288 : 256, LOSS ? 2 : 3)   // LOSS: 112 registers (three 6-warp blocks per SM), 8-warp launches allowed
 seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, int N, int Vs,
                const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh,
-               float* __restrict__ seg, unsigned char* __restrict__ saved) {
+               float* __restrict__ seg, unsigned char* __restrict__ saved, const SegLossArgs la) {
   extern __shared__ __align__(16) unsigned char raw[];
   const SegSmem sm = carve(raw, E, wh);
   const int n = blockIdx.x;
@@ -480,6 +499,17 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     float S[kNB];
 #pragma unroll
     for (int q = 0; q < kNB; ++q) S[q] = 0.f;
+    // LOSS: softmax denominator, exp(score) of the label's channel and the label of each of the lane's pixels
+    float Zs[kNB], el[kNB];
+    int lab[kNB];
+    if (LOSS) {
+#pragma unroll
+      for (int q = 0; q < kNB; ++q) {
+        const int r = r0 + (q >> 1), c = c0 + (q & 1);
+        Zs[q] = 0.f; el[q] = 0.f;
+        lab[q] = (r < wh && c < wh) ? (int)la.labels[(size_t)n * wh * wh + (size_t)(wh - 1 - r) * wh + c] : 0;
+      }
+    }
 
     // channel chunks 1, 2, 3, then chunk 0 last: its channel 0 (background) needs the sum over all parts
     for (int cc = 1; cc <= 4; ++cc) {
@@ -538,14 +568,45 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
             stage[(sub * kNB + q) * 32] = sc[q];
             S[q] += sc[q];
             if (TRACK) cw[half][q] |= barg[q];
+            if (LOSS) {                                              // softmax numerator of this channel (scores are in [0, 1]: no max shift)
+              const float ex = ex2_approx(sc[q] * kLog2e);
+              Zs[q] += ex;
+              el[q] = (lab[q] == ch) ? ex : el[q];
+            }
           }
         }
       }
       if (chunk == 0) {
 #pragma unroll
         for (int q = 0; q < kNB; ++q) {
-          stage[q * 32] = 1.0f - fminf(fmaxf(S[q], 0.f), 1.f);       // :61-64
-          if (TRACK) cw[0][q] |= (S[q] >= 0.f && S[q] <= 1.f) ? 1u : 0u;   // clip gate (inclusive), for the backward
+          const float bg = 1.0f - fminf(fmaxf(S[q], 0.f), 1.f);      // :61-64
+          stage[q * 32] = bg;
+          const bool gate = S[q] >= 0.f && S[q] <= 1.f;              // clip gate (inclusive), for the backward
+          if (TRACK) cw[0][q] |= gate ? 1u : 0u;
+          if (LOSS) {
+            const int r = r0 + (q >> 1), c = c0 + (q & 1);
+            if (r < wh && c < wh) {
+              const float e0 = ex2_approx(bg * kLog2e);
+              const float Z = Zs[q] + e0;
+              const float elq = (lab[q] == 0) ? e0 : el[q];
+              const float invZ = 1.0f / Z;
+              const float ql = elq * invZ;                           // softmax of the label's channel (model.py:120)
+              const float pl = fminf(fmaxf(ql, kKerasEps), 1.0f - kKerasEps);   // focal_loss.py:16
+              const bool inlab = lab[q] < C;
+              const float wl = (la.class_w && inlab) ? la.class_w[lab[q]] : 1.0f;
+              const float om = 1.0f - pl, lg = logf(pl);
+              float al = 0.f;
+              if (inlab && ql >= kKerasEps && ql <= 1.0f - kKerasEps) {          // TF: the clip's gradient passes on the closed interval
+                const float dpow = la.gamma == 2.0f ? 2.0f * om : la.gamma * powf(om, la.gamma - 1.0f);
+                al = wl * (dpow * lg - pow_gamma(om, la.gamma) / pl);
+              }
+              const size_t opx = (size_t)n * wh * wh + (size_t)(wh - 1 - r) * wh + c;
+              la.loss[opx] = inlab ? pow_gamma(om, la.gamma) * ((-lg) * wl) : 0.f;   // focal_loss.py:17, 40, 44-45
+              const float x = al * ql, y = x * invZ;
+              const float z = gate ? x * ((lab[q] == 0) ? 1.0f : 0.f) - y * e0 : 0.f;
+              la.aux[opx] = make_float4(x, y, z, (float)lab[q]);
+            }
+          }
         }
       }
       // one 32-byte sector per pixel; rows flipped (:68)
@@ -589,6 +650,7 @@ constexpr int kIL = 32;            // interleaved light slots per part
 constexpr int kAccRows = kIL + 1;  // accumulator rows per warp: row kIL takes the (discarded) sums of "none" and rare codes
 constexpr unsigned kNoVid = 0xffffu;
 constexpr int kOvPriv = 64;        // private overflow slots per warp; a sample that needs more spills to shared atomics
+constexpr size_t kBwdHeader = 512; // head of the block's shared memory: per-warp scratch of the LOSS variant (8 warps x 64 B)
 
 struct BwdSmem {
   float2* lpos;          // [kAccRows][32]   row kIL = zeros: what "none" and the rare codes read
@@ -605,14 +667,14 @@ struct BwdSmem {
 };
 __host__ __device__ __forceinline__ size_t bwd_smem_bytes(int OV, int nwarps) {
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
-  const size_t need = 256 + (size_t)kAccRows * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + 16 + ov * 8 * 2 + ov * 2 +
+  const size_t need = kBwdHeader + (size_t)kAccRows * 32 * 8 + (size_t)kIL * 32 * 2 + 2 * 32 * 4 + 36 * 4 + 16 + ov * 8 * 2 + ov * 2 +
                       (size_t)nwarps * (kAccRows * 32 + kOvPriv) * 8;
   return need;
 }
 __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* raw, int OV, int nwarps) {
   BwdSmem b;
   const size_t ov = ((size_t)OV + 7) & ~(size_t)7;
-  size_t off = 256;
+  size_t off = kBwdHeader;
   b.lpos = reinterpret_cast<float2*>(raw + off); off += (size_t)kAccRows * 32 * 8;
   b.wacc = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kAccRows * 32 * 8;
   b.wov = reinterpret_cast<float2*>(raw + off); off += (size_t)nwarps * kOvPriv * 8;
@@ -683,9 +745,10 @@ __device__ void classify_light(const BwdSmem& b, const float* __restrict__ proj,
 // rare: the forward's winner at this pixel was a heavy / generic vertex (or a light index that did not fit a byte):
 // exact weighted nearest-vertex re-query of part [p0,p1) straight from global memory, with the forward's rule -- the
 // light minimum over squared distances (lowest index on ties), beaten only by a strictly smaller d*w of another vertex.
+// The upstream gradient of the score is G(s) = ga - gb * exp(s): gb = 0 for a plain g_seg, the fused loss's form otherwise.
 __device__ __noinline__ void slow_pixel_grad_global(const float* __restrict__ proj, const float* __restrict__ mask,
                                                     const int* __restrict__ idx, int p0, int p1, float gx, float gy,
-                                                    float G, float* __restrict__ out) {
+                                                    float ga, float gb, float* __restrict__ out) {
   float best = CUDART_INF_F, xo = CUDART_INF_F;
   int lv = -1, ov = -1;
   for (int e = p0; e < p1; ++e) {
@@ -705,6 +768,7 @@ __device__ __noinline__ void slow_pixel_grad_global(const float* __restrict__ pr
   const float du = __fsub_rn(proj[vid * 3], gx), dv = __fsub_rn(proj[vid * 3 + 1], gy);
   const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
   const float s = expf(-__fmul_rn(d, w));
+  const float G = ga - gb * expf(s);
   const float coef = (d > 0.f) ? (-w * s * G) / d : 0.f;           // d(exp(-d w))/dp = -w s (p - g)/d
   atomicAdd(&out[vid * 3], coef * du);
   atomicAdd(&out[vid * 3 + 1], coef * dv);
@@ -714,12 +778,13 @@ __device__ __noinline__ void slow_pixel_grad_global(const float* __restrict__ pr
 // first kOvPriv overflow slots of a sample are private to (warp, lane = part): plain read-modify-write; beyond that,
 // shared atomics.
 __device__ __forceinline__ void overflow_pixel_grad(const BwdSmem& b, float2* wov_w, int ob, int od, int j, float gx,
-                                                    float gy, float G) {
+                                                    float gy, float ga, float gb) {
   const float2 e = b.opos[ob + j];
   const float du = __fsub_rn(e.x, gx), dv = __fsub_rn(e.y, gy);
   const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
   const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
   const float s = ex2_approx((d2 * rs) * (-kLog2e));
+  const float G = ga - gb * ex2_approx(s * kLog2e);
   const float coef = (s * G) * (-rs);
   if (od + j < kOvPriv) {
     float2 a = wov_w[od + j];
@@ -731,12 +796,17 @@ __device__ __forceinline__ void overflow_pixel_grad(const BwdSmem& b, float2* wo
   }
 }
 
-template <bool C32, bool ALIGNED>
-__global__ void __launch_bounds__(192, 3)
+// LOSS: instead of an upstream gradient row per pixel the kernel reads the forward's 16-byte `aux` record and the
+// upstream gradient of the per-pixel loss (see SegLossArgs): lane (j & 3) of a group loads pixel j's record, the group's
+// values cross lanes by shuffle, and the score's own gradient  g (x [c == l] - y exp(s_c) - z)  is formed from the
+// recomputed score.
+template <bool C32, bool ALIGNED, bool LOSS>
+__global__ void __launch_bounds__(192, LOSS ? 2 : 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
                const int* __restrict__ idx, const int* __restrict__ obase, int P, int OV, int wh,
-               float* __restrict__ g_projects, int pf_ok) {
+               float* __restrict__ g_projects, int pf_ok, const float4* __restrict__ aux,
+               const float* __restrict__ g_loss) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -753,9 +823,10 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   // cp.async.bulk.prefetch needs 16-byte aligned addresses: the rows are multiples of 16 bytes here, and the launcher
   // clears pf_ok when the caller's g_seg / saved base pointers are not (a contiguous autograd view with an odd offset)
   const bool kPrefetch = C32 && ALIGNED && pf_ok;
-  const unsigned char* pf_base = (lane == 0) ? reinterpret_cast<const unsigned char*>(g_seg + (size_t)n * npx * 32)
+  const unsigned char* pf_base = (lane == 0) ? (LOSS ? reinterpret_cast<const unsigned char*>(aux + (size_t)n * npx)
+                                                     : reinterpret_cast<const unsigned char*>(g_seg + (size_t)n * npx * 32))
                                              : saved + (size_t)n * npx * 32;
-  const uint32_t pf_row = (uint32_t)wh * ((lane == 0) ? 128u : 32u);   // bytes per output row
+  const uint32_t pf_row = (uint32_t)wh * ((lane == 0) ? (LOSS ? 16u : 128u) : 32u);   // bytes per output row
   if (kPrefetch && lane < 2 && warp < wh) prefetch_l2_bulk(pf_base + (size_t)warp * pf_row, pf_row);
   const float* proj_n = projects + (size_t)n * Vs * 3;
   const float* mask_n = mask + (size_t)n * Vs;
@@ -787,13 +858,22 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int ob = b.obase[k], od = b.odyn[k];
   float2* wov_w = b.wov + (size_t)warp * kOvPriv;
   const unsigned char* sv = saved + (size_t)n * npx * 32 + lane;
-  const float* g_n = g_seg + (size_t)n * npx * C + (lane < C ? lane : 0);
+  const float* g_n = LOSS ? nullptr : g_seg + (size_t)n * npx * C + (lane < C ? lane : 0);
   const bool ld_g = C32 || lane < C;
+  // LOSS: this lane fetches the record of pixel (lane & 3) of every group; lanes 0..3 publish {x g - z g, -z g, y g, label}
+  // of their pixel in a 64-byte per-warp scratch at the head of the block's shared memory (kBwdHeader), which every lane
+  // then reads as a broadcast: one LDS.128 per pixel instead of five shuffles (32 lanes per clock per SM)
+  const float4* ax_n = LOSS ? aux + (size_t)n * npx + (lane & 3) : nullptr;
+  const float* gl_n = LOSS ? g_loss + (size_t)n * npx + (lane & 3) : nullptr;
+  const float lane_f = (float)lane;
+  float4* scr = reinterpret_cast<float4*>(raw) + (size_t)warp * 4;   // [4] records of the group being computed
 
   // Register loads run one group ahead in two named register sets (no copies), pointers advance linearly.
   const int px0 = ALIGNED ? warp * wh : b0 * 4;                     // first pixel of this warp
   const unsigned char* svp = sv + (size_t)px0 * 32;
-  const float* gp = g_n + (size_t)px0 * C;
+  const float* gp = LOSS ? nullptr : g_n + (size_t)px0 * C;
+  const float4* axp = LOSS ? ax_n + px0 : nullptr;
+  const float* glp = LOSS ? gl_n + px0 : nullptr;
   int px = px0;                                                     // first pixel of the group being COMPUTED (!ALIGNED)
   int pxl = px;                                                     // first pixel of the group being LOADED (!ALIGNED)
   int rL = warp, gL = 0;                                            // ALIGNED: load cursor (output row, group in the row)
@@ -804,16 +884,24 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #pragma unroll
   for (int j = 0; j < 4; ++j) GP[j] = pk2((float)j, (float)(wh - 1 - rC));
   const f32x2 step_in = pk2(4.0f, 0.0f);
-#define SEG_LOAD4(code, g)                                                                                             \
+#define SEG_LOAD4(code, g, ax)                                                                                         \
   do {                                                                                                                 \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
       const bool in = ALIGNED || pxl + j < npx;                                                                        \
       code[j] = in ? (int)svp[j * 32] : 0;                                                                             \
-      g[j] = (in && ld_g) ? gp[j * C] : 0.f;                                                                           \
+      if (!LOSS) g[j] = (in && ld_g) ? gp[j * C] : 0.f;                                                                \
     }                                                                                                                  \
-    svp += 4 * 32; gp += 4 * C; pxl += 4;                                                                              \
+    if (LOSS) {                                                     /* pixel (lane & 3) of the group: record + dL/dloss */ \
+      const bool in = ALIGNED || pxl + (lane & 3) < npx;                                                               \
+      ax = in ? *axp : make_float4(0.f, 0.f, 0.f, 0.f);                                                                \
+      g[0] = in ? *glp : 0.f;                                                                                          \
+      axp += 4; glp += 4;                                                                                              \
+    } else {                                                                                                           \
+      gp += 4 * C;                                                                                                     \
+    }                                                                                                                  \
+    svp += 4 * 32; pxl += 4;                                                                                           \
   } while (0)
-#define SEG_COMPUTE4(code, g)                                                                                          \
+#define SEG_COMPUTE4(code, g, ax)                                                                                      \
   do {                                                                                                                 \
     if (!ALIGNED) {                                                                                                    \
       _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                  \
@@ -822,13 +910,28 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       }                                                                                                                \
     }                                                                                                                  \
     f32x2 c2[4];                                                                                                       \
-    float Gv[4];                                                                                                       \
+    float Gv[4], Gb[4];                                             /* upstream gradient of the score: Gv - Gb exp(s) */ \
     int li[4];                                                                                                         \
     uint32_t row[4];                                                                                                   \
+    if (LOSS) {                                                     /* lanes 0..3 publish their pixel's record */      \
+      __syncwarp();                                                 /* the previous group's reads are done */          \
+      if (lane < 4) {                                                                                                  \
+        const float zg = ax.z * g[0];                                                                                  \
+        scr[lane] = make_float4(fmaf(ax.x, g[0], -zg), -zg, ax.y * g[0], ax.w);                                        \
+      }                                                                                                                \
+      __syncwarp();                                                                                                    \
+    }                                                                                                                  \
     /* (a) four pixels, mutually independent: the arithmetic of the four chains interleaves */                        \
     _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                    \
-      const float t0 = (code[j] & 1) ? g[j] : 0.f;                 /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
-      Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                  \
+      if (LOSS) {                                                                                                      \
+        const float4 rj = scr[j];                                   /* same address on every lane: one broadcast */    \
+        Gb[j] = rj.z;                                                                                                  \
+        Gv[j] = (rj.w == lane_f) ? rj.x : rj.y;                                                                        \
+      } else {                                                                                                         \
+        const float t0 = (code[j] & 1) ? g[j] : 0.f;               /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
+        Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                \
+        Gb[j] = 0.f;                                                                                                   \
+      }                                                                                                                \
       li[j] = code[j] - 1;                                          /* -1 none, >= kIL overflow, 254 re-query */       \
       row[j] = min((unsigned)li[j], (unsigned)kIL) * 256u;          /* "none" and the rare codes: row kIL */           \
       const f32x2 e = lds_b64_nv(lpos_sa + row[j]);                                                                    \
@@ -838,7 +941,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       const float d2 = __fadd_rn(du2, dv2);                                                                            \
       const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));                                                                \
       const float s = ex2_approx((d2 * rs) * (-kLog2e));                                                               \
-      const float coef = (s * Gv[j]) * (-rs);                       /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
+      const float Gj = LOSS ? fmaf(-Gb[j], ex2_approx(s * kLog2e), Gv[j]) : Gv[j];                                     \
+      const float coef = (s * Gj) * (-rs);                          /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
       c2[j] = mul2(pk2(coef, coef), d);                                                                                \
     }                                                                                                                  \
     /* (b) the four read-modify-writes of this lane's private slots (it is their only writer), in order; "none" and  */\
@@ -852,8 +956,8 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
         if (live && li[j] >= kIL) {                                 /* rare: overflow slot, or re-query (code 255) */  \
           float gxj, gyj;                                                                                              \
           upk2(GP[j], gxj, gyj);                                                                                       \
-          if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxj, gyj, Gv[j], out);                 \
-          else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxj, gyj, Gv[j]);                                    \
+          if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxj, gyj, Gv[j], Gb[j], out);          \
+          else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxj, gyj, Gv[j], Gb[j]);                             \
         }                                                                                                              \
       }                                                                                                                \
     }                                                                                                                  \
@@ -878,38 +982,41 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       int r = 0;                                                                                                       \
       if (lane == 0) r = atomicAdd(b.next_row, 1);                                                                     \
       rL = __shfl_sync(0xffffffffu, r, 0);                                                                             \
-      svp = sv + (size_t)rL * wh * 32; gp = g_n + (size_t)rL * wh * C;                                                 \
+      svp = sv + (size_t)rL * wh * 32;                                                                                 \
+      if (LOSS) { axp = ax_n + (size_t)rL * wh; glp = gl_n + (size_t)rL * wh; }                                        \
+      else gp = g_n + (size_t)rL * wh * C;                                                                             \
       if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row); \
     }                                                                                                                  \
   } while (0)
   {
     int codeA[4], codeB[4];
     float gA[4], gB[4];
+    float4 axA = make_float4(0.f, 0.f, 0.f, 0.f), axB = axA;
     if (ALIGNED) {
       if (rL < wh) {
         if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row);
-        SEG_LOAD4(codeA, gA);
+        SEG_LOAD4(codeA, gA, axA);
         for (;;) {
           SEG_ADVANCE_LOAD();
-          if (rL < wh) SEG_LOAD4(codeB, gB);
-          SEG_COMPUTE4(codeA, gA);
+          if (rL < wh) SEG_LOAD4(codeB, gB, axB);
+          SEG_COMPUTE4(codeA, gA, axA);
           if (rC >= wh) break;
           SEG_ADVANCE_LOAD();
-          if (rL < wh) SEG_LOAD4(codeA, gA);
-          SEG_COMPUTE4(codeB, gB);
+          if (rL < wh) SEG_LOAD4(codeA, gA, axA);
+          SEG_COMPUTE4(codeB, gB, axB);
           if (rC >= wh) break;
         }
       }
     } else {
       const int nbw = b1 - b0;
-      if (nbw > 0) SEG_LOAD4(codeA, gA);
+      if (nbw > 0) SEG_LOAD4(codeA, gA, axA);
       for (int i = 0; i < nbw; i += 2) {
         const bool hasB = i + 1 < nbw;
-        if (hasB) SEG_LOAD4(codeB, gB);
-        SEG_COMPUTE4(codeA, gA);
+        if (hasB) SEG_LOAD4(codeB, gB, axB);
+        SEG_COMPUTE4(codeA, gA, axA);
         if (hasB) {
-          if (i + 2 < nbw) SEG_LOAD4(codeA, gA);
-          SEG_COMPUTE4(codeB, gB);
+          if (i + 2 < nbw) SEG_LOAD4(codeA, gA, axA);
+          SEG_COMPUTE4(codeB, gB, axB);
         }
       }
     }
@@ -943,7 +1050,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 constexpr size_t kMaxSmem = 227 * 1024;
 
 cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
-                            float* seg, unsigned char* saved, cudaStream_t st) {
+                            float* seg, unsigned char* saved, const SegLossArgs* la, cudaStream_t st) {
   const SegGeom g = seg_geom(wh);
   int warps = 1;
   for (int w = 8; w >= 1; --w)                 // the largest warp count <= 8 that divides the tile count evenly
@@ -959,17 +1066,17 @@ cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   dim3 grid(N, split);
   LaunchScope scope(KID_SEG_FWD, st);
-  cudaError_t e;
-  if (saved) {
-    e = cudaFuncSetAttribute(seg_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    seg_fwd_kernel<true><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg, saved);
-  } else {
-    e = cudaFuncSetAttribute(seg_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    seg_fwd_kernel<false><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg,
-                                                          nullptr);
-  }
+  const SegLossArgs none{nullptr, nullptr, 0.f, nullptr, nullptr};
+#define SMPL_SEG_FWD(TR, LO)                                                                                           \
+  do {                                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(seg_fwd_kernel<TR, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                    \
+    seg_fwd_kernel<TR, LO><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg,  \
+                                                           saved, la ? *la : none);                                    \
+  } while (0)
+  if (la) { if (saved) SMPL_SEG_FWD(true, true); else SMPL_SEG_FWD(false, true); }
+  else { if (saved) SMPL_SEG_FWD(true, false); else SMPL_SEG_FWD(false, false); }
+#undef SMPL_SEG_FWD
   return cudaGetLastError();
 }
 
@@ -979,11 +1086,19 @@ size_t seg_saved_bytes(int N, int wh) { return (size_t)N * wh * wh * 32; }
 
 cudaError_t launch_seg_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
                            float* seg, unsigned char* saved, cudaStream_t st) {
-  return launch_fwd_impl(p, projects, mask, N, Vs, wh, seg, saved, st);
+  return launch_fwd_impl(p, projects, mask, N, Vs, wh, seg, saved, nullptr, st);
 }
 
-cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
-                           const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st) {
+cudaError_t launch_seg_loss_fwd(const SmplB200Parts* p, const float* projects, const float* mask, int N, int Vs, int wh,
+                                const unsigned char* labels, float gamma, const float* class_w, float* seg, float* loss,
+                                unsigned char* saved, void* aux, cudaStream_t st) {
+  const SegLossArgs la{labels, class_w, gamma, loss, reinterpret_cast<float4*>(aux)};
+  return launch_fwd_impl(p, projects, mask, N, Vs, wh, seg, saved, &la, st);
+}
+
+static cudaError_t launch_bwd_impl(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
+                                   const unsigned char* saved, int N, int Vs, int wh, float* g_projects,
+                                   const void* aux, const float* g_loss, cudaStream_t st) {
   if (Vs >= (int)kNoVid) return cudaErrorInvalidValue;              // vertex ids are kept as 16 bits
   // the largest warp count whose blocks still fit three to an SM; at least 4
   int warps = 6;                     // measured: 4 x 5 warps and 4 x 4 warps per SM are slower than 3 x 6; 7 warps spill
@@ -991,21 +1106,41 @@ cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const 
   const size_t smem = bwd_smem_bytes(p->ovf, warps);
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   LaunchScope scope(KID_SEG_BWD, st);
-#define SMPL_SEG_BWD(C32, AL)                                                                                          \
+#define SMPL_SEG_BWD(C32, AL, LO)                                                                                      \
   do {                                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    seg_bwd_kernel<C32, AL><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx, p->obase, \
-                                                          p->P, p->ovf, wh, g_projects, pf_ok);                        \
+    seg_bwd_kernel<C32, AL, LO><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx,       \
+                                                              p->obase, p->P, p->ovf, wh, g_projects, pf_ok,           \
+                                                              reinterpret_cast<const float4*>(aux), g_loss);           \
   } while (0)
   const bool c32 = p->P == 31, al = wh % 4 == 0 && wh >= 8;
-  const int pf_ok = (reinterpret_cast<uintptr_t>(g_seg) % 16 == 0 && reinterpret_cast<uintptr_t>(saved) % 16 == 0) ? 1 : 0;
-  if (c32 && al) SMPL_SEG_BWD(true, true);
-  else if (c32) SMPL_SEG_BWD(true, false);
-  else if (al) SMPL_SEG_BWD(false, true);
-  else SMPL_SEG_BWD(false, false);
+  const void* row0 = aux ? aux : (const void*)g_seg;
+  const int pf_ok = (reinterpret_cast<uintptr_t>(row0) % 16 == 0 && reinterpret_cast<uintptr_t>(saved) % 16 == 0) ? 1 : 0;
+  if (aux) {
+    if (c32 && al) SMPL_SEG_BWD(true, true, true);
+    else if (c32) SMPL_SEG_BWD(true, false, true);
+    else if (al) SMPL_SEG_BWD(false, true, true);
+    else SMPL_SEG_BWD(false, false, true);
+  } else {
+    if (c32 && al) SMPL_SEG_BWD(true, true, false);
+    else if (c32) SMPL_SEG_BWD(true, false, false);
+    else if (al) SMPL_SEG_BWD(false, true, false);
+    else SMPL_SEG_BWD(false, false, false);
+  }
 #undef SMPL_SEG_BWD
   return cudaGetLastError();
+}
+
+cudaError_t launch_seg_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_seg,
+                           const unsigned char* saved, int N, int Vs, int wh, float* g_projects, cudaStream_t st) {
+  return launch_bwd_impl(p, projects, mask, g_seg, saved, N, Vs, wh, g_projects, nullptr, nullptr, st);
+}
+
+cudaError_t launch_seg_loss_bwd(const SmplB200Parts* p, const float* projects, const float* mask, const float* g_loss,
+                                const unsigned char* saved, const void* aux, int N, int Vs, int wh, float* g_projects,
+                                cudaStream_t st) {
+  return launch_bwd_impl(p, projects, mask, nullptr, saved, N, Vs, wh, g_projects, aux, g_loss, st);
 }
 
 }  // namespace smplb200

@@ -21,7 +21,10 @@
 // lower bounds stay valid for vertices clamped into border cells, so every path returns the exact minimum,
 // bit-identical to the brute-force value.
 // Backward (TF autodiff): d s/d p_i* = -(1/1.2) s (p_i* - g)/d at the first arg-min (ties: measure zero), 0 when d == 0
-// (TF: NaN); upstream is g[...,1] - g[...,0].  The search is repeated (no saved state); sums go to shared memory.
+// (TF: NaN); upstream is g[...,1] - g[...,0].  When the forward was given a `saved` buffer it records the arg-min vertex
+// of every pixel (16 bits, in the output's pixel order) and the backward is a streaming kernel (sil_bwd_saved_kernel:
+// no search; runs of pixels that share their vertex -- the whole background -- are summed across the warp before one
+// shared-memory add).  Without it the search is repeated.
 #include <math_constants.h>
 #include <algorithm>
 #include "common.cuh"
@@ -43,6 +46,7 @@ struct SilSmem {
   unsigned short* cstart;  // [cells + 1]
   int* scratch;            // [cells + 1] counting / cursors while binning; afterwards the survivor lists live here
   float* gacc;             // [Vs][2] (backward only)
+  unsigned short* saved;   // global: [N][wh][wh] arg-min vertex ids in output pixel order (forward only; may be null)
 };
 
 struct Grid {
@@ -295,6 +299,8 @@ __device__ __forceinline__ void eval_list(const SilSmem& sm, const unsigned shor
 }
 
 // one pixel: score, store (forward) or gradient contribution (backward)
+constexpr unsigned short kSilNone = 0xffffu;   // saved arg-min of a pixel with no vertex at all
+
 template <bool BWD>
 __device__ __forceinline__ void finish_pixel(const SilSmem& sm, int n, int wh, int c, int r, bool active, float best,
                                              int barg, const float* __restrict__ g_sil, float* __restrict__ out,
@@ -303,6 +309,8 @@ __device__ __forceinline__ void finish_pixel(const SilSmem& sm, int n, int wh, i
   const float s = expf(__fdiv_rn(-d, 1.2f));             // tf.exp(tf.negative(norm) / 1.2) (:37)
   fwd_val = make_float2(1.0f - s, s);
   cu = 0.f; cv = 0.f; vid = -1;
+  if (!BWD && active && sm.saved)                         // forward: the arg-min vertex, for the search-free backward
+    sm.saved[((size_t)n * wh + (wh - 1 - r)) * wh + c] = barg >= 0 ? sm.vid[barg] : kSilNone;
   if (BWD && active && barg >= 0) {
     const size_t o = (((size_t)n * wh + (wh - 1 - r)) * wh + c) * 2;
     const float2 g = *reinterpret_cast<const float2*>(g_sil + o);
@@ -411,6 +419,7 @@ __device__ __forceinline__ SilSmem carve_sil(unsigned char* raw, int Vs, int cel
   sm.gacc = bwd ? reinterpret_cast<float*>(raw + off) : nullptr; off += bwd ? (size_t)Vs * 8 : 0;
   sm.vid = reinterpret_cast<unsigned short*>(raw + off); off += ((size_t)Vs * 2 + 15) & ~(size_t)15;
   sm.cstart = reinterpret_cast<unsigned short*>(raw + off);
+  sm.saved = nullptr;
   return sm;
 }
 size_t sil_smem_bytes(int Vs, int G, int nwarps, bool bwd) {
@@ -422,10 +431,11 @@ size_t sil_smem_bytes(int Vs, int G, int nwarps, bool bwd) {
 template <bool BWD>
 __global__ void __launch_bounds__(kSilWarps * 32)
 sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, int N, int Vs, int wh, int B, int G,
-           int dense, float* __restrict__ out) {
+           int dense, float* __restrict__ out, unsigned short* __restrict__ saved) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const SilSmem sm = carve_sil(raw, Vs, G * G, nwarps, BWD);
+  SilSmem sm = carve_sil(raw, Vs, G * G, nwarps, BWD);
+  sm.saved = BWD ? nullptr : saved;
   const int n = blockIdx.x;
   Grid gr;
   gr.B = B; gr.G = G; gr.S = (G + kStrip - 1) / kStrip; gr.wh = wh;
@@ -519,6 +529,70 @@ sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, 
   }
 }
 
+// Search-free backward from the forward's saved arg-min map.  One block per (sample, slice of output rows); the sample's
+// (u, v) and the per-vertex sums live in shared memory.  A warp takes 32 consecutive pixels of the output; lanes whose
+// neighbours hold the same vertex form a run (the background is one run per hull vertex), runs are summed by a segmented
+// shuffle reduction and only the run heads touch the accumulators.
+__global__ void __launch_bounds__(512)
+sil_bwd_saved_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil,
+                     const unsigned short* __restrict__ saved, int N, int Vs, int wh, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* pts = reinterpret_cast<float2*>(raw);                    // [Vs]
+  float* gacc = reinterpret_cast<float*>(raw + (size_t)Vs * 8);    // [Vs][2]
+  const int n = blockIdx.x, lane = threadIdx.x & 31;
+  const float* proj = projects + (size_t)n * Vs * 3;
+  for (int i = threadIdx.x; i < Vs; i += blockDim.x) {
+    pts[i] = make_float2(proj[i * 3], proj[i * 3 + 1]);
+    gacc[2 * i] = 0.f; gacc[2 * i + 1] = 0.f;
+  }
+  __syncthreads();
+  const int npx = wh * wh;
+  const int p0 = (int)(((long long)npx * blockIdx.y) / gridDim.y) & ~31;                 // whole warps' worth of pixels
+  const int p1 = (blockIdx.y + 1 == gridDim.y) ? npx : ((int)(((long long)npx * (blockIdx.y + 1)) / gridDim.y) & ~31);
+  const unsigned short* sv = saved + (size_t)n * npx;
+  const float2* g2 = reinterpret_cast<const float2*>(g_sil) + (size_t)n * npx;
+  for (int base = p0 + (threadIdx.x & ~31); base < p1; base += blockDim.x) {
+    const int i = base + lane;
+    const bool in = i < p1;
+    const unsigned vid = in ? sv[i] : kSilNone;
+    float cu = 0.f, cv = 0.f;
+    if (vid != kSilNone) {
+      const float2 g = g2[i];
+      const int ro = i / wh, c = i - ro * wh, r = wh - 1 - ro;     // output row -> grid row (:42)
+      const float2 p = pts[vid];
+      const float du = __fsub_rn(p.x, (float)c), dv = __fsub_rn(p.y, (float)r);
+      const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+      const float s = expf(__fdiv_rn(-d, 1.2f));
+      const float coef = (d > 0.f) ? (-(g.y - g.x) * s / 1.2f) / d : 0.f;
+      cu = coef * du; cv = coef * dv;
+    }
+    // runs of equal vertex ids among consecutive lanes
+    const unsigned prev = __shfl_up_sync(0xffffffffu, vid, 1);
+    const bool head = lane == 0 || prev != vid;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned above = heads & ~((2u << lane) - 1u);           // heads strictly after this lane
+    const int end = above ? (__ffs(above) - 2) : 31;               // last lane of my run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float tu = __shfl_down_sync(0xffffffffu, cu, o), tv = __shfl_down_sync(0xffffffffu, cv, o);
+      if (lane + o <= end) { cu += tu; cv += tv; }
+    }
+    if (head && vid != kSilNone) {
+      atomicAdd(&gacc[2 * vid], cu);
+      atomicAdd(&gacc[2 * vid + 1], cv);
+    }
+  }
+  __syncthreads();
+  float* gp = out + (size_t)n * Vs * 3;
+  for (int i = threadIdx.x; i < Vs * 2; i += blockDim.x) {
+    const int v = i >> 1, k = i & 1;
+    if (gridDim.y == 1) gp[v * 3 + k] = gacc[i];
+    else if (gacc[i] != 0.f) atomicAdd(&gp[v * 3 + k], gacc[i]);
+  }
+  if (gridDim.y == 1)
+    for (int i = threadIdx.x; i < Vs; i += blockDim.x) gp[i * 3 + 2] = 0.f;
+}
+
 void sil_grid(int wh, int& B, int& G) {
   B = 2;
   while ((wh + B - 1) / B > kMaxGrid) B *= 2;
@@ -526,8 +600,26 @@ void sil_grid(int wh, int& B, int& G) {
 }
 
 template <bool BWD>
-cudaError_t launch_sil(const float* projects, const float* g_sil, int N, int Vs, int wh, float* out, cudaStream_t st) {
+cudaError_t launch_sil(const float* projects, const float* g_sil, int N, int Vs, int wh, float* out, unsigned short* saved,
+                       cudaStream_t st) {
   if (Vs >= 65535) return cudaErrorInvalidValue;         // sorted positions and vertex ids are kept as 16 bits
+  if (BWD && saved) {                                    // search-free backward
+    const size_t smem = (size_t)Vs * 16;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(sil_bwd_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // enough blocks to fill the GPU (two per SM fit at 6890 vertices): slices of the image when the batch is small
+    int split = 1;
+    const int npx32 = (wh * wh + 31) / 32;
+    if (N < 2 * 148) split = max(1, min(npx32, (2 * 148 + N - 1) / N));
+    if (split > 1) {
+      e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * Vs * 3, st);
+      if (e != cudaSuccess) return e;
+    }
+    LaunchScope scope(KID_SIL_BWD, st);
+    sil_bwd_saved_kernel<<<dim3(N, split), 512, smem, st>>>(projects, g_sil, saved, N, Vs, wh, out);
+    return cudaGetLastError();
+  }
   int B, G;
   sil_grid(wh, B, G);
   // Survivor lists only pay where pixels outnumber vertices; denser launches use the plain ring search throughout.
@@ -547,19 +639,19 @@ cudaError_t launch_sil(const float* projects, const float* g_sil, int N, int Vs,
   }
   dim3 grid(N, split);
   LaunchScope scope(BWD ? KID_SIL_BWD : KID_SIL_FWD, st);
-  sil_kernel<BWD><<<grid, warps * 32, smem, st>>>(projects, g_sil, N, Vs, wh, B, G, dense, out);
+  sil_kernel<BWD><<<grid, warps * 32, smem, st>>>(projects, g_sil, N, Vs, wh, B, G, dense, out, saved);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, cudaStream_t st) {
-  return launch_sil<false>(projects, nullptr, N, Vs, wh, sil, st);
+cudaError_t launch_sil_fwd(const float* projects, int N, int Vs, int wh, float* sil, unsigned short* saved, cudaStream_t st) {
+  return launch_sil<false>(projects, nullptr, N, Vs, wh, sil, saved, st);
 }
 
 cudaError_t launch_sil_bwd(const float* projects, const float* g_sil, int N, int Vs, int wh, float* g_projects,
-                           cudaStream_t st) {
-  return launch_sil<true>(projects, g_sil, N, Vs, wh, g_projects, st);
+                           const unsigned short* saved, cudaStream_t st) {
+  return launch_sil<true>(projects, g_sil, N, Vs, wh, g_projects, const_cast<unsigned short*>(saved), st);
 }
 
 }  // namespace smplb200

@@ -328,24 +328,32 @@ class _SilFn(torch.autograd.Function):
         lib = _lib.load()
         pwd = _check_cuda_f32(pwd, "projects_with_depth")
         N, Vs = pwd.shape[0], pwd.shape[1]
+        need_grad = bool(ctx.needs_input_grad[0])
         with torch.cuda.device(pwd.device):
             sil = torch.empty((N, img_wh, img_wh, 2), dtype=torch.float32, device=pwd.device)
-            _lib.check(lib.smpl_b200_silhouette_fwd(_ptr(pwd), N, Vs, img_wh, _ptr(sil), None, 0, _stream()),
+            # the backward's state: the arg-min vertex of every pixel (2 bytes), so it never repeats the search
+            saved = _workspace(N * img_wh * img_wh * 2, pwd.device) if need_grad else None
+            _lib.check(lib.smpl_b200_silhouette_fwd(_ptr(pwd), N, Vs, img_wh, _ptr(sil), _ptr(saved),
+                                                    saved.numel() if saved is not None else 0, _stream()),
                        "smpl_b200_silhouette_fwd")
         ctx.img_wh = img_wh
-        ctx.save_for_backward(pwd)
+        ctx.have_state = need_grad
+        if need_grad:
+            ctx.save_for_backward(pwd, saved)
         return sil
 
     @staticmethod
     def backward(ctx, g_sil):
         lib = _lib.load()
-        (pwd,) = ctx.saved_tensors
+        if not ctx.have_state:
+            return None, None
+        pwd, saved = ctx.saved_tensors
         g_sil = _check_cuda_f32(g_sil, "grad silhouette")
         N, Vs = pwd.shape[0], pwd.shape[1]
         with torch.cuda.device(pwd.device):
             g_pwd = torch.empty_like(pwd)
-            _lib.check(lib.smpl_b200_silhouette_bwd(_ptr(pwd), _ptr(g_sil), N, Vs, ctx.img_wh, _ptr(g_pwd), None, 0,
-                                                    _stream()), "smpl_b200_silhouette_bwd")
+            _lib.check(lib.smpl_b200_silhouette_bwd(_ptr(pwd), _ptr(g_sil), N, Vs, ctx.img_wh, _ptr(g_pwd), _ptr(saved),
+                                                    saved.numel(), _stream()), "smpl_b200_silhouette_bwd")
         return g_pwd, None
 
 
@@ -400,6 +408,51 @@ class _FullFn(torch.autograd.Function):
                                               _ptr(mask), _ptr(g_seg), _ptr(state), _ptr(g_params), _ptr(ws), ws.numel(),
                                               _stream()), "smpl_b200_full_bwd")
         return g_params, None, None, None, None, None
+
+
+class _SegLossFn(torch.autograd.Function):
+    """projects_to_seg (projects_to_seg.py:9-69) -> Reshape -> softmax (model.py:119-120) -> categorical focal loss
+    (focal_loss.py:10-48) as ONE kernel each way; integer labels."""
+
+    @staticmethod
+    def forward(ctx, pwd, mask, labels, class_w, table: PartTable, img_wh: int, gamma: float, want_seg: bool):
+        lib = _lib.load()
+        pwd = _check_cuda_f32(pwd, "projects_with_depth")
+        mask = _check_cuda_f32(mask, "mask_vals")
+        N, Vs = pwd.shape[0], pwd.shape[1]
+        if pwd.dim() != 3 or pwd.shape[2] != 3 or tuple(mask.shape) != (N, Vs):
+            raise ValueError("expected projects (N,Vs,3) and mask (N,Vs), got %s and %s" %
+                             (tuple(pwd.shape), tuple(mask.shape)))
+        if labels.dtype != torch.uint8 or labels.numel() != N * img_wh * img_wh or labels.device != pwd.device:
+            raise ValueError("labels must be uint8 class ids of shape (N, img_wh*img_wh) on the projections' device")
+        labels = labels.contiguous()
+        with torch.cuda.device(pwd.device):
+            seg = torch.empty((N, img_wh, img_wh, table.P + 1), dtype=torch.float32, device=pwd.device) if want_seg else None
+            loss = torch.empty((N, img_wh * img_wh), dtype=torch.float32, device=pwd.device)
+            state = _workspace(lib.smpl_b200_seg_loss_state_bytes(N, img_wh), pwd.device)
+            _lib.check(lib.smpl_b200_seg_loss_fwd(table.handle, _ptr(pwd), _ptr(mask), N, Vs, img_wh, _ptr(labels),
+                                                  float(gamma), _ptr(class_w), _ptr(seg), _ptr(loss), _ptr(state),
+                                                  _stream()), "smpl_b200_seg_loss_fwd")
+        ctx.table, ctx.img_wh = table, img_wh
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(pwd, mask, state)
+        if seg is not None:
+            ctx.mark_non_differentiable(seg)       # a by-product here: differentiate through projects_to_seg for its own gradient
+        return loss, seg
+
+    @staticmethod
+    def backward(ctx, g_loss, g_seg):
+        lib = _lib.load()
+        if g_loss is None:
+            return None, None, None, None, None, None, None, None
+        pwd, mask, state = ctx.saved_tensors
+        g_loss = _check_cuda_f32(g_loss, "grad loss")
+        N, Vs = pwd.shape[0], pwd.shape[1]
+        with torch.cuda.device(pwd.device):
+            g_pwd = torch.empty_like(pwd)
+            _lib.check(lib.smpl_b200_seg_loss_bwd(ctx.table.handle, _ptr(pwd), _ptr(mask), _ptr(g_loss), _ptr(state), N, Vs,
+                                                  ctx.img_wh, _ptr(g_pwd), _stream()), "smpl_b200_seg_loss_bwd")
+        return g_pwd, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -615,6 +668,25 @@ def categorical_focal_loss(gamma=2.0, weight_classes=False, from_logits=False):
     return categorical_focal_loss_fixed
 
 
+def projects_to_seg_focal_loss(input, labels, img_wh, vertex_sampling, gamma=2.0, weight_classes=False,
+                               part_indices_path: Optional[str] = None, parts=None, return_seg: bool = False):
+    """The tail of every training graph of the reference as one op: ``projects_to_seg`` (projects_to_seg.py:9-69) ->
+    ``Reshape((img_wh*img_wh, 32))`` -> ``Activation('softmax')`` (model.py:119-120) -> ``categorical_focal_loss(gamma,
+    weight_classes)`` (focal_loss.py:10-48), for integer class ids ``labels`` (N, img_wh*img_wh) [or (N, img_wh, img_wh)]
+    in the order of ``y_true``'s pixels.  Returns the per-pixel loss (N, img_wh*img_wh) like the reference's loss
+    function (and the segmentation, detached, if ``return_seg``).  Equal to
+    ``categorical_focal_loss(gamma, weight_classes, from_logits=True)(labels, projects_to_seg(input, ...))`` without ever
+    writing the (N, wh, wh, 32) scores or reading an upstream gradient of that shape."""
+    projects_with_depth, mask_vals = input
+    table = get_part_table(vertex_sampling, projects_with_depth.shape[1], projects_with_depth.device,
+                           part_indices_path, parts)
+    N = projects_with_depth.shape[0]
+    lab = labels.reshape(N, -1).to(device=projects_with_depth.device, dtype=torch.uint8)
+    cw = torch.as_tensor(focal_class_weights(table.P + 1), device=projects_with_depth.device) if weight_classes else None
+    loss, seg = _SegLossFn.apply(projects_with_depth, mask_vals, lab, cw, table, int(img_wh), float(gamma), bool(return_seg))
+    return (loss, seg) if return_seg else loss
+
+
 def categorical_crossentropy(y_true, y_pred, from_logits=False):
     """The silhouette branch's loss (train_stage2_silhouette.py:226-228, Keras 'categorical_crossentropy' on the
     softmax(2) of the silhouette): -sum_c y_c log clip(p_c, eps, 1-eps) per pixel, i.e. the focal kernel with gamma = 0
@@ -665,6 +737,19 @@ class SmplDecoder(torch.nn.Module):
         if self.silhouette_wh:
             out["silhouette"] = _SilFn.apply(proj, int(self.silhouette_wh))
         return out
+
+    def focal_loss(self, params: torch.Tensor, labels: torch.Tensor, gamma: float = 2.0, weight_classes: bool = False):
+        """The decoder's training objective in one call: params (N,86) -> per-pixel categorical focal loss (N, wh*wh)
+        against integer labels (model.py:108-120 + focal_loss.py), with the segmentation -> softmax -> loss tail fused
+        into the rasteriser (projects_to_seg_focal_loss).  Returns dict(loss, projects, mask, joints)."""
+        dm = self.smpl._model_for(params)
+        vs = _vs(self.vertex_sampling)
+        _, joints, _, proj = _DecodeFn.apply(params, dm, False, 0, vs)
+        self.smpl.J_transformed = joints
+        mask = compute_mask(proj)
+        loss = projects_to_seg_focal_loss([proj, mask], labels, self.img_wh, self.vertex_sampling, gamma, weight_classes,
+                                          self._parts_path, self._parts)
+        return {"loss": loss, "projects": proj, "mask": mask, "joints": joints}
 
 
 class GraphedDecoderStep:

@@ -70,6 +70,13 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     g_sil.view(torch.float32, (n, wh, wh, 2)).normal_()
     binding.check(lib.smpl_b200_silhouette_fwd(proj.ptr, n, Vs, wh, sil.ptr, None, 0, stream), "sil_fwd")
     binding.check(lib.smpl_b200_silhouette_bwd(proj.ptr, g_sil.ptr, n, Vs, wh, g_proj2.ptr, None, 0, stream), "sil_bwd")
+    # the same pair with the arg-min map handed from forward to backward (search-free backward)
+    sil_b, g_proj3 = Guarded(n * wh * wh * 8, dev), Guarded(n * Vs * 12, dev)
+    sil_ws = Guarded(dm.workspace_bytes(binding.OP_SILHOUETTE_FWD, n, wh, 0), dev)
+    assert sil_ws.n >= n * wh * wh * 2
+    binding.check(lib.smpl_b200_silhouette_fwd(proj.ptr, n, Vs, wh, sil_b.ptr, sil_ws.ptr, sil_ws.n, stream), "sil_fwd saved")
+    binding.check(lib.smpl_b200_silhouette_bwd(proj.ptr, g_sil.ptr, n, Vs, wh, g_proj3.ptr, sil_ws.ptr, sil_ws.n, stream),
+                  "sil_bwd saved")
     g_params = Guarded(n * 86 * 4, dev)
     ws_b = Guarded(dm.workspace_bytes(binding.OP_DECODE_BWD, n, 0, vs), dev)
     binding.check(lib.smpl_b200_decode_bwd(dm.handle, params.ptr, n, vposed.ptr, None, None, g_proj.ptr, vs, None,
@@ -112,7 +119,7 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
                         ws_b=ws_b, g_verts=g_verts, g_params2=g_params2, ws_b2=ws_b2, proj_s=proj_s, g_verts_s=g_verts_s,
                         g_params_s=g_params_s, vps=vps, g_params_c=g_params_c, f_verts=f_verts, f_joints=f_joints,
                         f_proj=f_proj, f_mask=f_mask, f_seg=f_seg, f_gp=f_gp, f_state=f_state, ws_ff=ws_ff, ws_fb=ws_fb,
-                        f_seg2=f_seg2, f_proj2=f_proj2, f_mask2=f_mask2).items():
+                        f_seg2=f_seg2, f_proj2=f_proj2, f_mask2=f_mask2, sil_b=sil_b, g_proj3=g_proj3, sil_ws=sil_ws).items():
         assert g.intact(), "guard band damaged around %s" % name
     # and the results are the real thing
     ref = np_oracle.smpl_layer_call(host_model, p_np)
@@ -127,5 +134,8 @@ def test_cabi_guard_bands(pkg, host_model, parts_by_vs, make_params, n, vs, wh):
     assert torch.equal(f32(f_proj, (n, Vs, 3)), f32(proj, (n, Vs, 3))) and torch.equal(f32(f_mask, (n, Vs)), f32(mask, (n, Vs)))
     assert torch.equal(f32(f_seg, (n, wh, wh, 32)), f32(seg, (n, wh, wh, 32)))
     assert torch.equal(f32(f_seg2, (n, wh, wh, 32)), f32(seg, (n, wh, wh, 32)))
+    assert torch.equal(f32(sil_b, (n, wh, wh, 2)), f32(sil, (n, wh, wh, 2)))
+    g3, g2 = f32(g_proj3, (n, Vs, 3)), f32(g_proj2, (n, Vs, 3))
+    assert float((g3 - g2).abs().max()) <= 1e-5 * float(g2.abs().max())      # same terms, summed in another order
     ga, gb = f32(f_gp, (n, 86)), f32(g_params, (n, 86))
     assert float((ga - gb).abs().max()) <= 1e-5 * float(gb.abs().max())     # the seg backward sums rows in on-demand order

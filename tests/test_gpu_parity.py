@@ -633,3 +633,83 @@ def test_seg_narrow_tables_and_odd_sizes(pkg, host_model, parts_by_vs, make_para
     scale = np.abs(ref64).max() + 1e-9
     bad = np.abs(gg - ref64) > 2e-4 * scale
     assert bad.mean() <= 2e-3, (bad.mean(), np.abs(gg - ref64).max(), scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# projects_to_seg -> softmax -> categorical focal loss, fused into the rasteriser (integer labels)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,wh,vs,nparts,weighted,gamma", [(3, 48, 5, 31, True, 2.0), (2, 48, None, 31, False, 2.0),
+                                                            (2, 33, 5, 20, True, 2.0), (2, 20, 2, 31, True, 1.5),
+                                                            (2, 48, 5, 31, False, 0.0)])
+def test_fused_seg_focal_loss(pkg, host_model, parts_by_vs, make_params, n, wh, vs, nparts, weighted, gamma):
+    """loss and d loss / d projections of the fused op against the fp64 torch twin of the reference chain
+    (projects_to_seg.py -> model.py:119-120 softmax -> focal_loss.py) and against the unfused CUDA ops."""
+    parts = parts_by_vs[vs][:nparts]
+    C = nparts + 1
+    p, pr, mask = _oracle_inputs(host_model, make_params, n, wh, vs, seed=97)
+    rng = np.random.default_rng(19)
+    lab = rng.integers(0, C, (n, wh * wh))
+    lab[0, :7] = [0, 0, 1, C - 1, C - 1, 5 % C, 0]
+    wgt = rng.standard_normal((n, wh * wh)).astype(np.float32)
+    # oracle, fp64
+    x64 = torch.tensor(pr, dtype=torch.float64, requires_grad=True)
+    seg64 = torch_oracle.projects_to_seg([x64, torch.tensor(mask, dtype=torch.float64)], wh, vs, parts)
+    y64 = torch.nn.functional.one_hot(torch.tensor(lab), C).double()
+    prob = torch.softmax(seg64.reshape(n, wh * wh, C), -1)
+    pc = torch.clamp(prob, 1e-7, 1 - 1e-7)
+    ce = -y64 * torch.log(pc)
+    if weighted:
+        ce = ce * torch.tensor(np_oracle.focal_class_weights(C, np.float64))
+    ref = (torch.pow(1 - pc, gamma) * ce).sum(-1)
+    (ref * torch.tensor(wgt, dtype=torch.float64)).sum().backward()
+    ref_g = x64.grad.numpy()
+    # fused
+    x = t(pr).requires_grad_(True)
+    labt = torch.as_tensor(lab, device=dev(), dtype=torch.uint8)
+    loss, seg = pkg.projects_to_seg_focal_loss([x, t(mask)], labt, wh, vs, gamma=gamma, weight_classes=weighted, parts=parts,
+                                               return_seg=True)
+    assert tuple(loss.shape) == (n, wh * wh) and tuple(seg.shape) == (n, wh, wh, C)
+    (loss * t(wgt)).sum().backward()
+    got, got_g = loss.detach().cpu().numpy().astype(np.float64), x.grad.cpu().numpy().astype(np.float64)
+    r = ref.detach().numpy()
+    assert np.abs(got - r).max() <= 3e-6 * max(1.0, np.abs(r).max()), np.abs(got - r).max()
+    assert np.all(got_g[..., 2] == 0)
+    scale = np.abs(ref_g).max() + 1e-12
+    bad = np.abs(got_g - ref_g) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(got_g - ref_g).max(), scale)
+    # unfused CUDA chain: same scores, the loss kernel's own softmax
+    x2 = t(pr).requires_grad_(True)
+    seg2 = pkg.projects_to_seg([x2, t(mask)], wh, vs, parts=parts)
+    assert torch.equal(seg2.detach(), seg)
+    loss2 = pkg.categorical_focal_loss(gamma, weighted, from_logits=True)(labt, seg2)
+    (loss2 * t(wgt)).sum().backward()
+    assert float((loss2.detach() - loss.detach()).abs().max()) <= 3e-6 * max(1.0, float(loss2.abs().max()))
+    g2 = x2.grad
+    assert float((g2 - x.grad).abs().max()) <= 2e-5 * float(g2.abs().max())
+
+
+@pytest.mark.gpu
+def test_fused_decoder_focal_loss_gradient(pkg, host_model, parts_by_vs, tconst64, make_params):
+    """End to end d(sum of weighted focal loss)/d(params) of SmplDecoder.focal_loss vs the fp64 torch twin."""
+    n, wh, vs = 3, 48, 5
+    p = make_params(n, wh, seed=87)
+    rng = np.random.default_rng(3)
+    lab = rng.integers(0, 32, (n, wh * wh))
+    x64 = torch.tensor(p, dtype=torch.float64, requires_grad=True)
+    o = torch_oracle.decode(tconst64, x64, wh, vs, parts_by_vs[vs])
+    y64 = torch.nn.functional.one_hot(torch.tensor(lab), 32).double()
+    ref = torch_oracle.softmax_focal_loss(y64, o["seg"].reshape(n, wh * wh, 32), 2.0, True, True)
+    ref.sum().backward()
+    dec = pkg.SmplDecoder(host_model, wh, vs, need_verts=False, parts=parts_by_vs[vs], device=dev())
+    x = t(p).requires_grad_(True)
+    out = dec.focal_loss(x, torch.as_tensor(lab, device=dev(), dtype=torch.uint8), 2.0, True)
+    out["loss"].sum().backward()
+    same = (out["mask"].cpu().numpy() == o["mask"].numpy()).all(axis=1)
+    assert same.any()
+    got, want = x.grad.cpu().numpy().astype(np.float64), x64.grad.numpy()
+    lg, lr = out["loss"].detach().cpu().numpy()[same], ref.detach().numpy()[same]
+    assert np.abs(lg - lr).max() <= 1e-3 * max(1.0, np.abs(lr).max())        # scores move with the 1e-5 geometry noise
+    scale = np.abs(want).max(axis=0, keepdims=True) + 1e-6
+    err = (np.abs(got - want) / scale)[same]
+    assert err.max() <= 2e-2 and np.median(err) <= 1e-4, (err.max(), np.median(err))
