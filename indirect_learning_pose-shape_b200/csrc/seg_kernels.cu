@@ -447,6 +447,32 @@ struct SegLossArgs {
 constexpr float kKerasEps = 1e-7f;          // K.epsilon(), focal_loss.py:15
 __device__ __forceinline__ float pow_gamma(float x, float gamma) { return gamma == 2.0f ? x * x : powf(x, gamma); }
 
+// One pixel's focal loss and backward record from its softmax bookkeeping (Zp = sum of exp(s_k) over the parts, elp =
+// exp(score) of the label's channel if it is a part, bg = the background score).  Out of line: once per pixel, and the
+// rasteriser's instruction footprint is what its issue rate hangs on (inlined four times per lane with logf / powf it
+// grew the kernel from 44 to 72 KB).
+__device__ __noinline__ float4 loss_pixel(float Zp, float elp, float bg, int lab, int C, bool gate,
+                                          const float* __restrict__ class_w, float gamma, float* __restrict__ loss_out) {
+  const float e0 = ex2_approx(bg * kLog2e);
+  const float Z = Zp + e0;
+  const float elq = (lab == 0) ? e0 : elp;
+  const float invZ = 1.0f / Z;
+  const float ql = elq * invZ;                                       // softmax of the label's channel (model.py:120)
+  const float pl = fminf(fmaxf(ql, kKerasEps), 1.0f - kKerasEps);    // focal_loss.py:16
+  const bool inlab = lab < C;
+  const float wl = (class_w && inlab) ? class_w[lab] : 1.0f;
+  const float om = 1.0f - pl, lg = logf(pl);
+  float al = 0.f;
+  if (inlab && ql >= kKerasEps && ql <= 1.0f - kKerasEps) {          // TF: the clip's gradient passes on the closed interval
+    const float dpow = gamma == 2.0f ? 2.0f * om : gamma * powf(om, gamma - 1.0f);
+    al = wl * (dpow * lg - pow_gamma(om, gamma) / pl);
+  }
+  *loss_out = inlab ? pow_gamma(om, gamma) * ((-lg) * wl) : 0.f;     // focal_loss.py:17, 40, 44-45
+  const float x = al * ql, y = x * invZ;
+  const float z = gate ? x * ((lab == 0) ? 1.0f : 0.f) - y * e0 : 0.f;
+  return make_float4(x, y, z, (float)lab);
+}
+
 // saved layout: 32 bytes per OUTPUT pixel, [n][wh-1-r][c][32].  byte 0: bit 0 = clip gate.  byte 1+k (part k): 0 none,
 // 1..254 light index + 1, 255 re-query (heavy / generic winner or light index >= 254).
 // (The LOSS variant carries twelve more live values through the part loop -- softmax denominators, the label's
@@ -586,25 +612,8 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
           if (LOSS) {
             const int r = r0 + (q >> 1), c = c0 + (q & 1);
             if (r < wh && c < wh) {
-              const float e0 = ex2_approx(bg * kLog2e);
-              const float Z = Zs[q] + e0;
-              const float elq = (lab[q] == 0) ? e0 : el[q];
-              const float invZ = 1.0f / Z;
-              const float ql = elq * invZ;                           // softmax of the label's channel (model.py:120)
-              const float pl = fminf(fmaxf(ql, kKerasEps), 1.0f - kKerasEps);   // focal_loss.py:16
-              const bool inlab = lab[q] < C;
-              const float wl = (la.class_w && inlab) ? la.class_w[lab[q]] : 1.0f;
-              const float om = 1.0f - pl, lg = logf(pl);
-              float al = 0.f;
-              if (inlab && ql >= kKerasEps && ql <= 1.0f - kKerasEps) {          // TF: the clip's gradient passes on the closed interval
-                const float dpow = la.gamma == 2.0f ? 2.0f * om : la.gamma * powf(om, la.gamma - 1.0f);
-                al = wl * (dpow * lg - pow_gamma(om, la.gamma) / pl);
-              }
               const size_t opx = (size_t)n * wh * wh + (size_t)(wh - 1 - r) * wh + c;
-              la.loss[opx] = inlab ? pow_gamma(om, la.gamma) * ((-lg) * wl) : 0.f;   // focal_loss.py:17, 40, 44-45
-              const float x = al * ql, y = x * invZ;
-              const float z = gate ? x * ((lab[q] == 0) ? 1.0f : 0.f) - y * e0 : 0.f;
-              la.aux[opx] = make_float4(x, y, z, (float)lab[q]);
+              la.aux[opx] = loss_pixel(Zs[q], el[q], bg, lab[q], C, gate, la.class_w, la.gamma, la.loss + opx);
             }
           }
         }
