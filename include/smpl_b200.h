@@ -217,6 +217,25 @@ int smpl_b200_focal_loss_bwd(const float* seg, const float* y_true, const uint8_
                              long long num_pixels, int num_classes, float gamma, const float* class_weights,
                              int from_logits, float* g_seg, void* stream);
 
+/* ---- the op right before the path: the regression module's Dense layers (model.py:63-105) --------
+ * Keras Dense in fp32: Y (M,out) = act(X (M,in) W (in,out) + bias (out)), act = ReLU (relu != 0) or linear; W is the Keras
+ * kernel as stored (in, out), row-major.  Row strides (ldx, ldy, ...) in floats, so a layer can read and write column
+ * blocks of a wider state row (the IEF state [features | params], model.py:69,83).  The products run as 3xTF32 split GEMMs on
+ * the tensor cores (fp32 accuracy).  Workspace: smpl_b200_dense_workspace_bytes(M, in, out), 256-byte aligned.
+ * bwd (TF autodiff): gZ = gY [Y > 0] (ReLU) ; gX (M,in) = gZ W^T (NULL to skip) ; gW (in,out) = X^T gZ and gb (out) = column
+ * sums of gZ (NULL to skip), ADDED to their previous contents when accumulate != 0 (the IEF loop shares its three layers
+ * across three iterations). */
+size_t smpl_b200_dense_workspace_bytes(int M, int in, int out);
+int smpl_b200_dense_fwd(const float* X, int ldx, const float* W, const float* bias, int M, int in, int out, int relu, float* Y,
+                        int ldy, void* workspace, size_t workspace_bytes, void* stream);
+int smpl_b200_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* gY, int ldg, int M,
+                        int in, int out, int relu, float* gX, int ldgx, float* gW, float* gb, int accumulate, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* out[r][c] = a[r][c] + scale * d[r][c] over a (rows x cols) block with independent row strides; a or d may be NULL
+ * (param_{k+1} = param_k + scaledown * delta_k, model.py:80-82; the column copies that assemble the IEF state). */
+int smpl_b200_axpy_cols(const float* a, int lda, const float* d, int ldd, float scale, int rows, int cols, float* out, int ldo,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

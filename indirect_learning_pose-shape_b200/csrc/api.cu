@@ -29,7 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // ---- built-in profiler: CUDA-event pairs around every launch, on the launching stream ---------------------------
 static const char* const kKernelNames[KID_COUNT] = {
     "pose_fwd", "blend_fwd", "lbs_fwd", "joints_reg", "lbs_bwd_vertex", "lbs_bwd_joint", "blend_bwd", "pose_bwd",
-    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd"};
+    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd", "dense"};
 struct ProfRecord { int kid; cudaEvent_t a, b; };
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mutex;
@@ -691,6 +691,63 @@ int smpl_b200_seg_loss_bwd(const SmplB200Parts* parts, const float* projects, co
     return SMPL_B200_ERR_UNSUPPORTED;
   }
   CHECK_LAUNCH(e);
+  return SMPL_B200_OK;
+}
+
+// ---- the regression module ahead of the decoder: Dense layers (model.py:63-105) -------------------------------------
+static int current_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+size_t smpl_b200_dense_workspace_bytes(int M, int in, int out) {
+  if (M < 0 || in < 1 || out < 1) return 0;
+  size_t a = dense_gemm_ws(M, out, in);        // forward:  [M][in]  x [out][in]^T
+  size_t b = dense_gemm_ws(M, in, out);        // gX:       [M][out] x [in][out]^T
+  size_t c = dense_gemm_ws(in, out, M);        // gW:       [in][M]  x [out][M]^T
+  return std::max(a, std::max(b, c));
+}
+
+static int dense_check(const char* who, const void* X, const void* W, int M, int in, int out, const void* ws, size_t ws_bytes) {
+  if (!X || !W || M < 0 || in < 1 || out < 1) { set_error("%s: null/invalid argument", who); return SMPL_B200_ERR_BAD_ARG; }
+  if (!ws || ws_bytes < smpl_b200_dense_workspace_bytes(M, in, out) || !aligned(ws, 256)) {
+    set_error("%s: workspace too small or not 256-byte aligned (%zu < %zu bytes)", who, ws_bytes,
+              smpl_b200_dense_workspace_bytes(M, in, out));
+    return SMPL_B200_ERR_WORKSPACE;
+  }
+  return 0;
+}
+
+int smpl_b200_dense_fwd(const float* X, int ldx, const float* W, const float* bias, int M, int in, int out, int relu, float* Y,
+                        int ldy, void* workspace, size_t workspace_bytes, void* stream) {
+  if (M == 0) return SMPL_B200_OK;
+  int rc = dense_check("dense_fwd", X, W, M, in, out, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!Y || ldx < in || ldy < out) { set_error("dense_fwd: null output or row stride shorter than the row"); return SMPL_B200_ERR_BAD_ARG; }
+  CHECK_LAUNCH(launch_dense_fwd(X, ldx, W, bias, M, in, out, relu != 0, Y, ldy, workspace, current_sms(), (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* gY, int ldg, int M,
+                        int in, int out, int relu, float* gX, int ldgx, float* gW, float* gb, int accumulate, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (M == 0) return SMPL_B200_OK;
+  int rc = dense_check("dense_bwd", X, W, M, in, out, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!gY || ldg < out || (relu && (!Y || ldy < out)) || (gX && ldgx < in)) {
+    set_error("dense_bwd: null gY / Y (needed for the ReLU gate) or row stride shorter than the row"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  CHECK_LAUNCH(launch_dense_bwd(X, ldx, W, Y, ldy, gY, ldg, M, in, out, relu != 0, gX, ldgx, gW, gb, accumulate != 0, workspace,
+                                current_sms(), (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+int smpl_b200_axpy_cols(const float* a, int lda, const float* d, int ldd, float scale, int rows, int cols, float* out, int ldo,
+                        void* stream) {
+  if (rows == 0 || cols == 0) return SMPL_B200_OK;
+  if (!out || rows < 0 || cols < 0 || (!a && !d)) { set_error("axpy_cols: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
+  CHECK_LAUNCH(launch_axpy_cols(a, lda, d, ldd, scale, rows, cols, out, ldo, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 

@@ -24,7 +24,7 @@ void count_launch();
 enum KernelId {
   KID_POSE_FWD = 0, KID_BLEND_FWD, KID_LBS_FWD, KID_JOINTS_REG, KID_LBS_BWD_VERTEX, KID_LBS_BWD_JOINT, KID_BLEND_BWD,
   KID_POSE_BWD, KID_PROJECT_FWD, KID_PROJECT_BWD, KID_MASK, KID_SEG_FWD, KID_SEG_BWD, KID_SIL_FWD, KID_SIL_BWD,
-  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_COUNT
+  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_DENSE, KID_COUNT
 };
 // RAII scope around one kernel launch: counts it and, while profiling is enabled, brackets it with CUDA events
 // recorded on the launching stream.
@@ -181,6 +181,20 @@ cudaError_t launch_focal_loss_fwd(const float* seg, const float* y_true, const u
 cudaError_t launch_focal_loss_bwd(const float* seg, const float* y_true, const uint8_t* labels, const float* g_loss,
                                   long long npix, int C, float gamma, const float* class_w, int from_logits, float* g_seg,
                                   cudaStream_t st);
+
+// ---- the regression module ahead of the decoder (model.py:63-105): Dense layers as 3xTF32 tcgen05 GEMMs ---------------
+cudaError_t launch_dense_gemm(const float* Ah, const float* Al, const float* Bh, const float* Bl, int ldk, float* D, int ldd,
+                              const float* bias, int M, int Np, int ncols, int K, bool relu, bool accumulate, int num_sms,
+                              cudaStream_t st);
+int dense_np(int n);
+size_t dense_gemm_ws(int M, int N, int K);
+cudaError_t launch_dense_fwd(const float* X, int ldx, const float* W, const float* b, int M, int in, int out, bool relu,
+                             float* Y, int ldy, void* ws, int num_sms, cudaStream_t st);
+cudaError_t launch_dense_bwd(const float* X, int ldx, const float* W, const float* Y, int ldy, const float* gY, int ldg, int M,
+                             int in, int out, bool relu, float* gX, int ldgx, float* gW, float* gb, bool accumulate, void* ws,
+                             int num_sms, cudaStream_t st);
+cudaError_t launch_axpy_cols(const float* a, int lda, const float* d, int ldd, float scale, int rows, int cols, float* out,
+                             int ldo, cudaStream_t st);
 
 // small device helpers
 // Asynchronous request of [p, p + bytes) into L2 (cp.async.bulk.prefetch: no register, no scoreboard; one thread moves a

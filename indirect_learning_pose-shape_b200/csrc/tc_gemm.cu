@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    float* __restrict__ D, int ldd, const float* __restrict__ bias, int M, int kblocks, int tiles_m,
-                   int tiles_n, float out_scale, int ksplit, size_t plane_stride) {
+                   int tiles_n, float out_scale, int ksplit, size_t plane_stride, int ncols, int epi) {
+  // ncols: valid output columns (the last column tile may hang over it); epi: bit 0 = ReLU, bit 1 = accumulate into D,
+  // bit 2 = D rows are 32-byte aligned with whole 8-column groups (vector stores)
   // Work unit = (output tile, K slice s of ksplit): slice s covers K blocks [s kblocks / ksplit, (s+1) kblocks / ksplit)
   // and writes its partial tile to plane s of D (D + s * plane_stride); the consumer adds the planes in fixed order
   // (deterministic, unlike atomics).  ksplit = 1: the plain GEMM.  The backward blend product has only 2 N / 128 output
@@ -289,9 +291,23 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
             o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
           }
-          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + c), "f"(o[0]), "f"(o[1]), "f"(o[2]),
-                       "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
-                       : "memory");
+          const int col0 = n0 + hcol + c;
+          if (epi & 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (col0 + e < ncols) o[e] += drow[c + e];
+          }
+          if (epi & 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+          }
+          if ((epi & 4) && col0 + 8 <= ncols) {
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + c), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                         "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (col0 + e < ncols) drow[c + e] = o[e];
+          }
         }
       }
     }
@@ -533,7 +549,7 @@ cudaError_t make_map(CUtensorMap* map, const void* base, int rows, int cols, int
 template <int BN, bool BIAS, bool F16>
 cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh, const void* Bl, int ldb, float* D,
                         int ldd, const float* bias, int M, int Ntot, int K, float out_scale, int num_sms, cudaStream_t st,
-                        int ksplit = 1, size_t plane_stride = 0) {
+                        int ksplit = 1, size_t plane_stride = 0, int ncols = -1, int epi = 4) {
   cudaError_t e = load_encode();
   if (e != cudaSuccess) return e;
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -549,7 +565,8 @@ cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh,
   const int grid = min(tiles_m * tiles_n * ksplit, num_sms);
   constexpr int kBKe = F16 ? 2 * kBK : kBK;
   split3_gemm_kernel<BN, BIAS, F16><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, (K + kBKe - 1) / kBKe,
-                                                                   tiles_m, tiles_n, out_scale, ksplit, plane_stride);
+                                                                   tiles_m, tiles_n, out_scale, ksplit, plane_stride,
+                                                                   ncols < 0 ? Ntot : ncols, epi);
   return cudaGetLastError();
 }
 
@@ -621,6 +638,25 @@ cudaError_t launch_blend_bwd_tc(const SmplB200Model* m, const VsTables* t, const
   *planes = ks;
   return launch_gemm<kKPad / 2, false, false>(gvp_hi, gvp_lo, (int)gvp_ld, t->Bs_hi, t->Bs_lo, t->Kp, g_X, kKPad, nullptr,
                                               N, kKPad, t->Kp, 1.0f, m->num_sms, st, ks, (size_t)N * kKPad);
+}
+
+// D[M][ncols] (+)= A[M][K] * B[Np][K]^T (+ bias) (ReLU): the regressor's Dense products (model.py:63-105) as 3xTF32
+// tcgen05 GEMMs.  A / B arrive already split (hi + lo, rows of ldk floats, K padded with zeros to a multiple of 4; B padded
+// with zero rows to Np = a multiple of the column tile).  bias: Np floats or null.
+cudaError_t launch_dense_gemm(const float* Ah, const float* Al, const float* Bh, const float* Bl, int ldk, float* D, int ldd,
+                              const float* bias, int M, int Np, int ncols, int K, bool relu, bool accumulate, int num_sms,
+                              cudaStream_t st) {
+  const bool vec = (ldd % 8 == 0) && (reinterpret_cast<uintptr_t>(D) % 32 == 0);
+  const int epi = (relu ? 1 : 0) | (accumulate ? 2 : 0) | (vec ? 4 : 0);
+  if (Np % 128 == 0) {
+    if (bias) return launch_gemm<128, true, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, bias, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+    return launch_gemm<128, false, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, nullptr, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+  }
+  if (Np % 96 == 0) {
+    if (bias) return launch_gemm<96, true, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, bias, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+    return launch_gemm<96, false, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, nullptr, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace smplb200

@@ -204,7 +204,9 @@ class _DecodeFn(torch.autograd.Function):
             # the compact copy of the sampled vertices when the gradient can only arrive through the projection
             keep_full = need_verts or not project_vs
             vp = torch.empty((N, dm.LD), dtype=torch.float32, device=dev) if keep_full else None
-            vps = torch.empty((N, _vps_ld(Vs)), dtype=torch.float32, device=dev) if project_vs else None
+            # (with vertex_sampling = 1 the compact copy would duplicate the full one)
+            vps = (torch.empty((N, _vps_ld(Vs)), dtype=torch.float32, device=dev)
+                   if project_vs and not (keep_full and project_vs == 1) else None)
             ws_bytes = dm.workspace_bytes(_lib.OP_DECODE_FWD, N) + (0 if keep_full else _ru256(N * dm.LD * 4))
             ws = _workspace(ws_bytes, dev)
             _lib.check(lib.smpl_b200_decode_fwd(dm.handle, _ptr(params), N, _ptr(verts), _ptr(joints), _ptr(keyp),

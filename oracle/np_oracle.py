@@ -327,3 +327,35 @@ def categorical_focal_loss(y_true, y_pred, gamma=2.0, weight_classes=False):
         cross_entropy = cross_entropy * focal_class_weights(y_pred.shape[-1], dt)                 # :19-41
     focal = np.power(dt.type(1.0) - y_pred, dt.type(gamma)) * cross_entropy                       # :44
     return focal.sum(axis=2)                                                                      # :45
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the op before the path: the regression module (model.py:63-105)
+# ---------------------------------------------------------------------------------------------------------------
+def dense(x, kernel, bias, activation="linear"):
+    """keras.layers.Dense: K.dot(x, kernel) + bias, then the activation (model.py:66-68, 100-102)."""
+    y = x @ kernel + bias
+    return np.maximum(y, 0) if activation == "relu" else y
+
+
+def ief_regressor(img_features, weights, img_wh, mean_vals, scaledown=0.005, iterations=3):
+    """model.py:63-97.  weights = [(kernel, bias)] x 3 for IEF_layer_1..3, SHARED by the iterations."""
+    state = concat_mean_param(img_features, img_wh, mean_vals)                    # :70-71
+    param = state[:, img_features.shape[1]:]                                      # :72
+    for _ in range(iterations):
+        delta = dense(state, weights[0][0], weights[0][1], "relu")                # :77 / :86 / :95
+        delta = dense(delta, weights[1][0], weights[1][1], "relu")
+        delta = dense(delta, weights[2][0], weights[2][1], "linear")
+        delta = delta * img_features.dtype.type(scaledown)                        # :80
+        param = param + delta                                                     # :81
+        state = np.concatenate([img_features, param], axis=1)                     # :82
+    return param
+
+
+def plain_regressor(img_features, weights, img_wh, mean_vals, scaledown=0.005):
+    """model.py:99-105."""
+    smpl = dense(img_features, weights[0][0], weights[0][1], "relu")
+    smpl = dense(smpl, weights[1][0], weights[1][1], "relu")
+    smpl = dense(smpl, weights[2][0], weights[2][1], "linear")
+    smpl = smpl * img_features.dtype.type(scaledown)
+    return load_mean_set_cam_params(smpl, img_wh, mean_vals)
