@@ -786,6 +786,7 @@ __device__ __noinline__ void slow_pixel_grad_global(const float* __restrict__ pr
 // rare: light winner beyond the interleaved slots (a part with more than kIL visible vertices).  j = li - kIL.  The
 // first kOvPriv overflow slots of a sample are private to (warp, lane = part): plain read-modify-write; beyond that,
 // shared atomics.
+template <bool LOSS>
 __device__ __forceinline__ void overflow_pixel_grad(const BwdSmem& b, float2* wov_w, int ob, int od, int j, float gx,
                                                     float gy, float ga, float gb) {
   const float2 e = b.opos[ob + j];
@@ -793,7 +794,7 @@ __device__ __forceinline__ void overflow_pixel_grad(const BwdSmem& b, float2* wo
   const float d2 = __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
   const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));
   const float s = ex2_approx((d2 * rs) * (-kLog2e));
-  const float G = ga - gb * ex2_approx(s * kLog2e);
+  const float G = LOSS ? ga - gb * ex2_approx(s * kLog2e) : ga;
   const float coef = (s * G) * (-rs);
   if (od + j < kOvPriv) {
     float2 a = wov_w[od + j];
@@ -919,7 +920,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       }                                                                                                                \
     }                                                                                                                  \
     f32x2 c2[4];                                                                                                       \
-    float Gv[4], Gb[4];                                             /* upstream gradient of the score: Gv - Gb exp(s) */ \
+    float Gv[4], Gb[LOSS ? 4 : 1];                                  /* upstream gradient of the score: Gv - Gb exp(s) */ \
     int li[4];                                                                                                         \
     uint32_t row[4];                                                                                                   \
     if (LOSS) {                                                     /* lanes 0..3 publish their pixel's record */      \
@@ -939,7 +940,6 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       } else {                                                                                                         \
         const float t0 = (code[j] & 1) ? g[j] : 0.f;               /* lane 0: gate * g_bg   (d bg / d s_k = -gate) */  \
         Gv[j] = g[j] - __shfl_sync(0xffffffffu, t0, 0);                                                                \
-        Gb[j] = 0.f;                                                                                                   \
       }                                                                                                                \
       li[j] = code[j] - 1;                                          /* -1 none, >= kIL overflow, 254 re-query */       \
       row[j] = min((unsigned)li[j], (unsigned)kIL) * 256u;          /* "none" and the rare codes: row kIL */           \
@@ -950,7 +950,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       const float d2 = __fadd_rn(du2, dv2);                                                                            \
       const float rs = rsqrt_approx(fmaxf(d2, 1e-30f));                                                                \
       const float s = ex2_approx((d2 * rs) * (-kLog2e));                                                               \
-      const float Gj = LOSS ? fmaf(-Gb[j], ex2_approx(s * kLog2e), Gv[j]) : Gv[j];                                     \
+      const float Gj = LOSS ? fmaf(-Gb[LOSS ? j : 0], ex2_approx(s * kLog2e), Gv[j]) : Gv[j];                          \
       const float coef = (s * Gj) * (-rs);                          /* -s (p - g)/d ; d == 0 -> du = dv = 0 -> 0 */    \
       c2[j] = mul2(pk2(coef, coef), d);                                                                                \
     }                                                                                                                  \
@@ -965,8 +965,9 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
         if (live && li[j] >= kIL) {                                 /* rare: overflow slot, or re-query (code 255) */  \
           float gxj, gyj;                                                                                              \
           upk2(GP[j], gxj, gyj);                                                                                       \
-          if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxj, gyj, Gv[j], Gb[j], out);          \
-          else overflow_pixel_grad(b, wov_w, ob, od, li[j] - kIL, gxj, gyj, Gv[j], Gb[j]);                             \
+          const float gbj = LOSS ? Gb[LOSS ? j : 0] : 0.f;                                                             \
+          if (li[j] == 254) slow_pixel_grad_global(proj_n, mask_n, idx, p0, p1, gxj, gyj, Gv[j], gbj, out);            \
+          else overflow_pixel_grad<LOSS>(b, wov_w, ob, od, li[j] - kIL, gxj, gyj, Gv[j], gbj);                         \
         }                                                                                                              \
       }                                                                                                                \
     }                                                                                                                  \

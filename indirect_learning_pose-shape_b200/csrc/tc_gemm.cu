@@ -144,7 +144,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16) {
 
 // F16: operands are fp16 hi/lo pairs (64 per 128-byte K block, UMMA K = 16); the accumulated sum is multiplied by
 // out_scale (the inverse of the operands' power-of-two scales) before the bias.
-template <int BN, bool BIAS, bool F16>
+template <int BN, bool BIAS, bool F16, bool DENSE>   // DENSE: the general epilogue of the regressor's layers (ncols / epi)
 __global__ void __launch_bounds__(kThreads, 1)
 split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -292,15 +292,15 @@ split3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
           }
           const int col0 = n0 + hcol + c;
-          if (epi & 2) {
+          if (DENSE && (epi & 2)) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) if (col0 + e < ncols) o[e] += drow[c + e];
           }
-          if (epi & 1) {
+          if (DENSE && (epi & 1)) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
           }
-          if ((epi & 4) && col0 + 8 <= ncols) {
+          if (!DENSE || ((epi & 4) && col0 + 8 <= ncols)) {
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + c), "f"(o[0]), "f"(o[1]), "f"(o[2]),
                          "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
                          : "memory");
@@ -546,7 +546,7 @@ cudaError_t make_map(CUtensorMap* map, const void* base, int rows, int cols, int
   return cudaSuccess;
 }
 
-template <int BN, bool BIAS, bool F16>
+template <int BN, bool BIAS, bool F16, bool DENSE = false>
 cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh, const void* Bl, int ldb, float* D,
                         int ldd, const float* bias, int M, int Ntot, int K, float out_scale, int num_sms, cudaStream_t st,
                         int ksplit = 1, size_t plane_stride = 0, int ncols = -1, int epi = 4) {
@@ -559,12 +559,12 @@ cudaError_t launch_gemm(const void* Ah, const void* Al, int lda, const void* Bh,
   if ((e = make_map(&mBl, Bl, Ntot, K, ldb, BN, F16)) != cudaSuccess) return e;
   constexpr int kStageBytes = 2 * kBM * kBK * 4 + 2 * BN * kBK * 4;
   const size_t smem = (size_t)kStages * kStageBytes + 256 + 1024;
-  e = cudaFuncSetAttribute(split3_gemm_kernel<BN, BIAS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(split3_gemm_kernel<BN, BIAS, F16, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = Ntot / BN;
   const int grid = min(tiles_m * tiles_n * ksplit, num_sms);
   constexpr int kBKe = F16 ? 2 * kBK : kBK;
-  split3_gemm_kernel<BN, BIAS, F16><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, (K + kBKe - 1) / kBKe,
+  split3_gemm_kernel<BN, BIAS, F16, DENSE><<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, D, ldd, bias, M, (K + kBKe - 1) / kBKe,
                                                                    tiles_m, tiles_n, out_scale, ksplit, plane_stride,
                                                                    ncols < 0 ? Ntot : ncols, epi);
   return cudaGetLastError();
@@ -649,12 +649,12 @@ cudaError_t launch_dense_gemm(const float* Ah, const float* Al, const float* Bh,
   const bool vec = (ldd % 8 == 0) && (reinterpret_cast<uintptr_t>(D) % 32 == 0);
   const int epi = (relu ? 1 : 0) | (accumulate ? 2 : 0) | (vec ? 4 : 0);
   if (Np % 128 == 0) {
-    if (bias) return launch_gemm<128, true, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, bias, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
-    return launch_gemm<128, false, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, nullptr, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+    if (bias) return launch_gemm<128, true, false, true>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, bias, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+    return launch_gemm<128, false, false, true>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, nullptr, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
   }
   if (Np % 96 == 0) {
-    if (bias) return launch_gemm<96, true, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, bias, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
-    return launch_gemm<96, false, false>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, nullptr, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+    if (bias) return launch_gemm<96, true, false, true>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, bias, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
+    return launch_gemm<96, false, false, true>(Ah, Al, ldk, Bh, Bl, ldk, D, ldd, nullptr, M, Np, K, 1.0f, num_sms, st, 1, 0, ncols, epi);
   }
   return cudaErrorInvalidValue;
 }
