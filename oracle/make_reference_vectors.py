@@ -14,6 +14,7 @@ Run from the repository root IN THE BUILD CONTAINER (the GPU box has no /root/re
 Cases (model = smpl_io.make_synthetic_smpl(seed=0) written as an HMR-layout pickle and loaded by SMPLLayer.build itself):
   c5   N=2  wh=48 vertex_sampling=5   SMPLLayer -> orthographic_project -> compute_mask -> projects_to_seg, with
             d(sum(seg*G))/d(params) by autograd through the reference's code, and softmax -> categorical_focal_loss
+  v2   N=1  wh=64 vertex_sampling=2 (2_sampled_part_vertices.pkl), the same chain with its gradient
   c1   N=1  wh=48 vertex_sampling=None, params = load_mean_set_cam_params(zeros) (the shipped mean params; config C1)
   sil  N=1  wh=48 projects_to_silhouette on the c1 projections (the reference hard-codes 6890 vertices) + gradient
   a1   concat_mean_param / set_cam_params / load_mean_set_cam_params outputs at wh = 48 and 64
@@ -100,6 +101,14 @@ def main():
     loss.t.sum().backward()
     out["c5_labels"] = labels.numpy().astype(np.uint8)
     out["c5_focal1_g_params"] = x.grad.numpy().copy()
+
+    # ---- v2: the third part table, another resolution ----------------------------------------------------------------
+    p2 = synth.make_params(1, 64, seed=2025)
+    x2, _, _, _, seg2 = run_decoder(p2, 64, 2, "v2", True)
+    G2 = torch.randn(seg2.t.shape, generator=torch.Generator().manual_seed(10))
+    (seg2.t * G2).sum().backward()
+    out["v2_G"] = G2.numpy()
+    out["v2_g_params"] = x2.grad.numpy().copy()
 
     # ---- a1 + c1 -----------------------------------------------------------------------------------------------
     for w in (48, 64):

@@ -46,14 +46,14 @@ def test_a1_mean_and_camera_params_on_cuda(pkg, ref):
 
 
 @pytest.mark.parametrize("pad_to", [0, 128])
-@pytest.mark.parametrize("tag,vs", [("c5", 5), ("c1", None)])
-def test_forward_against_reference_source(pkg, host_model, parts_by_vs, make_params, ref, tag, vs, pad_to):
+@pytest.mark.parametrize("tag,vs,wh", [("c5", 5, 48), ("c1", None, 48), ("v2", 2, 64)])
+def test_forward_against_reference_source(pkg, host_model, parts_by_vs, make_params, ref, tag, vs, wh, pad_to):
     """pad_to = 128 embeds the reference samples in a dense batch so the tcgen05 blend path is the one compared."""
     p = ref[tag + "_params"]
     n = p.shape[0]
     if pad_to:
-        p = np.concatenate([p, make_params(pad_to - n, 48, seed=77)], 0)
-    dec = pkg.SmplDecoder(host_model, 48, vs, parts=parts_by_vs[vs], device=dev())
+        p = np.concatenate([p, make_params(pad_to - n, wh, seed=77)], 0)
+    dec = pkg.SmplDecoder(host_model, wh, vs, parts=parts_by_vs[vs], device=dev())
     out = dec(t(p))
     g = lambda k: out[k][:n].cpu().numpy()      # noqa: E731
     assert np.abs(g("verts") - ref[tag + "_verts"]).max() <= 1e-5
@@ -67,19 +67,20 @@ def test_forward_against_reference_source(pkg, host_model, parts_by_vs, make_par
     # rasterisers on the reference's own projections / mask: identical inputs
     pr, mk = t(ref[tag + "_projects"]), t(ref[tag + "_mask"])
     assert np.array_equal(pkg.compute_mask(pr).cpu().numpy(), ref[tag + "_mask"])
-    seg = pkg.projects_to_seg([pr, mk], 48, vs, parts=parts_by_vs[vs]).cpu().numpy()
+    seg = pkg.projects_to_seg([pr, mk], wh, vs, parts=parts_by_vs[vs]).cpu().numpy()
     assert np.abs(seg - ref[tag + "_seg"]).max() <= 2e-6
     assert (seg.argmax(-1) != ref[tag + "_seg"].argmax(-1)).mean() <= 1e-3
 
 
-def test_gradient_against_reference_autograd(pkg, host_model, parts_by_vs, ref):
+@pytest.mark.parametrize("tag,vs,wh", [("c5", 5, 48), ("v2", 2, 64)])
+def test_gradient_against_reference_autograd(pkg, host_model, parts_by_vs, ref, tag, vs, wh):
     """d sum(seg * G) / d params from the hand-written backward kernels vs torch autograd through the reference's code."""
-    dec = pkg.SmplDecoder(host_model, 48, 5, need_verts=False, parts=parts_by_vs[5], device=dev())
-    x = t(ref["c5_params"]).requires_grad_(True)
+    dec = pkg.SmplDecoder(host_model, wh, vs, need_verts=False, parts=parts_by_vs[vs], device=dev())
+    x = t(ref[tag + "_params"]).requires_grad_(True)
     out = dec(x)
-    (out["seg"] * t(ref["c5_G"])).sum().backward()
-    got, want = x.grad.cpu().numpy().astype(np.float64), ref["c5_g_params"].astype(np.float64)
-    same = (out["mask"].cpu().numpy() == ref["c5_mask"]).all(axis=1)
+    (out["seg"] * t(ref[tag + "_G"])).sum().backward()
+    got, want = x.grad.cpu().numpy().astype(np.float64), ref[tag + "_g_params"].astype(np.float64)
+    same = (out["mask"].cpu().numpy() == ref[tag + "_mask"]).all(axis=1)
     assert same.any()
     scale = np.abs(want).max(axis=0, keepdims=True) + 1e-6
     err = (np.abs(got - want) / scale)[same]

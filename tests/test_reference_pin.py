@@ -29,10 +29,10 @@ def ref():
     return np.load(GOLDEN)
 
 
-@pytest.mark.parametrize("tag,vs", [("c5", 5), ("c1", None)])
-def test_oracle_forward_matches_reference_source(ref, host_model, parts_by_vs, tag, vs):
+@pytest.mark.parametrize("tag,vs,wh", [("c5", 5, 48), ("c1", None, 48), ("v2", 2, 64)])
+def test_oracle_forward_matches_reference_source(ref, host_model, parts_by_vs, tag, vs, wh):
     p = ref[tag + "_params"]
-    o = np_oracle.decode(host_model, p, 48, vs, parts_by_vs[vs])
+    o = np_oracle.decode(host_model, p, wh, vs, parts_by_vs[vs])
     # geometry: same op order, different BLAS summation order only
     assert np.abs(o["verts"] - ref[tag + "_verts"]).max() <= 1e-6
     assert np.abs(o["J_transformed"] - ref[tag + "_J_transformed"]).max() <= 1e-6
@@ -43,7 +43,7 @@ def test_oracle_forward_matches_reference_source(ref, host_model, parts_by_vs, t
     # rasterisers on the reference's own projections and mask: rounding of exp/sqrt only
     assert np.array_equal(np_oracle.compute_mask(ref[tag + "_projects"]), ref[tag + "_mask"])
     assert np.array_equal(np_oracle.compute_mask(ref[tag + "_projects"], fast=False), ref[tag + "_mask"])
-    seg = np_oracle.projects_to_seg([ref[tag + "_projects"], ref[tag + "_mask"]], 48, vs, parts_by_vs[vs])
+    seg = np_oracle.projects_to_seg([ref[tag + "_projects"], ref[tag + "_mask"]], wh, vs, parts_by_vs[vs])
     assert np.abs(seg - ref[tag + "_seg"]).max() <= 5e-7
     assert np.abs(o["seg"] - ref[tag + "_seg"]).max() <= 2e-5                   # |ds| <= |dd| ~ projections' 1e-5
 
@@ -75,13 +75,14 @@ def test_silhouette_matches_reference_source(ref):
     assert bad.mean() <= 1e-3, (bad.mean(), np.abs(g - r).max())
 
 
-def test_oracle_gradient_matches_reference_autograd(ref, host_model, parts_by_vs):
+@pytest.mark.parametrize("tag,vs,wh", [("c5", 5, 48), ("v2", 2, 64)])
+def test_oracle_gradient_matches_reference_autograd(ref, host_model, parts_by_vs, tag, vs, wh):
     """d sum(seg * G) / d params: torch autograd through the reference's own statements vs the oracle's torch twin."""
     C = torch_oracle.TorchSmplConstants(host_model, torch.float32)
-    x = torch.tensor(ref["c5_params"], requires_grad=True)
-    o = torch_oracle.decode(C, x, 48, 5, parts_by_vs[5])
-    (o["seg"] * torch.tensor(ref["c5_G"])).sum().backward()
-    got, want = x.grad.numpy().astype(np.float64), ref["c5_g_params"].astype(np.float64)
+    x = torch.tensor(ref[tag + "_params"], requires_grad=True)
+    o = torch_oracle.decode(C, x, wh, vs, parts_by_vs[vs])
+    (o["seg"] * torch.tensor(ref[tag + "_G"])).sum().backward()
+    got, want = x.grad.numpy().astype(np.float64), ref[tag + "_g_params"].astype(np.float64)
     scale = np.abs(want).max(axis=0, keepdims=True) + 1e-6
     err = np.abs(got - want) / scale
     assert np.median(err) <= 1e-4 and err.max() <= 2e-2, (np.median(err), err.max())
