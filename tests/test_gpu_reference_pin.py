@@ -59,7 +59,9 @@ def test_forward_against_reference_source(pkg, host_model, parts_by_vs, make_par
     assert np.abs(g("verts") - ref[tag + "_verts"]).max() <= 1e-5
     assert np.abs(g("joints") - ref[tag + "_J_transformed"]).max() <= 1e-5
     dp = np.abs(g("projects") - ref[tag + "_projects"]).max()
-    assert dp <= 1.5e-5, dp          # 1e-5 + the reference-run's own fp32 rounding (|u| ~ 24..48, ulp 3.8e-6)
+    # 1e-5 + the reference-run's own fp32 rounding: two units in the last place of the largest pixel coordinate
+    # (3.8e-6 below 64 px, 7.6e-6 from 64 px on)
+    assert dp <= 1e-5 + 2.0 * float(np.spacing(np.float32(np.abs(ref[tag + "_projects"][..., :2]).max()))), dp
     mism = (g("mask") != ref[tag + "_mask"]).mean()
     assert mism <= 2e-3, mism        # a vertex within 1e-5 of a .5 pixel boundary may round the other way
     lab = (g("seg").argmax(-1) != ref[tag + "_seg"].argmax(-1)).mean()
