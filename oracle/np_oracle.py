@@ -1,4 +1,4 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED.**
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned to the reference's own source (see below); TensorFlow itself cannot run here.
 
 NumPy restatement of the reference's keras_smpl decoder path, statement by statement, evaluated the
 way the reference evaluates it (dense matmuls, brute-force O(wh^2 * V) rasterisers, O(4096 * V) mask).
@@ -7,15 +7,19 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 module; the product (indirect_learning_pose-shape_b200/) never does and fails loudly without its CUDA
 library.
 
-Why "parity unpinned": the reference is python-2.7 / Keras 2.1 / TensorFlow 1.x code (README.md:20-28)
-with no tests, golden vectors or recorded outputs; TensorFlow, Keras, h5py, deepdish, chumpy and python2
-are absent from this image and the SMPL model file it needs (neutral_smpl_with_cocoplus_reg.pkl) is not
-shipped (/root/reference/.MISSING_LARGE_BLOBS).  The arithmetic lives in the third-party TensorFlow
-runtime (unpinned, ">= 1.6"); this file restates the published semantics of the TF ops at the reference's
-own call sites.  It is validated by (i) an fp64 twin of itself, (ii) finite differences of the torch twin
-(oracle/torch_oracle.py), (iii) closed-form properties (zero pose => verts == v_shaped, pure root rotation,
-translation equivariance of the rasterisers), and (iv) the committed vectors in tests/golden/, which were
-produced by THIS oracle (not by the reference) and only guard against drift.
+How it is pinned: the reference is python-2.7 / Keras 2.1 / TensorFlow 1.x code (README.md:20-28) with no
+tests, golden vectors or recorded outputs; TensorFlow, Keras, h5py, deepdish, chumpy and python2 are absent
+from this image and the SMPL model file it needs (neutral_smpl_with_cocoplus_reg.pkl) is not shipped
+(/root/reference/.MISSING_LARGE_BLOBS).  oracle/make_reference_vectors.py therefore imports the reference's
+OWN, UNMODIFIED keras_smpl/*.py and focal_loss.py with `tensorflow` / `keras` / `deepdish` / `cPickle` resolved to
+the torch-CPU stand-ins of oracle/tf_shim/ (the ~70 TF/Keras symbols those files call, with TF's documented
+semantics), runs them on seeded inputs and commits the results as tests/golden/reference_vectors.npz;
+tests/test_reference_pin.py holds this restatement (and oracle/torch_oracle.py's gradients) to those vectors
+(masks and labels identical, vertices 3e-7, scores 2.4e-7, initialisation functions bit-exact).  Not pinned, because
+nothing here can run it: the floating-point rounding inside TensorFlow's own kernels (matmul summation order, exp).
+It is additionally validated by (i) an fp64 twin of itself, (ii) finite differences of the torch twin,
+(iii) closed-form properties, (iv) independent scipy implementations (tests/test_oracle_independent.py) and
+(v) the drift guard tests/golden/oracle_vectors.npz.
 
 All file:line citations are relative to /root/reference.
 """

@@ -1,4 +1,5 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED** (see oracle/np_oracle.py header).
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Gradients pinned to torch autograd through the reference's own source
+(tests/test_reference_pin.py; see oracle/np_oracle.py header).
 
 torch-CPU autograd twin of oracle/np_oracle.py: the same statements written with torch ops so that
 ``torch.autograd`` reproduces the gradient semantics TensorFlow's autodiff gives the reference
