@@ -6,10 +6,10 @@
 //   out[n, wh-1-r, c, :] = [bg, s_0 .. s_30]          :66-68   (rows flipped)
 //
 // exp, sqrt and the multiply by w are monotone, so  max_i exp(-(d_i w_i)) = exp(-min_i (d_i w_i)): both directions are
-// an exact weighted-nearest-vertex query: the arg-min over fp32 squared distances, computed in the hot loop as
-// fma(du, du, fl(dv^2)) on packed pairs -- one rounding fewer than tf.norm's fl(fl(du^2)+fl(dv^2)), so within one ulp of
-// it; the rare paths (heavy / generic vertices, classification) use the two-rounding form.  Vertices are split by weight
-// once per sample:
+// an exact weighted-nearest-vertex query: the arg-min over fp32 squared distances, computed everywhere with tf.norm's own
+// roundings, fl(fl(du^2) + fl(dv^2)) (round 1's hot loop used fma(du, du, fl(dv^2)), one rounding fewer; round 2 measured
+// both forms -- tools/q13_ab.py: 2.770 vs 2.773 ms, identical label and score agreement with the oracle -- and kept the
+// reference's).  Vertices are split by weight once per sample:
 //   light    w == 1        one per occupied z-buffer cell after compute_mask; min over SQUARED distances in the hot loop
 //   heavy    w >= 256      d*w > 128 unless d < 0.5, and exp(-128) is exactly 0 in fp32, so a heavy vertex can only
 //                           reach the one pixel it rounds to: chained per pixel, visited by that pixel alone
@@ -357,20 +357,15 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
 // Squared distances of one vertex to a lane's 2 x 2 pixel block, GX = (gx0, gx1), GY = (gy0, gy1):
-// d2[q] = fma(du, du, fl(dv^2)), five packed instructions for the four pixels.
+// d2[q] = fl(fl(du^2) + fl(dv^2)), six packed instructions for the four pixels.
 __device__ __forceinline__ void block_d2(float2 e, f32x2 GX, f32x2 GY, float (&d2)[kNB]) {
   const f32x2 dx = sub2(pk2(e.x, e.x), GX), dy = sub2(pk2(e.y, e.y), GY);
   float vy0, vy1;
   upk2(mul2(dy, dy), vy0, vy1);
-  upk2(fma2(dx, dx, pk2(vy0, vy0)), d2[0], d2[1]);
-  upk2(fma2(dx, dx, pk2(vy1, vy1)), d2[2], d2[3]);
+  const f32x2 dx2 = mul2(dx, dx);                                  // fl(du^2), then fl(. + fl(dv^2)): tf.norm's own roundings
+  upk2(add2(dx2, pk2(vy0, vy0)), d2[0], d2[1]);
+  upk2(add2(dx2, pk2(vy1, vy1)), d2[2], d2[3]);
 }
 
 // One survivor against a lane's 2 x 2 pixel block: best[q] = min squared distance, barg[q] = code of its arg-min,

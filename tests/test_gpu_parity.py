@@ -536,6 +536,32 @@ def test_seg_backward_misaligned_upstream_gradient(pkg, host_model, parts_by_vs,
     assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * scale
 
 
+def test_rasteriser_only_harness_of_profiling_renderer(pkg, parts_by_vs):
+    """profiling_renderer.py:28-50: compute_mask + projects_to_seg(img_wh=48, vertex_sampling=5) fed a random
+    (1, 6890, 3) * 80 tensor -- 6890 "sampled" vertices although the vs=5 table only addresses the first 1378 (SURVEY
+    quirk Q10), most of them outside the 48x48 image and many outside the 64x64 mask grid."""
+    rng = np.random.default_rng(2718)
+    pr = (rng.random((1, 6890, 3)) * 80).astype(np.float32)
+    ref_mask = np_oracle.compute_mask(pr)
+    ref = np_oracle.projects_to_seg([pr, ref_mask], 48, 5, parts_by_vs[5])
+    x = t(pr).requires_grad_(True)
+    mask = pkg.compute_mask(x)
+    assert np.array_equal(mask.cpu().numpy(), ref_mask)
+    seg = pkg.projects_to_seg([x, mask], 48, 5, parts=parts_by_vs[5])
+    got = seg.detach().cpu().numpy()
+    assert got.shape == (1, 48, 48, 32)
+    assert np.abs(got - ref).max() <= TOL_SCORE
+    assert (_labels(got) != _labels(ref)).mean() <= LABEL_MISMATCH_MAX
+    g = rng.standard_normal(ref.shape).astype(np.float32)
+    ref64 = _seg_grad_oracle(pr, ref_mask, 48, 5, parts_by_vs[5], g, torch.float64)
+    (seg * t(g)).sum().backward()
+    gg = x.grad.cpu().numpy().astype(np.float64)
+    assert np.all(gg[:, 1378:] == 0)                       # vertices the table never addresses receive no gradient
+    scale = np.abs(ref64).max() + 1e-9
+    bad = np.abs(gg - ref64) > 2e-4 * scale
+    assert bad.mean() <= 2e-3, (bad.mean(), np.abs(gg - ref64).max(), scale)
+
+
 def test_errors(pkg, host_model):
     layer = pkg.SMPLLayer(host_model, device=dev())
     with pytest.raises(pkg.SmplB200Error):

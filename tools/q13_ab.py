@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Q13 (verdict, weak #4): the seg forward's hot loop forms d2 = fma(du, du, fl(dv^2)), the reference's tf.norm forms
+fl(fl(du^2) + fl(dv^2)).  A/B of the two forms: kernel time at N = 16384 and score / label agreement with the NumPy oracle
+(which uses the reference's two roundings) on the oracle's own projections.  Usage: q13_ab.py [path/to/alternative.so]"""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+binding = importlib.import_module("indirect_learning_pose-shape_b200._lib")
+if len(sys.argv) > 1:
+    binding.LIB_PATH = os.path.abspath(sys.argv[1])
+pkg = importlib.import_module("indirect_learning_pose-shape_b200")
+synth = importlib.import_module("indirect_learning_pose-shape_b200.synth")
+from oracle import np_oracle  # noqa: E402
+
+dev = torch.device("cuda", 0)
+host = pkg.smpl_io.make_synthetic_smpl(seed=0)
+parts = pkg.smpl_io.golden_part_vertices(5)
+n, wh = 48, 48
+p = synth.make_params(n, wh, seed=4242)
+pr = np_oracle.orthographic_project([np_oracle.smpl_layer_call(host, p), p], 5)
+mk = np_oracle.compute_mask(pr)
+ref = np_oracle.projects_to_seg([pr, mk], wh, 5, parts)
+got = pkg.projects_to_seg([torch.as_tensor(pr, device=dev), torch.as_tensor(mk, device=dev)], wh, 5, parts=parts).cpu().numpy()
+# arg-max flips of single parts: compare per-part scores where they differ by more than exp/sqrt rounding
+res = {"lib": binding.LIB_PATH, "max_abs_dscore": float(np.abs(got - ref).max()),
+       "label_mismatch_rate": float((got.argmax(-1) != ref.argmax(-1)).mean()),
+       "scores_differing_by_more_than_3e-7": float((np.abs(got - ref) > 3e-7).mean())}
+N = 16384
+x = torch.as_tensor(synth.make_params(N, wh, seed=0), device=dev)
+dec = pkg.SmplDecoder(host, wh, 5, parts=parts, device=dev, need_verts=False)
+with torch.no_grad():
+    out = dec(x)
+    prj, msk = out["projects"], out["mask"]
+    for _ in range(3):
+        pkg.projects_to_seg([prj, msk], wh, 5, parts=parts)
+    pkg.profile_enable(True); pkg.profile_collect()
+    for _ in range(10):
+        pkg.projects_to_seg([prj, msk], wh, 5, parts=parts)
+    pkg.profile_enable(False)
+    st = pkg.profile_collect()
+res["seg_fwd_no_track_ms"] = st["seg_fwd"][1] / st["seg_fwd"][0]
+xg = prj.clone().requires_grad_(True)
+pkg.profile_enable(True); pkg.profile_collect()
+for _ in range(10):
+    pkg.projects_to_seg([xg, msk], wh, 5, parts=parts)
+pkg.profile_enable(False)
+st = pkg.profile_collect()
+res["seg_fwd_track_ms"] = st["seg_fwd"][1] / st["seg_fwd"][0]
+print(json.dumps(res))
