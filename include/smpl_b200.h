@@ -183,7 +183,7 @@ int smpl_b200_seg_loss_bwd(const SmplB200Parts* parts, const float* projects, co
 /* ---- the whole path in one call (model.py:108-118: SMPLLayer -> orthographic_project -> compute_mask -> projects_to_seg)
  * params (N,86) -> projects (N,Vs,3), mask (N,Vs), seg (N,wh,wh,P+1) [+ verts (N,V,3), joints24 (N,24,3); NULL to skip].
  * `state` (nullable; smpl_b200_full_state_bytes, 16-byte aligned) receives what full_bwd needs: the compact sampled
- * v_posed and the seg arg-min bytes.  NULL = inference: nothing is saved and the rasteriser skips the arg-min tracking.
+ * v_posed, the 24 bone transforms per sample and the seg arg-min bytes.  NULL = inference: nothing is saved and the rasteriser skips the arg-min tracking.
  * Workspace: smpl_b200_workspace_bytes(model, SMPL_B200_OP_FULL_FWD / _BWD, N, img_wh, vertex_sampling).
  * full_bwd: g_seg (N,wh,wh,P+1) -> g_params (N,86), written; projects and mask are full_fwd's outputs. */
 size_t smpl_b200_full_state_bytes(const SmplB200Model* model, int N, int img_wh, int vertex_sampling);

@@ -503,9 +503,11 @@ size_t smpl_b200_workspace_bytes(const SmplB200Model* m, int op, int N, int img_
     }                                                                                \
   } while (0)
 
-int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, float* verts, float* joints24,
-                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* v_posed_sampled,
-                         float* projects, int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream) {
+// A_keep (nullable, [N][24][12]): the bone transforms, kept for a backward that then skips their recomputation
+static int decode_fwd_impl(const SmplB200Model* m, const float* params, int N, float* verts, float* joints24,
+                           float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* v_posed_sampled,
+                           float* projects, int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream,
+                           float* A_keep) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!m || !params || N < 0 || (!verts && !projects)) { set_error("decode_fwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
@@ -527,19 +529,28 @@ int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, flo
   float* vp = v_posed_save ? v_posed_save : (float*)((char*)workspace + w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const bool dense = N >= kDenseBatch;                                  // tensor cores only where the batch makes the GEMM dense
-  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, dense ? w.Xlo : nullptr, w.A, joints24 ? joints24 : w.Jtr, st));
+  float* Abuf = A_keep ? A_keep : w.A;
+  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, dense ? w.Xlo : nullptr, Abuf, joints24 ? joints24 : w.Jtr, st));
   if (dense) CHECK_LAUNCH(launch_blend_fwd_tc(m, w.X, w.Xlo, N, vp, st));
   else CHECK_LAUNCH(launch_blend_fwd(m, w.X, N, vp, st));
   const int Vs = (m->V + vs - 1) / vs;
-  CHECK_LAUNCH(launch_lbs_fwd(m, vp, w.A, params, N, verts, projects, vs, v_posed_sampled, SMPL_B200_VPS_LD(Vs), st));
+  CHECK_LAUNCH(launch_lbs_fwd(m, vp, Abuf, params, N, verts, projects, vs, v_posed_sampled, SMPL_B200_VPS_LD(Vs), st));
   if (joints_reg) CHECK_LAUNCH(launch_joints_reg_fwd(m, verts, N, num_reg_joints_used, joints_reg, st));
   return SMPL_B200_OK;
 }
 
-int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, const float* v_posed_save,
-                         const float* v_posed_sampled, const float* g_verts, const float* g_projects,
-                         int vertex_sampling, const float* g_joints24, float* g_params, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+int smpl_b200_decode_fwd(const SmplB200Model* m, const float* params, int N, float* verts, float* joints24,
+                         float* joints_reg, int num_reg_joints_used, float* v_posed_save, float* v_posed_sampled,
+                         float* projects, int vertex_sampling, void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_fwd_impl(m, params, N, verts, joints24, joints_reg, num_reg_joints_used, v_posed_save, v_posed_sampled,
+                         projects, vertex_sampling, workspace, workspace_bytes, stream, nullptr);
+}
+
+// A_saved (nullable): decode_fwd_impl's A_keep; without it the transforms are recomputed from params
+static int decode_bwd_impl(const SmplB200Model* m, const float* params, int N, const float* v_posed_save,
+                           const float* v_posed_sampled, const float* g_verts, const float* g_projects,
+                           int vertex_sampling, const float* g_joints24, float* g_params, void* workspace,
+                           size_t workspace_bytes, void* stream, const float* A_saved) {
   if (N == 0) return SMPL_B200_OK;   // empty batch: nothing to launch
   if (!m || !params || !g_params || N < 0) { set_error("decode_bwd: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG; }
   const int vs_in = vertex_sampling < 1 ? 1 : vertex_sampling;
@@ -559,9 +570,10 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool dense = N >= kDenseBatch;
-  CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, nullptr, w.A, w.Jtr, st));   // recompute A (cheap) instead of saving it
+  if (!A_saved) CHECK_LAUNCH(launch_pose_fwd(m, params, N, w.X, nullptr, w.A, w.Jtr, st));   // recompute A instead of saving it
+  const float* Abuf = A_saved ? A_saved : w.A;
   int cam_chunks = w.cam_chunks;
-  CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, w.A, params, g_verts, g_projects, N, w.gvp,
+  CHECK_LAUNCH(launch_lbs_bwd(m, t, vs_in, v_posed_save, Abuf, params, g_verts, g_projects, N, w.gvp,
                               dense ? w.gvplo : nullptr, w.gvp_ld, w.gA, w.gcam, &cam_chunks,
                               full ? nullptr : v_posed_sampled, SMPL_B200_VPS_LD(t->Vs), st));
   int gx_planes = 1;
@@ -569,6 +581,14 @@ int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, con
   else CHECK_LAUNCH(launch_blend_bwd(m, t, w.gvp, w.gvp_ld, N, w.gX, st));
   CHECK_LAUNCH(launch_pose_bwd(m, params, w.gA, w.gX, gx_planes, g_joints24, w.gcam, cam_chunks, N, g_params, st));
   return SMPL_B200_OK;
+}
+
+int smpl_b200_decode_bwd(const SmplB200Model* m, const float* params, int N, const float* v_posed_save,
+                         const float* v_posed_sampled, const float* g_verts, const float* g_projects,
+                         int vertex_sampling, const float* g_joints24, float* g_params, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return decode_bwd_impl(m, params, N, v_posed_save, v_posed_sampled, g_verts, g_projects, vertex_sampling, g_joints24,
+                         g_params, workspace, workspace_bytes, stream, nullptr);
 }
 
 int smpl_b200_project_fwd(const float* verts, const float* params, int N, int V, int vertex_sampling, float* projects,
@@ -757,10 +777,13 @@ static size_t full_vps_bytes(const SmplB200Model* m, int N, int vs) {
   return ru((size_t)N * SMPL_B200_VPS_LD(Vs) * sizeof(float), 256);
 }
 
+static size_t full_A_bytes(int N) { return ru((size_t)N * kJ * 12 * sizeof(float), 256); }
+
+// state = [compact sampled v_posed][bone transforms][seg arg-min bytes]
 size_t smpl_b200_full_state_bytes(const SmplB200Model* m, int N, int img_wh, int vertex_sampling) {
   if (!m || N < 0 || img_wh < 0) return 0;
   const int vs = vertex_sampling < 1 ? 1 : vertex_sampling;
-  return full_vps_bytes(m, N, vs) + seg_saved_bytes(N, img_wh);
+  return full_vps_bytes(m, N, vs) + full_A_bytes(N) + seg_saved_bytes(N, img_wh);
 }
 
 int smpl_b200_full_fwd(const SmplB200Model* m, const SmplB200Parts* parts, const float* params, int N, int img_wh,
@@ -780,9 +803,10 @@ int smpl_b200_full_fwd(const SmplB200Model* m, const SmplB200Parts* parts, const
     set_error("full_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return SMPL_B200_ERR_WORKSPACE;
   }
   float* vps = state ? (float*)state : nullptr;
-  unsigned char* saved = state ? (unsigned char*)state + full_vps_bytes(m, N, vs) : nullptr;
-  rc = smpl_b200_decode_fwd(m, params, N, verts, joints24, nullptr, 0, nullptr, vps, projects, vs, workspace,
-                            workspace_bytes, stream);
+  float* A_keep = state ? (float*)((char*)state + full_vps_bytes(m, N, vs)) : nullptr;
+  unsigned char* saved = state ? (unsigned char*)state + full_vps_bytes(m, N, vs) + full_A_bytes(N) : nullptr;
+  rc = decode_fwd_impl(m, params, N, verts, joints24, nullptr, 0, nullptr, vps, projects, vs, workspace, workspace_bytes,
+                       stream, A_keep);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CHECK_LAUNCH(launch_mask_fwd(projects, N, Vs, mask, st));
@@ -813,7 +837,8 @@ int smpl_b200_full_bwd(const SmplB200Model* m, const SmplB200Parts* parts, const
   const size_t dbytes = decode_ws(m, N, true, false, vs, nullptr).bytes;
   float* g_proj = (float*)((char*)workspace + dbytes);
   const float* vps = (const float*)state;
-  const unsigned char* saved = (const unsigned char*)state + full_vps_bytes(m, N, vs);
+  const float* A_saved = (const float*)((const char*)state + full_vps_bytes(m, N, vs));
+  const unsigned char* saved = (const unsigned char*)state + full_vps_bytes(m, N, vs) + full_A_bytes(N);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = launch_seg_bwd(parts, projects, mask, g_seg, saved, N, Vs, img_wh, g_proj, st);
   if (e == cudaErrorInvalidConfiguration) {
@@ -821,7 +846,7 @@ int smpl_b200_full_bwd(const SmplB200Model* m, const SmplB200Parts* parts, const
     return SMPL_B200_ERR_UNSUPPORTED;
   }
   CHECK_LAUNCH(e);
-  return smpl_b200_decode_bwd(m, params, N, nullptr, vps, nullptr, g_proj, vs, nullptr, g_params, workspace, dbytes, stream);
+  return decode_bwd_impl(m, params, N, nullptr, vps, nullptr, g_proj, vs, nullptr, g_params, workspace, dbytes, stream, A_saved);
 }
 
 int smpl_b200_silhouette_fwd(const float* projects, int N, int Vs, int img_wh, float* sil, void* workspace,
