@@ -23,7 +23,7 @@ constexpr int kARow = kJ * 12;  // floats of bone transforms per sample
 template <int KW>
 struct Skin {
   float w[KW];
-  int j[KW];
+  int j[KW];        // byte offset of the joint's 3x4 transform inside a sample's block of 24 (joint * 48)
 };
 
 template <int KW>
@@ -33,23 +33,33 @@ __device__ __forceinline__ Skin<KW> load_skin(const uint8_t* __restrict__ idx, c
   for (int k = 0; k < KW; k += 4) {
     const uchar4 i4 = *reinterpret_cast<const uchar4*>(idx + (size_t)v * KW + k);
     const float4 w4 = *reinterpret_cast<const float4*>(w + (size_t)v * KW + k);
-    s.j[k] = i4.x; s.j[k + 1] = i4.y; s.j[k + 2] = i4.z; s.j[k + 3] = i4.w;
+    s.j[k] = i4.x * 48; s.j[k + 1] = i4.y * 48; s.j[k + 2] = i4.z * 48; s.j[k + 3] = i4.w * 48;
     s.w[k] = w4.x; s.w[k + 1] = w4.y; s.w[k + 2] = w4.z; s.w[k + 3] = w4.w;
   }
   return s;
 }
 
+// explicit shared-window load: through a generic pointer the compiler rebuilds the window base (S2UR + ULEA) in front of
+// every access of the loop -- six times per (vertex, sample), a tenth of the forward's stall samples
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // T (3x4, row-major) = sum_k w_k * A[j_k]   (batch_smpl.py:138-140; zero-weight joints contribute exact zeros)
+// As_sa: shared-window address of the sample's 24 transforms
 template <int KW>
-__device__ __forceinline__ void blend_T(const Skin<KW>& s, const float* __restrict__ As, float T[12]) {
+__device__ __forceinline__ void blend_T(const Skin<KW>& s, uint32_t As_sa, float T[12]) {
 #pragma unroll
   for (int e = 0; e < 12; ++e) T[e] = 0.f;
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
     const float w = s.w[k];
     if (w == 0.f) continue;      // ELL padding (2.9 of 4 entries are real on average): skipping an exact zero changes nothing
-    const float4* a = reinterpret_cast<const float4*>(As + s.j[k] * 12);
-    const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+    const uint32_t a = As_sa + (uint32_t)s.j[k];
+    const float4 r0 = lds_f4(a), r1 = lds_f4(a + 16), r2 = lds_f4(a + 32);
     T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
     T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
     T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
@@ -111,6 +121,7 @@ lbs_fwd_warp_kernel(const float* __restrict__ vp, int LD, const float* __restric
   const int q = v / vs;
   const int lim = (V * 3 - colw) / 2;                              // float2 slots of this warp's slice that exist (V*3, colw even)
   __syncthreads();                                                 // As / cam published; the only block-wide barrier
+  const uint32_t As_sa = smem_addr(As);
   for (int s = 0; s < rows; ++s) {
     const int n = n0 + s;
     issue(s + kLbsStages - 1);                                     // keeps kLbsStages-1 slices in flight behind this one
@@ -121,7 +132,7 @@ lbs_fwd_warp_kernel(const float* __restrict__ vp, int LD, const float* __restric
     if (need) {
       const float x = st[lane * 3], y = st[lane * 3 + 1], z = st[lane * 3 + 2];
       float T[12];
-      blend_T<KW>(skin, As + s * kARow, T);
+      blend_T<KW>(skin, As_sa + (uint32_t)(s * kARow * 4), T);
       ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
       oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
       oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
@@ -193,7 +204,7 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
       float gx, gy, gz, gu, gv;
       vertex_grad(g_verts, g_projects, n, v, V, vs_proj, Vs_proj, ku, kv, gx, gy, gz, gu, gv);
       float T[12];
-      blend_T<KW>(skin, As + s * kARow, T);
+      blend_T<KW>(skin, smem_addr(As) + (uint32_t)(s * kARow * 4), T);
       float* o = g_vp + (size_t)n * gvp_ld + (size_t)q * 3;
       float r3[3];
       r3[0] = fmaf(T[0], gx, fmaf(T[4], gy, T[8] * gz));
@@ -304,6 +315,7 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
   const float ku = params[(size_t)n * kParams], kv = params[(size_t)n * kParams + 1];
   __syncthreads();
   const float* gp = g_projects + (size_t)n * Vs * 3;
+  const uint32_t As_sa = smem_addr(As);
   float* orow = g_vp + (size_t)n * gvp_ld;
   float* lrow = g_vp_lo ? g_vp_lo + (size_t)n * gvp_ld : nullptr;
   float c4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -313,7 +325,7 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
     const float x = vrow[(size_t)q * step3], y = vrow[(size_t)q * step3 + 1], z = vrow[(size_t)q * step3 + 2];
     const float gx = gu * ku, gy = gv * kv;                       // u = u0 + x k_u, v = v0 + y k_v (projection.py:77-78)
     float T[12];
-    blend_T<KW>(skin, As, T);
+    blend_T<KW>(skin, As_sa, T);
     float r3[3];
     r3[0] = fmaf(T[0], gx, fmaf(T[4], gy, T[8] * gz));
     r3[1] = fmaf(T[1], gx, fmaf(T[5], gy, T[9] * gz));
