@@ -826,8 +826,10 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int nb = (npx + 3) >> 2;
   const int b0 = (int)(((long long)nb * warp) / nwarps), b1 = (int)(((long long)nb * (warp + 1)) / nwarps);
   // cp.async.bulk.prefetch needs 16-byte aligned addresses: the rows are multiples of 16 bytes here, and the launcher
-  // clears pf_ok when the caller's g_seg / saved base pointers are not (a contiguous autograd view with an odd offset)
-  const bool kPrefetch = C32 && ALIGNED && pf_ok;
+  // takes the unaligned schedule (no prefetch) when the caller's g_seg / saved base pointers are not (a contiguous
+  // autograd view with an odd offset)
+  constexpr bool kPrefetch = C32 && ALIGNED;
+  (void)pf_ok;
   const unsigned char* pf_base = (lane == 0) ? (LOSS ? reinterpret_cast<const unsigned char*>(aux + (size_t)n * npx)
                                                      : reinterpret_cast<const unsigned char*>(g_seg + (size_t)n * npx * 32))
                                              : saved + (size_t)n * npx * 32;
@@ -1119,9 +1121,9 @@ static cudaError_t launch_bwd_impl(const SmplB200Parts* p, const float* projects
                                                               p->obase, p->P, p->ovf, wh, g_projects, pf_ok,           \
                                                               reinterpret_cast<const float4*>(aux), g_loss);           \
   } while (0)
-  const bool c32 = p->P == 31, al = wh % 4 == 0 && wh >= 8;
   const void* row0 = aux ? aux : (const void*)g_seg;
   const int pf_ok = (reinterpret_cast<uintptr_t>(row0) % 16 == 0 && reinterpret_cast<uintptr_t>(saved) % 16 == 0) ? 1 : 0;
+  const bool c32 = p->P == 31, al = wh % 4 == 0 && wh >= 8 && (pf_ok || p->P != 31);
   if (aux) {
     if (c32 && al) SMPL_SEG_BWD(true, true, true);
     else if (c32) SMPL_SEG_BWD(true, false, true);
