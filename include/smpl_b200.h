@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SMPL_B200_ABI_VERSION 2
+#define SMPL_B200_ABI_VERSION 3
 #define SMPL_B200_NUM_PARAMS 86
 #define SMPL_B200_NUM_JOINTS 24
 #define SMPL_B200_VPOSED_LD(num_verts) ((((num_verts) + 255) / 256) * 768) /* row stride (floats) of the saved v_posed: whole 256-vertex chunks */
@@ -63,6 +63,7 @@ typedef struct SmplB200HostModel {
 
 typedef struct SmplB200Model SmplB200Model; /* immutable after create; one per device */
 typedef struct SmplB200Parts SmplB200Parts; /* immutable part->vertex table on one device */
+typedef struct SmplB200Renderer SmplB200Renderer; /* immutable mesh topology of the visualiser on one device */
 
 /* ---- library -------------------------------------------------------------------------------------- */
 int smpl_b200_abi_version(void);
@@ -235,6 +236,26 @@ int smpl_b200_dense_bwd(const float* X, int ldx, const float* W, const float* Y,
  * (param_{k+1} = param_k + scaledown * delta_k, model.py:80-82; the column copies that assemble the IEF state). */
 int smpl_b200_axpy_cols(const float* a, int lda, const float* d, int ldd, float scale, int rows, int cols, float* out, int ldo,
                         void* stream);
+
+/* ---- the consumer of `verts`: the mesh visualiser (renderer.py:23-115,146-197) ---------------------
+ * Replaces SMPLRenderer.__call__ -> render_model -> simple_renderer, i.e. OpenDR's ProjectPoints + LambertianPointLight +
+ * ColoredRenderer (third-party, absent from the reference tree; the algorithm restated is listed in
+ * csrc/render_kernels.cu and oracle/np_oracle.py:render_mesh).
+ * renderer_create: faces (num_faces,3) HOST int32 vertex indices (keras_smpl/smpl_faces.npy, renderer.py:27).
+ * render: verts (N,V,3) camera-frame vertices (x right, y down, z forward); cam (N,3) = [f, cx, cy] (renderer.py:54-62);
+ * near_far (N,2) clip planes (:64-67; near <= 0 clips at z > 0 only); albedo (3) or (V,3) floats in [0,1]
+ * (albedo_per_vertex != 0: the PLY part colours of render_seg, :158-168); lights: num_lights x [x,y,z,r,g,b] HOST floats
+ * (:171-195; num_lights = 0 renders the albedo unlit, as render_seg does); background: NULL = white (:153), else
+ * (height,width,3) uint8 shared by every image or (N,height,width,3) when background_per_image != 0 (:231-232);
+ * image (N,height,width,channels) uint8, channels 3, or 4 with the alpha of get_alpha / append_alpha (:200-218, :252-255).
+ * All pointers but faces / lights are DEVICE pointers.  Workspace: smpl_b200_render_workspace_bytes(r, N), 16-byte aligned. */
+int smpl_b200_renderer_create(int device, const int32_t* faces, int num_faces, int num_verts, SmplB200Renderer** out);
+void smpl_b200_renderer_destroy(SmplB200Renderer* renderer);
+size_t smpl_b200_render_workspace_bytes(const SmplB200Renderer* renderer, int N);
+int smpl_b200_render(const SmplB200Renderer* renderer, const float* verts, const float* cam, const float* near_far, int N,
+                     int height, int width, const float* albedo, int albedo_per_vertex, const float* lights,
+                     int num_lights, const uint8_t* background, int background_per_image, int channels, uint8_t* image,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

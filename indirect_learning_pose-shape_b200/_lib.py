@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsmpl_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OP_DECODE_FWD, OP_DECODE_BWD, OP_SILHOUETTE_FWD, OP_SILHOUETTE_BWD, OP_FULL_FWD, OP_FULL_BWD = 0, 1, 2, 3, 4, 5
 
 _f32p = C.POINTER(C.c_float)
@@ -86,6 +86,12 @@ SIGNATURES = {
                                            C.c_int, C.c_void_p, C.c_void_p]),
     "smpl_b200_focal_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float,
                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "smpl_b200_renderer_create": (C.c_int, [C.c_int, _i32p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "smpl_b200_renderer_destroy": (None, [C.c_void_p]),
+    "smpl_b200_render_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "smpl_b200_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, _f32p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_size_t, C.c_void_p]),
 }
 
 _lock = threading.Lock()

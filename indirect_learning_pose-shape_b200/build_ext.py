@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsmpl_b200.so")
 SOURCES = ["api.cu", "pose_kernels.cu", "blend_kernels.cu", "lbs_kernels.cu", "mask_kernels.cu", "seg_kernels.cu",
-           "sil_kernels.cu", "tc_gemm.cu", "loss_kernels.cu", "dense_kernels.cu"]
+           "sil_kernels.cu", "tc_gemm.cu", "loss_kernels.cu", "dense_kernels.cu", "render_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # No --use_fast_math: sqrt, division and exp must keep their IEEE / documented-ulp behaviour for parity.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -29,7 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // ---- built-in profiler: CUDA-event pairs around every launch, on the launching stream ---------------------------
 static const char* const kKernelNames[KID_COUNT] = {
     "pose_fwd", "blend_fwd", "lbs_fwd", "joints_reg", "lbs_bwd_vertex", "lbs_bwd_joint", "blend_bwd", "pose_bwd",
-    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd", "dense"};
+    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd", "dense", "render_vertex", "render_raster"};
 struct ProfRecord { int kid; cudaEvent_t a, b; };
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mutex;
@@ -900,6 +900,89 @@ int smpl_b200_focal_loss_bwd(const float* seg, const float* y_true, const uint8_
   if (num_classes < 1 || num_classes > 32) { set_error("focal_loss_bwd: num_classes=%d unsupported (1..32)", num_classes); return SMPL_B200_ERR_UNSUPPORTED; }
   CHECK_LAUNCH(launch_focal_loss_bwd(seg, y_true, labels, g_loss, num_pixels, num_classes, gamma, class_weights, from_logits,
                                      g_seg, (cudaStream_t)stream));
+  return SMPL_B200_OK;
+}
+
+// ---- mesh visualiser (renderer.py:23-115,146-197) ------------------------------------------------
+void smpl_b200_renderer_destroy(SmplB200Renderer* r) {
+  if (!r) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(r->device);
+  cudaFree(r->faces); cudaFree(r->adj_ptr); cudaFree(r->adj_face); cudaFree(r->q8);
+  cudaSetDevice(prev);
+  delete r;
+}
+
+int smpl_b200_renderer_create(int device, const int32_t* faces, int num_faces, int num_verts, SmplB200Renderer** out) {
+  if (!faces || !out || num_faces < 1 || num_verts < 1) { set_error("renderer_create: bad argument"); return SMPL_B200_ERR_BAD_ARG; }
+  *out = nullptr;
+  std::vector<int> f(faces, faces + (size_t)num_faces * 3), ptr(num_verts + 1, 0), adj((size_t)num_faces * 3);
+  for (size_t i = 0; i < f.size(); ++i) {
+    if (f[i] < 0 || f[i] >= num_verts) { set_error("renderer_create: vertex index %d out of range [0,%d)", f[i], num_verts); return SMPL_B200_ERR_BAD_ARG; }
+    ++ptr[f[i] + 1];
+  }
+  for (int v = 0; v < num_verts; ++v) ptr[v + 1] += ptr[v];
+  {
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int t = 0; t < num_faces; ++t)                    // ascending face index within each vertex's segment
+      for (int c = 0; c < 3; ++c) adj[fill[f[(size_t)t * 3 + c]]++] = t;
+  }
+  std::vector<unsigned char> q8(256);
+  for (int k = 0; k < 256; ++k) q8[k] = (unsigned char)(((double)k / 255.0) * 255.0);   // renderer.py:85 on OpenDR's k / 255.
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("renderer_create: no usable CUDA device %d", device); return SMPL_B200_ERR_NO_DEVICE;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU_TRY(cudaSetDevice(device));
+  SmplB200Renderer* r = new SmplB200Renderer();
+  struct Guard {
+    SmplB200Renderer* r; int prev;
+    ~Guard() { if (r) smpl_b200_renderer_destroy(r); cudaSetDevice(prev); }
+  } guard{r, prev};
+  r->device = device; r->V = num_verts; r->F = num_faces;
+  CU_TRY(upload(&r->faces, f));
+  CU_TRY(upload(&r->adj_ptr, ptr));
+  CU_TRY(upload(&r->adj_face, adj));
+  CU_TRY(upload(&r->q8, q8));
+  CU_TRY(cudaDeviceSynchronize());
+  guard.r = nullptr;
+  *out = r;
+  return SMPL_B200_OK;
+}
+
+size_t smpl_b200_render_workspace_bytes(const SmplB200Renderer* r, int N) {
+  if (!r || N < 0) return 0;
+  return (size_t)N * r->V * 2 * sizeof(float4);
+}
+
+int smpl_b200_render(const SmplB200Renderer* r, const float* verts, const float* cam, const float* near_far, int N,
+                     int height, int width, const float* albedo, int albedo_per_vertex, const float* lights,
+                     int num_lights, const uint8_t* background, int background_per_image, int channels, uint8_t* image,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return SMPL_B200_OK;
+  if (!r || !verts || !cam || !near_far || !albedo || !image || N < 0 || (num_lights > 0 && !lights)) {
+    set_error("render: null/invalid argument"); return SMPL_B200_ERR_BAD_ARG;
+  }
+  if (height < 1 || width < 1 || height > 8192 || width > 8192) { set_error("render: image %dx%d unsupported (1..8192)", height, width); return SMPL_B200_ERR_UNSUPPORTED; }
+  if (channels != 3 && channels != 4) { set_error("render: channels=%d (3 or 4)", channels); return SMPL_B200_ERR_BAD_ARG; }
+  if (num_lights < 0 || num_lights > kMaxLights) { set_error("render: num_lights=%d unsupported (0..%d)", num_lights, kMaxLights); return SMPL_B200_ERR_UNSUPPORTED; }
+  if (N > 65535) { set_error("render: at most 65535 images per call (got %d)", N); return SMPL_B200_ERR_UNSUPPORTED; }
+  const size_t need = smpl_b200_render_workspace_bytes(r, N);
+  if (!workspace || workspace_bytes < need || !aligned(workspace, 16)) {
+    set_error("render: workspace too small or misaligned (%zu < %zu bytes)", workspace_bytes, need); return SMPL_B200_ERR_WORKSPACE;
+  }
+  RenderLights L;
+  L.count = num_lights;
+  for (int l = 0; l < num_lights; ++l)
+    for (int c = 0; c < 3; ++c) { L.pos[l][c] = lights[l * 6 + c]; L.color[l][c] = lights[l * 6 + 3 + c]; }
+  float4* vscreen = reinterpret_cast<float4*>(workspace);
+  float4* vcolor = vscreen + (size_t)N * r->V;
+  CHECK_LAUNCH(launch_render(r, verts, cam, near_far, N, height, width, albedo, albedo_per_vertex, L, background,
+                             background_per_image, channels, vscreen, vcolor, image, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 

@@ -24,7 +24,7 @@ void count_launch();
 enum KernelId {
   KID_POSE_FWD = 0, KID_BLEND_FWD, KID_LBS_FWD, KID_JOINTS_REG, KID_LBS_BWD_VERTEX, KID_LBS_BWD_JOINT, KID_BLEND_BWD,
   KID_POSE_BWD, KID_PROJECT_FWD, KID_PROJECT_BWD, KID_MASK, KID_SEG_FWD, KID_SEG_BWD, KID_SIL_FWD, KID_SIL_BWD,
-  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_DENSE, KID_COUNT
+  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_DENSE, KID_RENDER_VERTEX, KID_RENDER_RASTER, KID_COUNT
 };
 // RAII scope around one kernel launch: counts it and, while profiling is enabled, brackets it with CUDA events
 // recorded on the launching stream.
@@ -49,6 +49,13 @@ struct VsTables {       // per vertex_sampling derived tables (device pointers)
   float* csc_w = nullptr;     // [nnz]
   uint8_t* lbs_idx_s = nullptr;  // [Vs][KW] skin-weight joints of the sampled vertices (compact copy of lbs_idx)
   float* lbs_w_s = nullptr;      // [Vs][KW]
+};
+
+constexpr int kMaxLights = 8;
+struct RenderLights {   // passed by value to the visualiser's vertex kernel; count == 0: unlit (albedo as is)
+  int count;
+  float pos[kMaxLights][3];
+  float color[kMaxLights][3];
 };
 
 struct TreeInfo {       // passed by value to the pose kernels
@@ -99,6 +106,15 @@ struct SmplB200Parts {
   int max_part = 0;
   int ovf = 0;               // sum_k max(size_k - 32, 0): overflow slots of the seg backward's interleaved light lists
   int* obase = nullptr;      // [P+1] device, exclusive prefix of max(size_k - 32, 0)
+};
+
+struct SmplB200Renderer {   // mesh topology of the visualiser (renderer.py:27), immutable
+  int device = 0;
+  int V = 0, F = 0;
+  int* faces = nullptr;       // [F][3] device
+  int* adj_ptr = nullptr;     // [V+1]  device: vertex -> incident faces (ascending face index)
+  int* adj_face = nullptr;    // [3F]
+  unsigned char* q8 = nullptr;  // [256] device: uint8((k / 255.) * 255.) -- the reference's float image -> uint8 round trip
 };
 
 namespace smplb200 {
@@ -195,6 +211,12 @@ cudaError_t launch_dense_bwd(const float* X, int ldx, const float* W, const floa
                              int num_sms, cudaStream_t st);
 cudaError_t launch_axpy_cols(const float* a, int lda, const float* d, int ldd, float scale, int rows, int cols, float* out,
                              int ldo, cudaStream_t st);
+
+// mesh visualiser (renderer.py): vscreen / vcolor = [N][V] float4 scratch
+cudaError_t launch_render(const SmplB200Renderer* r, const float* verts, const float* cam, const float* near_far, int N,
+                          int h, int w, const float* albedo, int albedo_per_vertex, const RenderLights& lights,
+                          const unsigned char* background, int bg_per_image, int channels, float4* vscreen, float4* vcolor,
+                          unsigned char* out, cudaStream_t st);
 
 // small device helpers
 // Asynchronous request of [p, p + bytes) into L2 (cp.async.bulk.prefetch: no register, no scoreboard; one thread moves a

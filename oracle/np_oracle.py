@@ -363,3 +363,167 @@ def plain_regressor(img_features, weights, img_wh, mean_vals, scaledown=0.005):
     smpl = dense(smpl, weights[2][0], weights[2][1], "linear")
     smpl = smpl * img_features.dtype.type(scaledown)
     return load_mean_set_cam_params(smpl, img_wh, mean_vals)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the consumer of `verts`: the mesh visualiser (renderer.py:23-115,146-197)
+# ---------------------------------------------------------------------------------------------------------------
+# renderer.py drives OpenDR (opendr.camera.ProjectPoints, opendr.lighting.LambertianPointLight,
+# opendr.renderer.ColoredRenderer; unpinned, absent from the reference tree and from this image).  What follows restates
+# OpenDR's published algorithm in float64 at exactly the reference's call sites; oracle/tf_shim/opendr wraps these same
+# functions in OpenDR's names so that renderer.py itself can be run (oracle/make_render_vectors.py).  "parity unpinned"
+# for OpenDR's GL rasterisation: the fill rule at exact edge hits, GL's fixed-point vertex snapping and the `overdraw`
+# anti-aliasing of silhouette edges are not restated.
+RENDER_COLORS = {"light_blue": [0.65098039, 0.74117647, 0.85882353], "light_pink": [.9, .7, .7]}   # renderer.py:16-20
+# simple_renderer's three point lights, renderer.py:171-195: (position, colour)
+RENDER_LIGHTS = (([-200.0, -100.0, -100.0], [1.0, 1.0, 1.0]), ([800.0, 10.0, 300.0], [1.0, 1.0, 1.0]),
+                 ([-500.0, 500.0, 1000.0], [0.7, 0.7, 0.7]))
+
+
+def rotate_y(points, angle):
+    """renderer.py:138-143 (_rotateY)."""
+    ry = np.array([[np.cos(angle), 0., np.sin(angle)], [0., 1., 0.], [-np.sin(angle), 0., np.cos(angle)]])
+    return np.dot(points, ry)
+
+
+def vert_normals(verts, faces):
+    """opendr.geometry.VertNormals: the (v1 - v0) x (v2 - v0) of every face summed onto its three vertices, normalised."""
+    v = np.asarray(verts, np.float64)
+    tn = np.cross(v[faces[:, 1]] - v[faces[:, 0]], v[faces[:, 2]] - v[faces[:, 0]])
+    n = np.zeros_like(v)
+    for c in range(3):
+        np.add.at(n, faces[:, c], tn)
+    nn = np.sqrt((n * n).sum(1, keepdims=True))
+    return np.where(nn > 0, n / np.where(nn > 0, nn, 1.0), 0.0)
+
+
+def lambertian_point_light(verts, faces, light_pos, vc, light_color):
+    """opendr.lighting.LambertianPointLight (single sided): max(n . normalise(light_pos - v), 0) * vc * light_color."""
+    v = np.asarray(verts, np.float64)
+    vn = vert_normals(v, faces)
+    ld = np.asarray(light_pos, np.float64).reshape(1, 3) - v
+    ld = ld / np.sqrt((ld * ld).sum(1, keepdims=True))
+    d = np.maximum((vn * ld).sum(1), 0.0)
+    return d.reshape(-1, 1) * np.asarray(vc, np.float64).reshape(-1, 3) * np.asarray(light_color, np.float64).reshape(1, 3)
+
+
+def _edge(ax, ay, bx, by, px, py):
+    return (bx - ax) * (py - ay) - (by - ay) * (px - ax)
+
+
+def _edge_owns(ax, ay, bx, by):
+    dx, dy = bx - ax, by - ay
+    return (dy < 0) or (dy == 0 and dx < 0)
+
+
+def rasterise(verts, faces, vc, f, c, h, w, near, far, background=None):
+    """opendr.renderer.ColoredRenderer.r for camera ProjectPoints(f, rt=0, t=0, k=0, c): z-buffered triangles, vertex colours
+    clamped to [0,1] and interpolated perspective-correctly, 8-bit frame buffer.  Pixel (r, c) is sampled at the projected
+    position (c, r).  Returns the float image OpenDR hands back: uint8 / 255. (h, w, 3)."""
+    v = np.asarray(verts, np.float64)
+    col = np.clip(np.broadcast_to(np.asarray(vc, np.float64).reshape(-1, 3), v.shape), 0.0, 1.0)
+    Z = v[:, 2]
+    iz = np.where(Z > 0, 1.0 / np.where(Z > 0, Z, 1.0), 0.0)
+    fx, fy = (float(f[0]), float(f[1])) if np.ndim(f) else (float(f), float(f))
+    X = fx * v[:, 0] * iz + float(c[0])
+    Y = fy * v[:, 1] * iz + float(c[1])
+    iz_hi = 1.0 / near if near > 0 else np.inf
+    iz_lo = 1.0 / far if far > 0 else 0.0
+    best = np.full((h, w), -1.0)
+    img = np.ones((h, w, 3)) if background is None else np.array(background, np.float64)
+    if background is not None:
+        img = np.rint(np.clip(img, 0.0, 1.0) * 255.0) / 255.0      # the 8-bit frame buffer holds the background too
+    for t in range(faces.shape[0]):
+        i0, i1, i2 = (int(q) for q in faces[t])
+        if not (Z[i0] > 0 and Z[i1] > 0 and Z[i2] > 0):
+            continue
+        x0, y0, x1, y1, x2, y2 = X[i0], Y[i0], X[i1], Y[i1], X[i2], Y[i2]
+        area = _edge(x0, y0, x1, y1, x2, y2)
+        if area == 0:
+            continue
+        c_lo, c_hi = max(int(np.ceil(min(x0, x1, x2))), 0), min(int(np.floor(max(x0, x1, x2))), w - 1)
+        r_lo, r_hi = max(int(np.ceil(min(y0, y1, y2))), 0), min(int(np.floor(max(y0, y1, y2))), h - 1)
+        if c_lo > c_hi or r_lo > r_hi:
+            continue
+        px, py = np.meshgrid(np.arange(c_lo, c_hi + 1, dtype=np.float64), np.arange(r_lo, r_hi + 1, dtype=np.float64))
+        w0, w1, w2 = _edge(x1, y1, x2, y2, px, py), _edge(x2, y2, x0, y0, px, py), _edge(x0, y0, x1, y1, px, py)
+        if area > 0:
+            inside = ((w0 > 0) | ((w0 == 0) & _edge_owns(x1, y1, x2, y2))) & \
+                     ((w1 > 0) | ((w1 == 0) & _edge_owns(x2, y2, x0, y0))) & \
+                     ((w2 > 0) | ((w2 == 0) & _edge_owns(x0, y0, x1, y1)))
+        else:
+            inside = ((w0 < 0) | ((w0 == 0) & _edge_owns(x2, y2, x1, y1))) & \
+                     ((w1 < 0) | ((w1 == 0) & _edge_owns(x0, y0, x2, y2))) & \
+                     ((w2 < 0) | ((w2 == 0) & _edge_owns(x1, y1, x0, y0)))
+        if not inside.any():
+            continue
+        s = w0 + w1 + w2
+        s = np.where(s == 0, 1.0, s)
+        b0, b1, b2 = w0 / s, w1 / s, w2 / s
+        z = b0 * iz[i0] + b1 * iz[i1] + b2 * iz[i2]
+        sub = best[r_lo:r_hi + 1, c_lo:c_hi + 1]
+        win = inside & (z >= iz_lo) & (z <= iz_hi) & (z > sub)          # strict: the first face drawn keeps a tie (GL_LESS)
+        if not win.any():
+            continue
+        q0, q1, q2 = b0 * iz[i0], b1 * iz[i1], b2 * iz[i2]
+        rgb = (q0[..., None] * col[i0] + q1[..., None] * col[i1] + q2[..., None] * col[i2]) / (q0 + q1 + q2)[..., None]
+        rgb = np.rint(np.clip(rgb, 0.0, 1.0) * 255.0) / 255.0         # the 8-bit frame buffer, read back as k / 255.
+        sub[win] = z[win]
+        img[r_lo:r_hi + 1, c_lo:c_hi + 1][win] = rgb[win]
+    return img
+
+
+def render_mesh(verts, faces, cam=None, img=None, do_alpha=False, far=None, near=None, color="light_blue", img_size=None,
+                render_seg=False, part_colors=None, default_size=224, flength=500.0, yrot=0.0):
+    """SMPLRenderer.__call__ -> render_model -> simple_renderer (renderer.py:34-85, 221-256, 146-197) on one mesh.
+    ``color``: the albedo's name (renderer.py:240-244 picks it from the dict by ``color_id``); ``part_colors`` (6890,3)
+    uint8: the PLY's vertex colours (render_seg, :158-168).  Returns uint8 (h, w, 3 or 4)."""
+    verts = np.asarray(verts, np.float64)
+    if img is not None:
+        h, w = img.shape[:2]                                                     # :47-48
+    elif img_size is not None:
+        h, w = img_size[0], img_size[1]                                          # :49-51
+    else:
+        h = w = default_size                                                     # :52-54
+    if cam is None:
+        cam = [flength, w / 2., h / 2.]                                          # :56-57
+    if near is None:
+        near = np.maximum(np.min(verts[:, 2]) - 25, -0.2)                        # :64-65
+    if far is None:
+        far = np.maximum(np.max(verts[:, 2]) + 25, 25)                           # :66-67
+    bg = None
+    if img is not None:
+        bg = img / 255. if img.max() > 1 else img                                # :231-232
+    albedo = np.asarray(RENDER_COLORS[color], np.float64)                        # :234-244, :153-154
+    if render_seg:
+        vc = np.asarray(part_colors, np.float64) / 255.0                         # :158-168
+    else:
+        vc = np.zeros((verts.shape[0], 3))
+        for pos, lc in RENDER_LIGHTS:                                            # :171-195
+            vc = vc + lambertian_point_light(verts, faces, rotate_y(np.array(pos), yrot), albedo, np.array(lc))
+    im = rasterise(verts, faces, vc, cam[0] * np.ones(2), cam[1:3], h, w, near, far, bg)   # :57-62, :223-224
+    if img is None and do_alpha:                                                 # :252-253 get_alpha
+        alpha = (~np.all(im == 1., axis=2)).astype(im.dtype)
+        im = np.concatenate([im, alpha[..., None]], axis=2)
+    elif img is not None and do_alpha:                                           # :254-255 append_alpha
+        im = np.concatenate([im, np.ones_like(im[:, :, :1])], axis=2)
+    return (im * 255).astype('uint8')                                            # :85
+
+
+def rodrigues(r):
+    """cv2.Rodrigues(rvec)[0]: the rotation matrix of an axis-angle vector (renderer.py:99-104)."""
+    r = np.asarray(r, np.float64).reshape(3)
+    th = np.sqrt((r * r).sum())
+    if th < 1e-300:
+        return np.eye(3)
+    k = r / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(k, k) + np.sin(th) * K
+
+
+def rotated_verts(verts, deg, axis='y'):
+    """SMPLRenderer.rotated, renderer.py:97-107: rotate about the mesh's centroid."""
+    a = np.radians(deg)
+    around = rodrigues([0, a, 0] if axis == 'y' else ([a, 0, 0] if axis == 'x' else [0, 0, a]))
+    center = verts.mean(axis=0)
+    return np.dot((verts - center), around) + center

@@ -79,7 +79,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert declared == set(binding.SIGNATURES), declared ^ set(binding.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.smpl_b200_abi_version() == 2
+    assert lib.smpl_b200_abi_version() == 3
     assert isinstance(lib.smpl_b200_launch_count(), int)
 
 

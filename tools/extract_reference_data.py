@@ -16,6 +16,8 @@ the GPU box).  Only data is extracted, never source:
                   (read at concat_mean_param.py:9-15), plus their byte offsets
   * h5_bytes    : the raw 4848-byte h5 file, so the offset reader can be tested
                   on the GPU box / without the reference tree
+  * faces       : keras_smpl/smpl_faces.npy, the 13776 triangles of the SMPL mesh
+                  (loaded at renderer.py:27; input of the mesh visualiser)
 """
 import os
 import pickle
@@ -61,6 +63,9 @@ def main():
     out["h5_bytes"] = np.frombuffer(raw, np.uint8)
     out["mean_shape"] = np.frombuffer(raw, "<f8", count=10, offset=4192).copy()
     out["mean_pose"] = np.frombuffer(raw, "<f8", count=72, offset=4272).copy()
+    faces = np.load(os.path.join(REF, "keras_smpl", "smpl_faces.npy"))
+    assert faces.shape == (13776, 3) and faces.max() == 6889
+    out["faces"] = faces.astype(np.int32)
     np.savez_compressed(OUT, **out)
     print("wrote", os.path.normpath(OUT), {k: v.shape for k, v in out.items()})
 
