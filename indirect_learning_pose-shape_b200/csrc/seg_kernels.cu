@@ -331,6 +331,46 @@ __device__ __forceinline__ void prune_tile(const SegSmem& sm, unsigned* kw, int 
   __syncwarp();
 }
 
+// The same pruning for ALL tiles of the block at once, lane = tile, warp = part: the part's vertices are walked with a
+// warp-uniform trip count and broadcast loads, where prune_tile's lane = part loop runs to the LARGEST part's count with
+// most lanes idle (ncu: 11 - 16 % of the forward).  Same arithmetic, so the survivor words are identical.  kwt =
+// [tiles of this block][KW] words; tile ti (visiting order, see the kernel) owns row ti - t0.
+__device__ void prune_all_tiles(const SegSmem& sm, unsigned* kwt, int KW, int P, int t0, int t1, int tiles_x, int tiles_y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int tb = t0; tb < t1; tb += 32) {
+    const bool act = tb + lane < t1;
+    const int ti = act ? tb + lane : t0;
+    const int ci = ti / tiles_y, ty = ti - ci * tiles_y;
+    const int tx = (tiles_x >> 1) + ((ci & 1) ? -((ci + 1) >> 1) : (ci >> 1));
+    const float tcx = (float)(tx * kTW) + kTileHW, tcy = (float)(ty * kTH) + kTileHH;
+    unsigned* kwl = kwt + (size_t)(ti - t0) * KW;
+    for (int k = warp; k < P; k += nwarps) {
+      const int n0 = sm.lcount[k];                                   // same address on every lane: broadcast
+      if (n0 == 0) continue;
+      const float4* ek = sm.ent + sm.pptr[k];
+      unsigned* kwp = kwl + sm.woff[k];
+      float bd = CUDART_INF_F, u0 = 0.f, v0 = 0.f;
+      for (int v = 0; v < n0; ++v) {
+        const float2 e = *reinterpret_cast<const float2*>(&ek[v]);
+        const float du = e.x - tcx, dv = e.y - tcy;
+        const float d = du * du + dv * dv;
+        if (d < bd) { bd = d; u0 = e.x; v0 = e.y; }
+      }
+      unsigned word = 0u;
+      for (int v = 0; v < n0; ++v) {
+        const float2 e = *reinterpret_cast<const float2*>(&ek[v]);
+        const float du = e.x - tcx, dv = e.y - tcy;
+        const float d = du * du + dv * dv;
+        const float slack = 2.0f * (fabsf(e.x - u0) * kTileHW + fabsf(e.y - v0) * kTileHH);
+        const bool keep = (d - bd) - slack < kPruneMargin + kPruneRel * d;
+        word |= (keep ? 1u : 0u) << (v & 31);
+        if ((v & 31) == 31) { if (act) kwp[v >> 5] = word; word = 0u; }
+      }
+      if ((n0 & 31) && act) kwp[n0 >> 5] = word;
+    }
+  }
+}
+
 // Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two fp32 lanes per instruction, each rounded to nearest like the
 // scalar op).  A pair lives in an aligned 64-bit register; ptxas reads a scalar operand as a broadcast (R.F32).
 typedef unsigned long long f32x2;
@@ -477,7 +517,7 @@ template <bool TRACK, bool LOSS>
 __global__ void __launch_bounds__(LOSS ? 288 : 256, LOSS ? 2 : 3)   // LOSS: 112 registers (three 6-warp blocks per SM), 8-warp launches allowed
 seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, int N, int Vs,
                const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh,
-               float* __restrict__ seg, unsigned char* __restrict__ saved, const SegLossArgs la) {
+               float* __restrict__ seg, unsigned char* __restrict__ saved, const SegLossArgs la, int KW, int kw_rows) {
   extern __shared__ __align__(16) unsigned char raw[];
   const SegSmem sm = carve(raw, E, wh);
   const int n = blockIdx.x;
@@ -489,10 +529,12 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   const int lx = lane & 7, ly = lane >> 3;
   unsigned char* sv = TRACK ? saved + (size_t)n * wh * wh * 32 : nullptr;
   float* seg_n = seg ? seg + (size_t)n * wh * wh * C : nullptr;
-  const int KW = seg_keep_words(E);
-  unsigned* kw = reinterpret_cast<unsigned*>(sm.rest) + (size_t)warp * KW;
+  // survivor words: kw_rows == nwarps: one row of KW words per warp, filled per tile by prune_tile; otherwise one row
+  // per tile of this block (kw_rows >= t1 - t0), filled once by prune_all_tiles
+  const bool kw_table = kw_rows != nwarps;
+  unsigned* const kw_base = reinterpret_cast<unsigned*>(sm.rest);
   // per-lane staging of one chunk: stage[(sub*4 + q)*32 + lane]  (lane-contiguous: conflict-free, no sync needed)
-  float* stage = reinterpret_cast<float*>(sm.rest + (((size_t)nwarps * KW * 4 + 15) & ~(size_t)15)) +
+  float* stage = reinterpret_cast<float*>(sm.rest + (((size_t)kw_rows * KW * 4 + 15) & ~(size_t)15)) +
                  (size_t)warp * (8 * kNB * 32) + lane;
 
   // Tiles are handed to the warps on demand (the first nwarps statically), the image's centre columns first: they hold
@@ -501,13 +543,18 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   classify(sm, projects + (size_t)n * Vs * 3, mask + (size_t)n * Vs, ptr, idx, P, wh);
   const int ghead = *sm.ghead;
   const bool any_heavy = *sm.nheavy > 0;
+  if (kw_table) {
+    prune_all_tiles(sm, kw_base, KW, P, t0, t1, tiles_x, tiles_y);
+    __syncthreads();
+  }
   for (int ti = t0 + warp; ti < t1;) {
     const int ci = ti / tiles_y, ty = ti - ci * tiles_y;
     const int tx = (tiles_x >> 1) + ((ci & 1) ? -((ci + 1) >> 1) : (ci >> 1));
     const int c0 = tx * kTW + lx * 2, r0 = ty * kTH + ly * 2;        // this lane's block origin (grid = (column,row), :26-31)
     const float gx0 = (float)c0, gx1 = (float)(c0 + 1), gy0 = (float)r0, gy1 = (float)(r0 + 1);
     const f32x2 GX = pk2(gx0, gx1), GY = pk2(gy0, gy1);
-    prune_tile(sm, kw, P, lane, (float)(tx * kTW) + kTileHW, (float)(ty * kTH) + kTileHH);
+    const unsigned* kw = kw_base + (size_t)(kw_table ? ti - t0 : warp) * KW;
+    if (!kw_table) prune_tile(sm, kw_base + (size_t)warp * KW, P, lane, (float)(tx * kTW) + kTileHW, (float)(ty * kTH) + kTileHH);
 
     bool blk_slow = ghead >= 0;                                      // any heavy vertex chained to one of my pixels?
     if (any_heavy) {
@@ -541,7 +588,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       for (int q = 0; q < kNB; ++q) { cw[0][q] = 0u; cw[1][q] = 0u; }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
+#pragma unroll 1   // (unrolling by two: 2.67 -> 3.92 ms; a single copy of the body for both halves: 2.675 -> 2.711 ms)
         for (int s4 = 0; s4 < 4; ++s4) {
           const int sub = half * 4 + s4;
           const int ch = chunk * 8 + sub;
@@ -1068,9 +1115,21 @@ cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const
     split = max(1, min(g.ntiles, (2 * 148 + N - 1) / N));
     warps = 8;     // every block re-classifies the sample's vertices: keep 8 warps for that even if it owns few tiles
   }
-  const size_t smem = seg_base_smem(p->E, wh) + (((size_t)warps * seg_keep_words(p->E) * 4 + 15) & ~(size_t)15) +
-                      (size_t)warps * 8 * kNB * 32 * 4;
-  if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
+  // Survivor words: one row per warp (pruned per tile, lane = part), or -- when it costs no resident block -- one row
+  // per tile of the block, pruned once with lane = tile (see prune_all_tiles).
+  const int KW = p->keep_words > 0 ? p->keep_words : seg_keep_words(p->E);
+  const size_t fixed = seg_base_smem(p->E, wh) + (size_t)warps * 8 * kNB * 32 * 4;
+  const size_t smem_warp = fixed + (((size_t)warps * KW * 4 + 15) & ~(size_t)15);
+  if (smem_warp > kMaxSmem) return cudaErrorInvalidConfiguration;
+  const int tiles_blk = (g.ntiles + split - 1) / split;
+  const size_t smem_table = fixed + (((size_t)tiles_blk * KW * 4 + 15) & ~(size_t)15);
+  constexpr size_t kSmSmem = 228 * 1024, kBlkReserve = 1024;   // per SM, and what the driver adds to every block
+  const int max_blocks = la ? 3 : 4;                          // the register cap of the kernel variants
+  const int blocks_warp = (int)std::min<size_t>(kSmSmem / (smem_warp + kBlkReserve), (size_t)max_blocks);
+  const bool table = tiles_blk != warps && smem_table <= kMaxSmem &&
+                     (int)std::min<size_t>(kSmSmem / (smem_table + kBlkReserve), (size_t)max_blocks) >= blocks_warp;
+  const size_t smem = table ? smem_table : smem_warp;
+  const int kw_rows = table ? tiles_blk : warps;
   dim3 grid(N, split);
   LaunchScope scope(KID_SEG_FWD, st);
   const SegLossArgs none{nullptr, nullptr, 0.f, nullptr, nullptr};
@@ -1079,7 +1138,7 @@ cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const
     cudaError_t e = cudaFuncSetAttribute(seg_fwd_kernel<TR, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
     seg_fwd_kernel<TR, LO><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg,  \
-                                                           saved, la ? *la : none);                                    \
+                                                           saved, la ? *la : none, KW, kw_rows);                       \
   } while (0)
   if (la) { if (saved) SMPL_SEG_FWD(true, true); else SMPL_SEG_FWD(false, true); }
   else { if (saved) SMPL_SEG_FWD(true, false); else SMPL_SEG_FWD(false, false); }
