@@ -429,7 +429,8 @@ int smpl_b200_parts_create(int device, int num_parts, const int32_t* part_ptr, c
   std::vector<int> ob(num_parts + 1, 0);
   for (int k = 0; k < num_parts; ++k) ob[k + 1] = ob[k] + std::max(ptr[k + 1] - ptr[k] - 32, 0);
   p->ovf = ob[num_parts];
-  for (int k = 0; k < num_parts; ++k) p->keep_words += (ptr[k + 1] - ptr[k] + 31) / 32;
+  p->keep_words = 32;     // a row of the seg forward's survivor table: 32 first words + the parts' further words
+  for (int k = 0; k < num_parts; ++k) p->keep_words += std::max((ptr[k + 1] - ptr[k] + 31) / 32 - 1, 0);
   CU_TRY(upload(&p->obase, ob));
   CU_TRY(cudaDeviceSynchronize());
   guard.p = nullptr;

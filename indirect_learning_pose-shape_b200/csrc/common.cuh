@@ -106,7 +106,7 @@ struct SmplB200Parts {
   int max_part = 0;
   int ovf = 0;               // sum_k max(size_k - 32, 0): overflow slots of the seg backward's interleaved light lists
   int* obase = nullptr;      // [P+1] device, exclusive prefix of max(size_k - 32, 0)
-  int keep_words = 0;        // sum_k ceil(size_k / 32): survivor words one tile of the seg forward needs at most
+  int keep_words = 0;        // 32 + sum_k max(ceil(size_k / 32) - 1, 0): survivor words one tile of the seg forward needs at most
 };
 
 struct SmplB200Renderer {   // mesh topology of the visualiser (renderer.py:27), immutable

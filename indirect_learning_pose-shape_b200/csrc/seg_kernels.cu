@@ -45,6 +45,9 @@ namespace {
 constexpr float kHeavyMin = 256.0f;
 constexpr float kDropX = 110.0f;      // exp(-x) == 0 in fp32 (denormals included) for x > 103.98
 constexpr unsigned kNone16 = 0xffffu;
+// A row of survivor words (one tile of the forward): word 0 of part k at [k] -- its address does not depend on the part's
+// descriptor, so the hot path loads both at once --, words w >= 1 at [kRow0 + woff[k] + w - 1].
+constexpr int kRow0 = 32;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct SegSmem {
@@ -53,7 +56,7 @@ struct SegSmem {
   int* lcount;     // [32] light entries per part (packed at the front of the part's CSR segment)
   int* lbase;      // [32] exclusive prefix sum of lcount
   int* pptr;       // [36] the part table's CSR pointers (P+1 used)
-  int* woff;       // [36] exclusive prefix sum of ceil(lcount / 32): offsets of the parts' survivor words
+  int* woff;       // [36] exclusive prefix sum of max(ceil(lcount / 32) - 1, 0): offsets of the parts' survivor words 1.. (see kRow0)
   int4* pdesc;     // [32] per part {shared address of its first entry, survivor words, word offset, -}: one load in the hot path
   int* ghead;      // [1]  chain of generic slots, -1 none
   int* nheavy;     // [1]  number of chained heavy entries
@@ -187,16 +190,17 @@ __device__ void classify(const SegSmem& sm, const float* __restrict__ proj, cons
   if (threadIdx.x < 32) {                               // exclusive scans of the light counts and of their word counts
     const int c = sm.lcount[threadIdx.x];
     const int cw = (c + 31) >> 5;
-    int s = c, sw = cw;
+    const int cx = max(cw - 1, 0);                      // words beyond the part's first (they follow the kRow0 first words)
+    int s = c, sw = cx;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, s, o), tw = __shfl_up_sync(0xffffffffu, sw, o);
       if ((int)threadIdx.x >= o) { s += t; sw += tw; }
     }
     sm.lbase[threadIdx.x] = s - c;
-    sm.woff[threadIdx.x] = sw - cw;
+    sm.woff[threadIdx.x] = sw - cx;
     sm.pdesc[threadIdx.x] = make_int4((int)((uint32_t)__cvta_generic_to_shared(sm.ent) + (uint32_t)sm.pptr[min((int)threadIdx.x, 35)] * 16u),
-                                      cw, sw - cw, 0);
+                                      cw, kRow0 + sw - cx - 1, 0);   // .z + w = row index of word w >= 1
   }
   __syncthreads();
 }
@@ -245,8 +249,8 @@ SegGeom seg_geom(int wh) {
   g.tiles_x = (wh + kTW - 1) / kTW; g.tiles_y = (wh + kTH - 1) / kTH; g.ntiles = g.tiles_x * g.tiles_y;
   return g;
 }
-// survivor words one warp needs: sum_k ceil(lcount_k / 32) <= E / 32 + P
-__host__ __device__ __forceinline__ int seg_keep_words(int E) { return E / 32 + 33; }
+// row length: kRow0 + sum_k max(ceil(lcount_k / 32) - 1, 0) <= kRow0 + E / 32
+__host__ __device__ __forceinline__ int seg_keep_words(int E) { return kRow0 + E / 32 + 1; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward
@@ -307,7 +311,7 @@ __device__ __forceinline__ void prune_tile(const SegSmem& sm, unsigned* kw, int 
     const int n0 = sm.lcount[lane];
     if (n0 > 0) {
       const float4* ek = sm.ent + sm.pptr[lane];
-      unsigned* kwp = kw + sm.woff[lane];
+      unsigned* kwx = kw + kRow0 + sm.woff[lane] - 1;              // word w >= 1 at kwx[w]
       float bd = CUDART_INF_F, u0 = 0.f, v0 = 0.f;
       for (int v = 0; v < n0; ++v) {
         const float2 e = *reinterpret_cast<const float2*>(&ek[v]);
@@ -323,9 +327,9 @@ __device__ __forceinline__ void prune_tile(const SegSmem& sm, unsigned* kw, int 
         const float slack = 2.0f * (fabsf(e.x - u0) * kTileHW + fabsf(e.y - v0) * kTileHH);
         const bool keep = (d - bd) - slack < kPruneMargin + kPruneRel * d;
         word |= (keep ? 1u : 0u) << (v & 31);
-        if ((v & 31) == 31) { kwp[v >> 5] = word; word = 0u; }
+        if ((v & 31) == 31) { *((v >> 5) ? kwx + (v >> 5) : kw + lane) = word; word = 0u; }
       }
-      if (n0 & 31) kwp[n0 >> 5] = word;
+      if (n0 & 31) *((n0 >> 5) ? kwx + (n0 >> 5) : kw + lane) = word;
     }
   }
   __syncwarp();
@@ -348,7 +352,7 @@ __device__ void prune_all_tiles(const SegSmem& sm, unsigned* kwt, int KW, int P,
       const int n0 = sm.lcount[k];                                   // same address on every lane: broadcast
       if (n0 == 0) continue;
       const float4* ek = sm.ent + sm.pptr[k];
-      unsigned* kwp = kwl + sm.woff[k];
+      unsigned* kwx = kwl + kRow0 + sm.woff[k] - 1;                 // word w >= 1 at kwx[w]
       float bd = CUDART_INF_F, u0 = 0.f, v0 = 0.f;
       for (int v = 0; v < n0; ++v) {
         const float2 e = *reinterpret_cast<const float2*>(&ek[v]);
@@ -364,9 +368,9 @@ __device__ void prune_all_tiles(const SegSmem& sm, unsigned* kwt, int KW, int P,
         const float slack = 2.0f * (fabsf(e.x - u0) * kTileHW + fabsf(e.y - v0) * kTileHH);
         const bool keep = (d - bd) - slack < kPruneMargin + kPruneRel * d;
         word |= (keep ? 1u : 0u) << (v & 31);
-        if ((v & 31) == 31) { if (act) kwp[v >> 5] = word; word = 0u; }
+        if ((v & 31) == 31) { if (act) *((v >> 5) ? kwx + (v >> 5) : kwl + k) = word; word = 0u; }
       }
-      if ((n0 & 31) && act) kwp[n0 >> 5] = word;
+      if ((n0 & 31) && act) *((n0 >> 5) ? kwx + (n0 >> 5) : kwl + k) = word;
     }
   }
 }
@@ -597,18 +601,19 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
             for (int q = 0; q < kNB; ++q) stage[(sub * kNB + q) * 32] = 0.f;
             continue;
           }
-          const int4 pd = sm.pdesc[ch - 1];                          // {entry address, survivor words, word offset}
+          const int4 pd = sm.pdesc[ch - 1];                          // {entry address, survivor words, row index of word 1 - 1}
+          const unsigned m0 = kw[ch - 1];                            // the part's first survivor word: independent of pd
           const unsigned sh = 8u * (unsigned)s4;
           float best[kNB];
           unsigned barg[kNB];                                        // arg-min code, already shifted to its byte
           // survivors are visited from the highest index down and replace on <=, so the LOWEST index wins exact ties
           if (pd.y == 1) {                                           // at most 32 visible vertices: the common case
-            scan_word<TRACK, false, true>(kw[pd.z], (uint32_t)pd.x, 0, sh, GX, GY, best, barg);
+            scan_word<TRACK, false, true>(m0, (uint32_t)pd.x, 0, sh, GX, GY, best, barg);
           } else {
 #pragma unroll
             for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
             for (int w = pd.y; w-- > 0;) {
-              const unsigned m = kw[pd.z + w];                       // same address on every lane: broadcast
+              const unsigned m = w ? kw[pd.z + w] : m0;              // same address on every lane: broadcast
               const uint32_t eb = (uint32_t)pd.x + (uint32_t)(w * 32) * 16u;
               if (TRACK && w >= 7) scan_word<TRACK, true, false>(m, eb, w, sh, GX, GY, best, barg);
               else scan_word<TRACK, false, false>(m, eb, w, sh, GX, GY, best, barg);
