@@ -242,6 +242,25 @@ lbs_bwd_vertex_kernel(const float* __restrict__ vp, int LD, const float* __restr
   }
 }
 
+// Warp sums of TWELVE per-lane values in 13 shuffles instead of 60: at every step a lane keeps half of its values and
+// receives its partner's partial sums of that half (12 -> 6 -> 3 -> 2 -> 1), the last step adds the pair.  Twelve even lanes
+// end up owning one total each: returns it, with its index in `idx` (-1 on the other lanes).  Fixed order: deterministic.
+// (ncu, sampled backward: the 12 x 5 shuffle + add rounds per joint were 27 % of the kernel's instructions.)
+__device__ __forceinline__ float warp_sum12(const float (&a)[12], int lane, int& idx) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  float s6[6], s3[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s6[i] = (b4 ? a[i + 6] : a[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a[i] : a[i + 6], 16);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s3[i] = (b3 ? s6[i + 3] : s6[i]) + __shfl_xor_sync(0xffffffffu, b3 ? s6[i] : s6[i + 3], 8);
+  const float t0 = (b2 ? s3[2] : s3[0]) + __shfl_xor_sync(0xffffffffu, b2 ? s3[0] : s3[2], 4);
+  const float t1 = (b2 ? 0.f : s3[1]) + __shfl_xor_sync(0xffffffffu, b2 ? s3[1] : 0.f, 4);
+  float r = (b1 ? t1 : t0) + __shfl_xor_sync(0xffffffffu, b1 ? t0 : t1, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  idx = ((lane & 1) || (b2 && b1)) ? -1 : (b4 ? 6 : 0) + (b3 ? 3 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+  return r;
+}
+
 // Joint-parallel half: one warp per (sample, joint) walks the joint's vertex list (CSC of the skin weights) and
 // reduces g_A[j] = sum_v w_vj * g_vert_v (x) [v_posed_v ; 1].  No atomics: the result is order-deterministic.
 __global__ void __launch_bounds__(256)
@@ -379,14 +398,20 @@ lbs_bwd_sampled_kernel(const float* __restrict__ vp, int LD, const float* __rest
       acc[4] = fmaf(gy, x, acc[4]); acc[5] = fmaf(gy, y, acc[5]); acc[6] = fmaf(gy, z, acc[6]); acc[7] += gy;
       acc[8] = fmaf(gz, x, acc[8]); acc[9] = fmaf(gz, y, acc[9]); acc[10] = fmaf(gz, z, acc[10]); acc[11] += gz;
     }
+    if (STAGE) {                       // measured: 0.462 -> 0.421 ms at vertex_sampling = 5 (C5) ...
+      int idx;
+      const float tot = warp_sum12(acc, lane, idx);
+      if (idx >= 0) g_A[((size_t)n * kJ + j) * 12 + idx] = tot;
+    } else {                           // ... but 0.586 -> 0.660 ms at full resolution (C3): the plain rounds stay there
 #pragma unroll
-    for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
-    if (lane < 3) {
-      float4 r;
-      if (lane == 0) r = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      else if (lane == 1) r = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      else r = make_float4(acc[8], acc[9], acc[10], acc[11]);
-      reinterpret_cast<float4*>(g_A + ((size_t)n * kJ + j) * 12)[lane] = r;
+      for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
+      if (lane < 3) {
+        float4 r;
+        if (lane == 0) r = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else if (lane == 1) r = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        else r = make_float4(acc[8], acc[9], acc[10], acc[11]);
+        reinterpret_cast<float4*>(g_A + ((size_t)n * kJ + j) * 12)[lane] = r;
+      }
     }
   }
 }
