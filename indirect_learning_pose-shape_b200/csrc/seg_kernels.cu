@@ -857,14 +857,18 @@ __device__ __forceinline__ void overflow_pixel_grad(const BwdSmem& b, float2* wo
 // upstream gradient of the per-pixel loss (see SegLossArgs): lane (j & 3) of a group loads pixel j's record, the group's
 // values cross lanes by shuffle, and the score's own gradient  g (x [c == l] - y exp(s_c) - z)  is formed from the
 // recomputed score.
-template <bool C32, bool ALIGNED, bool LOSS>
+// WH: img_wh as a compile-time constant (0 = the runtime argument).  ncu's source view of the runtime-wh kernel showed
+// the per-group bookkeeping re-loading wh from the constant bank (no register to keep it at the 96-register cap) and
+// stalling on it: ~8 % of the kernel's samples.
+template <bool C32, bool ALIGNED, bool LOSS, int WH>
 __global__ void __launch_bounds__(192, LOSS ? 2 : 3)
 seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, const float* __restrict__ g_seg,
                const unsigned char* __restrict__ saved, int N, int Vs, const int* __restrict__ ptr,
-               const int* __restrict__ idx, const int* __restrict__ obase, int P, int OV, int wh,
+               const int* __restrict__ idx, const int* __restrict__ obase, int P, int OV, int wh_arg,
                float* __restrict__ g_projects, int pf_ok, const float4* __restrict__ aux,
                const float* __restrict__ g_loss) {
   extern __shared__ __align__(16) unsigned char raw[];
+  const int wh = WH ? WH : wh_arg;
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const BwdSmem b = carve_bwd(raw, OV, nwarps);
@@ -960,7 +964,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     }                                                                                                                  \
     svp += 4 * 32; pxl += 4;                                                                                           \
   } while (0)
-#define SEG_COMPUTE4(code, g, ax)                                                                                      \
+#define SEG_COMPUTE4_CORE(code, g, ax)                                                                                 \
   do {                                                                                                                 \
     if (!ALIGNED) {                                                                                                    \
       _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                                  \
@@ -1020,6 +1024,10 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
         }                                                                                                              \
       }                                                                                                                \
     }                                                                                                                  \
+  } while (0)
+#define SEG_COMPUTE4(code, g, ax)                                                                                      \
+  do {                                                                                                                 \
+    SEG_COMPUTE4_CORE(code, g, ax);                                                                                    \
     px += 4;                                                                                                           \
     if (ALIGNED) {                                                  /* next group of the row, or the warp's next row */ \
       col += 4;                                                                                                        \
@@ -1051,7 +1059,46 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     int codeA[4], codeB[4];
     float gA[4], gB[4];
     float4 axA = make_float4(0.f, 0.f, 0.f, 0.f), axB = axA;
-    if (ALIGNED) {
+    if (ALIGNED && WH != 0 && ((WH >> 2) & 1) == 0) {
+      // img_wh known at compile time with an even number of groups per row: the two register sets alternate in step with
+      // the rows, so a row is a counted loop of G/2 (A, B) pairs and the per-group cursor bookkeeping of the general
+      // schedule below (column wrap, load-cursor compare, pointer rebuild: ~60 of ~220 instructions per group) goes away.
+      // The warp's next row is taken -- and the row nwarps further requested into L2 -- at the start of a row's last
+      // pair, as late as the general schedule takes it.
+      constexpr int kPairs = WH >> 3;
+      if (rC < wh) {
+        if (kPrefetch && lane < 2 && rC + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rC + nwarps) * pf_row, pf_row);
+        SEG_LOAD4(codeA, gA, axA);
+        for (;;) {
+          int rN = wh;
+#pragma unroll 1
+          for (int pr = 0; pr < kPairs; ++pr) {
+            const bool last = pr == kPairs - 1;
+            int r = 0;
+            if (last && lane == 0) r = atomicAdd(b.next_row, 1);    // consumed after the next compute: its latency is hidden
+            SEG_LOAD4(codeB, gB, axB);
+            SEG_COMPUTE4_CORE(codeA, gA, axA);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) GP[j] = add2(GP[j], step_in);
+            if (last) {                                             // the next group is the first of the warp's next row
+              rN = __shfl_sync(0xffffffffu, r, 0);
+              if (kPrefetch && lane < 2 && rN + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rN + nwarps) * pf_row, pf_row);
+              svp = sv + (size_t)rN * wh * 32;
+              if (LOSS) { axp = ax_n + (size_t)rN * wh; glp = gl_n + (size_t)rN * wh; }
+              else gp = g_n + (size_t)rN * wh * C;
+            }
+            if (!last || rN < wh) SEG_LOAD4(codeA, gA, axA);
+            SEG_COMPUTE4_CORE(codeB, gB, axB);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) GP[j] = add2(GP[j], step_in);
+          }
+          if (rN >= wh) break;
+          rC = rN;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) GP[j] = pk2((float)j, (float)(wh - 1 - rC));
+        }
+      }
+    } else if (ALIGNED) {
       if (rL < wh) {
         if (kPrefetch && lane < 2 && rL + nwarps < wh) prefetch_l2_bulk(pf_base + (size_t)(rL + nwarps) * pf_row, pf_row);
         SEG_LOAD4(codeA, gA, axA);
@@ -1083,6 +1130,7 @@ seg_bwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #undef SEG_ADVANCE_LOAD
 #undef SEG_LOAD4
 #undef SEG_COMPUTE4
+#undef SEG_COMPUTE4_CORE
   __syncthreads();
   // fold the warps' private slots and the overflow list into the output (a vertex may sit in more than one part)
   for (int s = threadIdx.x; s < kIL * 32; s += blockDim.x) {
@@ -1177,29 +1225,33 @@ static cudaError_t launch_bwd_impl(const SmplB200Parts* p, const float* projects
   const size_t smem = bwd_smem_bytes(p->ovf, warps);
   if (smem > kMaxSmem) return cudaErrorInvalidConfiguration;
   LaunchScope scope(KID_SEG_BWD, st);
-#define SMPL_SEG_BWD(C32, AL, LO)                                                                                      \
+#define SMPL_SEG_BWD_W(C32, AL, LO, W)                                                                                 \
   do {                                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(seg_bwd_kernel<C32, AL, LO, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
-    seg_bwd_kernel<C32, AL, LO><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx,       \
-                                                              p->obase, p->P, p->ovf, wh, g_projects, pf_ok,           \
-                                                              reinterpret_cast<const float4*>(aux), g_loss);           \
+    seg_bwd_kernel<C32, AL, LO, W><<<N, warps * 32, smem, st>>>(projects, mask, g_seg, saved, N, Vs, p->ptr, p->idx,    \
+                                                                 p->obase, p->P, p->ovf, wh, g_projects, pf_ok,        \
+                                                                 reinterpret_cast<const float4*>(aux), g_loss);        \
   } while (0)
+#define SMPL_SEG_BWD(C32, AL, LO) SMPL_SEG_BWD_W(C32, AL, LO, 0)
   const void* row0 = aux ? aux : (const void*)g_seg;
   const int pf_ok = (reinterpret_cast<uintptr_t>(row0) % 16 == 0 && reinterpret_cast<uintptr_t>(saved) % 16 == 0) ? 1 : 0;
   const bool c32 = p->P == 31, al = wh % 4 == 0 && wh >= 8 && (pf_ok || p->P != 31);
   if (aux) {
-    if (c32 && al) SMPL_SEG_BWD(true, true, true);
+    if (c32 && al && wh == 48) SMPL_SEG_BWD_W(true, true, true, 48);   // the training resolution: wh folded into the code
+    else if (c32 && al) SMPL_SEG_BWD(true, true, true);
     else if (c32) SMPL_SEG_BWD(true, false, true);
     else if (al) SMPL_SEG_BWD(false, true, true);
     else SMPL_SEG_BWD(false, false, true);
   } else {
-    if (c32 && al) SMPL_SEG_BWD(true, true, false);
+    if (c32 && al && wh == 48) SMPL_SEG_BWD_W(true, true, false, 48);
+    else if (c32 && al) SMPL_SEG_BWD(true, true, false);
     else if (c32) SMPL_SEG_BWD(true, false, false);
     else if (al) SMPL_SEG_BWD(false, true, false);
     else SMPL_SEG_BWD(false, false, false);
   }
 #undef SMPL_SEG_BWD
+#undef SMPL_SEG_BWD_W
   return cudaGetLastError();
 }
 

@@ -11,7 +11,7 @@ python tools/bench_render.py --batch 64 --steps 1 --warmup 1 > $O/${T}_render_pl
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
     python bench.py --steps 2 --warmup 1 > $O/${T}_launch_ncu.log 2>&1
 # (2) full capture of the library's kernels, one step at 2048 samples
-ncu --set full --clock-control none --import-source on -k regex:smplb200 -o $O/${T}_prof_step2048 -f \
+ncu --set full --clock-control none --import-source on -k "regex:pose_|blend_|lbs_|mask_|seg_|split3" -o $O/${T}_prof_step2048 -f \
     python tools/prof_step.py --batch 2048 --steps 1 > $O/${T}_prof_ncu.log 2>&1
 # (3) full capture of the visualiser's two kernels
 ncu --set full --clock-control none --import-source on -k regex:render_ -c 2 -o $O/${T}_prof_render -f \
