@@ -337,7 +337,10 @@ def run_c5(args, rank, world, local_rank, torch, dist, dev, h: Harness):
     use_graph = args.graph == "on" or (args.graph == "auto" and distributed)
     graphed = None
     if use_graph:
-        graphed = pkg.GraphedDecoderStep(dec, B, device=dev)
+        # small shards: slices on separate streams inside the graph, so one slice's partly filled last wave of blocks runs
+        # beside the other slices' kernels (measured on one GPU at the 8-GPU shard size, profiles/r2_v10_micro_batches.jsonl)
+        mb = args.micro_batches if args.micro_batches > 0 else (2 if B <= 4096 else 1)
+        graphed = pkg.GraphedDecoderStep(dec, B, device=dev, micro_batches=mb)
         graphed.params.copy_(params_dev)
         graphed.g_seg.copy_(g_seg)
         g_seg = graphed.g_seg                                        # one copy of the 295 KB/sample upstream gradient
@@ -469,7 +472,7 @@ def run_c5(args, rank, world, local_rank, torch, dist, dev, h: Harness):
                                             "lives on the device); params in / g_params out are the host copies of e2e",
                        "l2": "per-step working set %.1f GB >> 126 MB L2 (inputs larger than L2)" % (step_bytes * B / 1e9),
                        "clock_ramp_s": RAMP_S, "api": "SmplDecoder(fused=%s)" % (not args.no_fused),
-                       "cuda_graph": bool(use_graph),
+                       "cuda_graph": bool(use_graph), "micro_batches": graphed.micro_batches if graphed else 1,
                        "parallelism": "one 16384 batch in contiguous shards, no collective on the path" if
                        args.scaling == "strong" else "16384 samples per GPU, no collective on the path"},
             "clocks": clocks.summary(),
@@ -612,6 +615,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as a CUDA graph in the timed region (auto: when the batch is sharded, N > 1)")
+    ap.add_argument("--micro-batches", type=int, default=0,
+                    help="slices of the per-GPU batch captured on separate streams of the CUDA graph (0 = auto)")
     ap.add_argument("--no-fused", action="store_true", help="chain the modular ops instead of smpl_b200_full_fwd/_bwd")
     ap.add_argument("--no-validate", action="store_true", help="skip the NCCL all-gather validation leg at N > 1")
     ap.add_argument("--cpu-sample", type=int, default=16, help="samples per CPU-port step")

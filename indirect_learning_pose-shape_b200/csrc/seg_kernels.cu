@@ -81,24 +81,28 @@ __device__ __forceinline__ float dist2(float u, float v, float gx, float gy) {
   return __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
 }
 
+// Layout: the fixed-size fields first, so that their shared addresses are the block's base plus a compile-time constant
+// (the forward's per-part loop rebuilt `wh * wh * 2 + (E + 2) * 16 + ...` for every descriptor load when they followed
+// the variable-size arrays: ~8 of its ~63 fixed instructions per (tile, part)).
+constexpr size_t kSegFixed = 32 * 16 + 2 * 32 * 4 + 2 * 36 * 4 + 16;   // pdesc, lcount, lbase, pptr, woff, {ghead, nheavy, next_tile}
 __device__ __forceinline__ SegSmem carve(unsigned char* raw, int E, int wh) {
   SegSmem sm;
   size_t off = 0;
-  sm.ent = reinterpret_cast<float4*>(raw + off) + 1; off += (size_t)(E + 2) * 16;   // ent[-1], ent[E]: readable dummies
-  sm.head = reinterpret_cast<unsigned short*>(raw + off); off += ((size_t)wh * wh * 2 + 15) & ~(size_t)15;
+  sm.pdesc = reinterpret_cast<int4*>(raw + off); off += 32 * 16;
   sm.lcount = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.lbase = reinterpret_cast<int*>(raw + off); off += 32 * 4;
   sm.pptr = reinterpret_cast<int*>(raw + off); off += 36 * 4;
   sm.woff = reinterpret_cast<int*>(raw + off); off += 36 * 4;
-  sm.pdesc = reinterpret_cast<int4*>(raw + off); off += 32 * 16;
   sm.ghead = reinterpret_cast<int*>(raw + off);
   sm.nheavy = sm.ghead + 1;
   sm.next_tile = sm.ghead + 2; off += 16;
+  sm.head = reinterpret_cast<unsigned short*>(raw + off); off += ((size_t)wh * wh * 2 + 15) & ~(size_t)15;
+  sm.ent = reinterpret_cast<float4*>(raw + off) + 1; off += (size_t)(E + 2) * 16;   // ent[-1], ent[E]: readable dummies
   sm.rest = raw + off;
   return sm;
 }
 size_t seg_base_smem(int E, int wh) {
-  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 2 + 15) & ~(size_t)15) + 2 * 32 * 4 + 2 * 36 * 4 + 32 * 16 + 16;
+  return (size_t)(E + 2) * 16 + (((size_t)wh * wh * 2 + 15) & ~(size_t)15) + kSegFixed;
 }
 
 // Split the sample's part vertices into weight classes (one warp per part, ballot compaction).
@@ -295,6 +299,27 @@ __device__ __forceinline__ unsigned long long lds_b64(uint32_t a) {
 __device__ __forceinline__ unsigned long long lds_b64_nv(uint32_t a) {
   unsigned long long r;
   asm("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(a));
+  return r;
+}
+// (volatile: the survivor words are rewritten per tile in the per-warp-row mode and the descriptors by classify; the
+// statement must stay behind the __syncwarp / __syncthreads that publishes them and must not be merged across tiles)
+__device__ __forceinline__ unsigned lds_u32(uint32_t a) {
+  unsigned r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+  int4 r;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+// the forward's per-lane staging slots: written and read by the same lane, ordered by the volatile qualifier
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a) : "memory");
   return r;
 }
 __device__ __forceinline__ void sts_b64(uint32_t a, unsigned long long v) {
@@ -517,16 +542,20 @@ __device__ __noinline__ float4 loss_pixel(float Zp, float elp, float bg, int lab
 // (The LOSS variant carries twelve more live values through the part loop -- softmax denominators, the label's
 // numerator, the labels -- and spilled them at the 80 registers of four blocks per SM: it is compiled without that cap
 // and runs three 6-warp blocks per SM.)
-template <bool TRACK, bool LOSS>
+// WH: img_wh as a compile-time constant (0 = the runtime argument); C32: 31 parts + background = one 128-byte line per pixel.
+// The training resolution (48, a whole number of 16 x 8 tiles) compiles without bounds checks and with constant tile counts.
+template <bool TRACK, bool LOSS, int WH, bool C32>
 __global__ void __launch_bounds__(LOSS ? 288 : 256, LOSS ? 2 : 3)   // LOSS: 112 registers (three 6-warp blocks per SM), 8-warp launches allowed
 seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, int N, int Vs,
-               const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh,
+               const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh_arg,
                float* __restrict__ seg, unsigned char* __restrict__ saved, const SegLossArgs la, int KW, int kw_rows) {
   extern __shared__ __align__(16) unsigned char raw[];
+  const int wh = WH ? WH : wh_arg;
+  constexpr bool kWhole = WH != 0 && WH % kTW == 0 && WH % kTH == 0;   // no partial tiles: every pixel of a tile is in the image
   const SegSmem sm = carve(raw, E, wh);
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int C = P + 1;
+  const int C = C32 ? 32 : P + 1;
   const int tiles_x = (wh + kTW - 1) / kTW, tiles_y = (wh + kTH - 1) / kTH, ntiles = tiles_x * tiles_y;
   const int t0 = (int)(((long long)ntiles * blockIdx.y) / gridDim.y);
   const int t1 = (int)(((long long)ntiles * (blockIdx.y + 1)) / gridDim.y);
@@ -540,6 +569,9 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
   // per-lane staging of one chunk: stage[(sub*4 + q)*32 + lane]  (lane-contiguous: conflict-free, no sync needed)
   float* stage = reinterpret_cast<float*>(sm.rest + (((size_t)kw_rows * KW * 4 + 15) & ~(size_t)15)) +
                  (size_t)warp * (8 * kNB * 32) + lane;
+  // shared-window addresses of what the per-part loop touches (sm.pdesc sits at the block's base, see carve)
+  const uint32_t pdesc_sa = (uint32_t)__cvta_generic_to_shared(raw);
+  const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
 
   // Tiles are handed to the warps on demand (the first nwarps statically), the image's centre columns first: they hold
   // the body and cost the most, and a fixed tile -> warp map gave all of them to the same two warps.
@@ -558,6 +590,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
     const float gx0 = (float)c0, gx1 = (float)(c0 + 1), gy0 = (float)r0, gy1 = (float)(r0 + 1);
     const f32x2 GX = pk2(gx0, gx1), GY = pk2(gy0, gy1);
     const unsigned* kw = kw_base + (size_t)(kw_table ? ti - t0 : warp) * KW;
+    const uint32_t kw_sa = (uint32_t)__cvta_generic_to_shared(kw);
     if (!kw_table) prune_tile(sm, kw_base + (size_t)warp * KW, P, lane, (float)(tx * kTW) + kTileHW, (float)(ty * kTH) + kTileHH);
 
     bool blk_slow = ghead >= 0;                                      // any heavy vertex chained to one of my pixels?
@@ -565,7 +598,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #pragma unroll
       for (int q = 0; q < kNB; ++q) {
         const int r = r0 + (q >> 1), c = c0 + (q & 1);
-        if (c < wh && r < wh) blk_slow |= sm.head[r * wh + c] != kNone16;
+        if (kWhole || (c < wh && r < wh)) blk_slow |= sm.head[r * wh + c] != kNone16;
       }
     }
     float S[kNB];
@@ -579,14 +612,14 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
       for (int q = 0; q < kNB; ++q) {
         const int r = r0 + (q >> 1), c = c0 + (q & 1);
         Zs[q] = 0.f; el[q] = 0.f;
-        lab[q] = (r < wh && c < wh) ? (int)la.labels[(size_t)n * wh * wh + (size_t)(wh - 1 - r) * wh + c] : 0;
+        lab[q] = (kWhole || (r < wh && c < wh)) ? (int)la.labels[(size_t)n * wh * wh + (size_t)(wh - 1 - r) * wh + c] : 0;
       }
     }
 
     // channel chunks 1, 2, 3, then chunk 0 last: its channel 0 (background) needs the sum over all parts
     for (int cc = 1; cc <= 4; ++cc) {
       const int chunk = cc & 3;
-      if (chunk * 8 >= C) continue;
+      if (!C32 && chunk * 8 >= C) continue;
       unsigned cw[2][kNB];                                           // packed saved bytes, channels 0-3 / 4-7 of the chunk
 #pragma unroll
       for (int q = 0; q < kNB; ++q) { cw[0][q] = 0u; cw[1][q] = 0u; }
@@ -596,13 +629,14 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
         for (int s4 = 0; s4 < 4; ++s4) {
           const int sub = half * 4 + s4;
           const int ch = chunk * 8 + sub;
-          if (ch == 0 || ch >= C) {                                  // background is filled in after the loop
+          const uint32_t st_sa = stage_sa + (uint32_t)sub * (kNB * 32 * 4);
+          if ((half == 0 && ch == 0) || (!C32 && ch >= C)) {         // background is filled in after the loop
 #pragma unroll
-            for (int q = 0; q < kNB; ++q) stage[(sub * kNB + q) * 32] = 0.f;
+            for (int q = 0; q < kNB; ++q) sts_f32(st_sa + q * 128, 0.f);
             continue;
           }
-          const int4 pd = sm.pdesc[ch - 1];                          // {entry address, survivor words, row index of word 1 - 1}
-          const unsigned m0 = kw[ch - 1];                            // the part's first survivor word: independent of pd
+          const int4 pd = lds_v4(pdesc_sa + (uint32_t)(ch - 1) * 16u);   // {entry address, survivor words, row index of word 1 - 1}
+          const unsigned m0 = lds_u32(kw_sa + (uint32_t)(ch - 1) * 4u);  // the part's first survivor word: independent of pd
           const unsigned sh = 8u * (unsigned)s4;
           float best[kNB];
           unsigned barg[kNB];                                        // arg-min code, already shifted to its byte
@@ -627,7 +661,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #pragma unroll
             for (int q = 0; q < kNB; ++q) {
               const int r = r0 + (q >> 1), c = c0 + (q & 1);
-              if (c < wh && r < wh) {
+              if (kWhole || (c < wh && r < wh)) {
                 const int hd = (any_heavy && sm.head[r * wh + c] != kNone16) ? (int)sm.head[r * wh + c] : -1;
                 if (hd >= 0 || ghead >= 0) {
                   const float ss = slow_pixel_score(sm, sm.pptr[ch - 1], sm.pptr[ch], (q & 1) ? gx1 : gx0, (q >> 1) ? gy1 : gy0, hd, ghead, best[q]);
@@ -638,7 +672,7 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
           }
 #pragma unroll
           for (int q = 0; q < kNB; ++q) {
-            stage[(sub * kNB + q) * 32] = sc[q];
+            sts_f32(st_sa + q * 128, sc[q]);
             S[q] += sc[q];
             if (TRACK) cw[half][q] |= barg[q];
             if (LOSS) {                                              // softmax numerator of this channel (scores are in [0, 1]: no max shift)
@@ -653,12 +687,12 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #pragma unroll
         for (int q = 0; q < kNB; ++q) {
           const float bg = 1.0f - fminf(fmaxf(S[q], 0.f), 1.f);      // :61-64
-          stage[q * 32] = bg;
+          sts_f32(stage_sa + q * 128, bg);
           const bool gate = S[q] >= 0.f && S[q] <= 1.f;              // clip gate (inclusive), for the backward
           if (TRACK) cw[0][q] |= gate ? 1u : 0u;
           if (LOSS) {
             const int r = r0 + (q >> 1), c = c0 + (q & 1);
-            if (r < wh && c < wh) {
+            if (kWhole || (r < wh && c < wh)) {
               const size_t opx = (size_t)n * wh * wh + (size_t)(wh - 1 - r) * wh + c;
               la.aux[opx] = loss_pixel(Zs[q], el[q], bg, lab[q], C, gate, la.class_w, la.gamma, la.loss + opx);
             }
@@ -669,14 +703,14 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
 #pragma unroll
       for (int q = 0; q < kNB; ++q) {
         const int r = r0 + (q >> 1), c = c0 + (q & 1);
-        if (r < wh && c < wh) {
+        if (kWhole || (r < wh && c < wh)) {
           const size_t opx = (size_t)(wh - 1 - r) * wh + c;
           if (seg_n) {
             float* o = seg_n + opx * C + chunk * 8;
             float v8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v8[e] = stage[(e * kNB + q) * 32];
-            if (C == 32) {
+            for (int e = 0; e < 8; ++e) v8[e] = lds_f32(stage_sa + (e * kNB + q) * 128);
+            if (C32) {
               st_global_v8(o, v8);
             } else {
 #pragma unroll
@@ -1187,15 +1221,22 @@ cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const
   dim3 grid(N, split);
   LaunchScope scope(KID_SEG_FWD, st);
   const SegLossArgs none{nullptr, nullptr, 0.f, nullptr, nullptr};
+#define SMPL_SEG_FWD_K(TR, LO, W, C3)                                                                                   \
+  do {                                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(seg_fwd_kernel<TR, LO, W, C3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                    \
+    seg_fwd_kernel<TR, LO, W, C3><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg, \
+                                                                  saved, la ? *la : none, KW, kw_rows);               \
+  } while (0)
+  // the training resolution with the 31-part table: img_wh and the channel count folded into the code
 #define SMPL_SEG_FWD(TR, LO)                                                                                           \
   do {                                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(seg_fwd_kernel<TR, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                    \
-    seg_fwd_kernel<TR, LO><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg,  \
-                                                           saved, la ? *la : none, KW, kw_rows);                       \
+    if (wh == 48 && p->P == 31) SMPL_SEG_FWD_K(TR, LO, 48, true);                                                      \
+    else SMPL_SEG_FWD_K(TR, LO, 0, false);                                                                             \
   } while (0)
   if (la) { if (saved) SMPL_SEG_FWD(true, true); else SMPL_SEG_FWD(false, true); }
   else { if (saved) SMPL_SEG_FWD(true, false); else SMPL_SEG_FWD(false, false); }
+#undef SMPL_SEG_FWD_K
 #undef SMPL_SEG_FWD
   return cudaGetLastError();
 }

@@ -481,6 +481,19 @@ def test_fused_decoder_backward_matches_modular(pkg, host_model, parts_by_vs, ma
     assert float((got - grads[False]).abs().max()) <= 1e-5 * scale
     got2 = gs(t(p) * 1.0, 2.0 * g).clone()                               # new inputs through the static buffers
     assert float((got2 - 2.0 * grads[False]).abs().max()) <= 2e-5 * scale
+    # the same step cut into three slices on three streams inside one graph (fork / join): samples are independent.
+    # (192 = 3 x 64: every slice stays on the dense-batch tensor-core blend, like the whole batch.)
+    n3 = 192
+    p3 = make_params(n3, wh, seed=84)
+    g3 = torch.randn((n3, wh, wh, 32), device=dev(), generator=torch.Generator(device=dev()).manual_seed(6))
+    gs1 = pkg.GraphedDecoderStep(dec, n3, device=dev())
+    ref3 = gs1(t(p3), g3).clone()
+    gs3 = pkg.GraphedDecoderStep(dec, n3, device=dev(), micro_batches=3)
+    got3 = gs3(t(p3), g3).clone()
+    assert gs3.micro_batches == 3 and gs3.launches_per_step == 3 * gs1.launches_per_step
+    assert float((got3 - ref3).abs().max()) <= 1e-5 * float(ref3.abs().max())
+    assert torch.equal(gs3.out["projects"], gs1.out["projects"])
+    assert torch.equal(gs3.out["seg"].argmax(-1), gs1.out["seg"].argmax(-1))
 
 
 def test_seg_duplicate_entries_tie_gradient(pkg):
