@@ -16,9 +16,10 @@ gradients over NCCL and rank 0 compares them with the same batch decoded on its 
                pair on the launching stream around every launch) against the measured HBM peak of MEASURED_PEAKS.json
   cpu_baseline the oracle port (torch-CPU twin of the reference's brute-force algorithm) on a bounded sample, rank 0
 
-At N = 1 the timed region is the eager public API with the event profiler riding along.  At N > 1 (2048..8192 samples per
-GPU: 1-4 ms of kernels per step) the step is captured once as a CUDA graph (GraphedDecoderStep) and the timed region
-replays it; the per-kernel durations then come from an eager pass of the same K steps right after (`--graph` overrides).
+The step is captured once as a CUDA graph (GraphedDecoderStep: the public SmplDecoder forward + backward, the per-GPU
+batch cut into two slices on two streams inside the graph) and the timed region replays it; the per-kernel durations then
+come from an eager pass of the same K steps right after, with the library's event profiler (`--graph off`: the eager API
+in the timed region itself, profiler riding along).
 
 `--config c2|c3|c4` runs BASELINE.json's secondary configurations with the same contract keys.
 `--impl reference` times the CPU port alone as the reference arm (the reference itself is Python 2.7 / TF 1.x and cannot
@@ -334,12 +335,14 @@ def run_c5(args, rank, world, local_rank, torch, dist, dev, h: Harness):
         out["seg"].backward(g_seg)
         return x.grad, out
 
-    use_graph = args.graph == "on" or (args.graph == "auto" and distributed)
+    use_graph = args.graph in ("on", "auto")
     graphed = None
     if use_graph:
-        # small shards: slices on separate streams inside the graph, so one slice's partly filled last wave of blocks runs
-        # beside the other slices' kernels (measured on one GPU at the 8-GPU shard size, profiles/r2_v10_micro_batches.jsonl)
-        mb = args.micro_batches if args.micro_batches > 0 else (2 if B <= 4096 else 1)
+        # two slices on separate streams inside the graph: one slice's partly filled last wave of blocks (and its
+        # issue-bound seg kernels) run beside the other slice's kernels.  Measured at 2048 / 4096 / 8192 / 16384 samples
+        # per GPU: -9.0 / -4.9 / -4.3 / -1.5 % against one slice; 3 and 4 slices no better
+        # (profiles/r2_v10_micro_batches.jsonl)
+        mb = args.micro_batches if args.micro_batches > 0 else 2
         graphed = pkg.GraphedDecoderStep(dec, B, device=dev, micro_batches=mb)
         graphed.params.copy_(params_dev)
         graphed.g_seg.copy_(g_seg)
@@ -614,7 +617,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="global batch (strong) or samples per GPU (weak)")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step as a CUDA graph in the timed region (auto: when the batch is sharded, N > 1)")
+                    help="replay the step as a CUDA graph in the timed region (auto = on; off: the eager API)")
     ap.add_argument("--micro-batches", type=int, default=0,
                     help="slices of the per-GPU batch captured on separate streams of the CUDA graph (0 = auto)")
     ap.add_argument("--no-fused", action="store_true", help="chain the modular ops instead of smpl_b200_full_fwd/_bwd")
