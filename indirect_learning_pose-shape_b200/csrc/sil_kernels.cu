@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(kSilWarps * 32)
 sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, int N, int Vs, int wh, int B, int G,
            int dense, float* __restrict__ out, unsigned short* __restrict__ saved) {
   extern __shared__ __align__(16) unsigned char raw[];
+  __shared__ int next_tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   SilSmem sm = carve_sil(raw, Vs, G * G, nwarps, BWD);
   sm.saved = BWD ? nullptr : saved;
@@ -441,6 +442,10 @@ sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, 
   gr.B = B; gr.G = G; gr.S = (G + kStrip - 1) / kStrip; gr.wh = wh;
   if (BWD)
     for (int i = threadIdx.x; i < Vs * 2; i += blockDim.x) sm.gacc[i] = 0.f;
+  if (threadIdx.x == 0) {                                 // first tile handed out on demand (see the tile loop); ordered
+    const int T = kStrip * B, tt = (wh + T - 1) / T;      // before its first use by the barriers of bin_vertices
+    next_tile = (int)(((long long)tt * tt * blockIdx.y) / gridDim.y) + nwarps;
+  }
   bin_vertices(sm, projects + (size_t)n * Vs * 3, Vs, gr);
   // from here on `scratch` holds the per-warp survivor lists
   unsigned short* L1 = reinterpret_cast<unsigned short*>(sm.scratch) + (size_t)warp * (kCap1 + kCap2 + kCap3);
@@ -450,8 +455,20 @@ sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, 
   const int ttx = (wh + TT - 1) / TT, ntop = ttx * ttx;
   const int t0 = (int)(((long long)ntop * blockIdx.y) / gridDim.y);
   const int t1 = (int)(((long long)ntop * (blockIdx.y + 1)) / gridDim.y);
-  for (int t = t0 + warp; t < t1; t += nwarps) {
-    const int tx0 = (t % ttx) * TT, ty0 = (t / ttx) * TT;
+  // Top tiles are handed to the warps on demand, the image's centre first: the body sits there and its tiles cost many
+  // times a background tile.  (A static t -> warp map with t = row * ttx + column gave warp w the SAME column in every
+  // row -- all of the body to two or three of the sixteen warps: ncu had 14.7 % warp occupancy against the 25 % one
+  // block per SM allows.)
+  for (int k = t0 + warp; k < t1;) {
+    const int ka = k / ttx, kb = k - ka * ttx;
+    const int tyi = (ttx >> 1) + ((ka & 1) ? -((ka + 1) >> 1) : (ka >> 1));
+    const int txi = (ttx >> 1) + ((kb & 1) ? -((kb + 1) >> 1) : (kb >> 1));
+    {
+      int nk = 0;
+      if (lane == 0) nk = atomicAdd(&next_tile, 1);
+      k = __shfl_sync(0xffffffffu, nk, 0);
+    }
+    const int tx0 = txi * TT, ty0 = tyi * TT;
     const int tw = min(TT, wh - tx0), th = min(TT, wh - ty0);    // the part of the tile inside the image
     int n1 = -1;
     if (!dense) {
