@@ -6,10 +6,14 @@
 //   out[n, wh-1-r, c, :] = [bg, s_0 .. s_30]          :66-68   (rows flipped)
 //
 // exp, sqrt and the multiply by w are monotone, so  max_i exp(-(d_i w_i)) = exp(-min_i (d_i w_i)): both directions are
-// an exact weighted-nearest-vertex query: the arg-min over fp32 squared distances, computed everywhere with tf.norm's own
-// roundings, fl(fl(du^2) + fl(dv^2)) (round 1's hot loop used fma(du, du, fl(dv^2)), one rounding fewer; round 2 measured
-// both forms -- tools/q13_ab.py: 2.770 vs 2.773 ms, identical label and score agreement with the oracle -- and kept the
-// reference's).  Vertices are split by weight once per sample:
+// an exact weighted-nearest-vertex query: the arg-min over fp32 squared distances, everywhere with tf.norm's own
+// roundings, fl(fl(du^2) + fl(dv^2)).  The scalar paths spell that with __fmul_rn / __fadd_rn.  The forward's packed hot
+// loop cannot simply write mul.rn.f32x2 then add.rn.f32x2: ptxas 12.9 contracts that pair into one FFMA2 (the scalar .rn
+// forms are never contracted, the f32x2 ones are -- a two-line kernel shows it), which is fma(du, du, fl(dv^2)), one
+// rounding fewer; rounds 1 and 2 ran like that (round 2's "A/B of both forms", tools/q13_ab.py, timed the same SASS
+// twice).  The loop now forms the sum as fma.rn.f32x2(fl(du^2), one, fl(dv^2)) with `one` a kernel parameter that ptxas can
+// neither drop nor fuse: the reference's two roundings for one more FMUL2 per candidate (measured: 2.548 -> 2.574 ms; label
+// mismatch 0 and scores within 3.6e-7 of the oracle either way, tools/seg_ab.py).  Vertices are split by weight once per sample:
 //   light    w == 1        one per occupied z-buffer cell after compute_mask; min over SQUARED distances in the hot loop
 //   heavy    w >= 256      d*w > 128 unless d < 0.5, and exp(-128) is exactly 0 in fp32, so a heavy vertex can only
 //                           reach the one pixel it rounds to: chained per pixel, visited by that pixel alone
@@ -427,14 +431,20 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return r;
 }
 // Squared distances of one vertex to a lane's 2 x 2 pixel block, GX = (gx0, gx1), GY = (gy0, gy1):
-// d2[q] = fl(fl(du^2) + fl(dv^2)), six packed instructions for the four pixels.
-__device__ __forceinline__ void block_d2(float2 e, f32x2 GX, f32x2 GY, float (&d2)[kNB]) {
+// d2[q] = fl(fl(du^2) + fl(dv^2)): two FADD2, two FMUL2, two FFMA2 for the four pixels.
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void block_d2(float2 e, f32x2 GX, f32x2 GY, float (&d2)[kNB], f32x2 ONE2) {
   const f32x2 dx = sub2(pk2(e.x, e.x), GX), dy = sub2(pk2(e.y, e.y), GY);
   float vy0, vy1;
   upk2(mul2(dy, dy), vy0, vy1);
-  const f32x2 dx2 = mul2(dx, dx);                                  // fl(du^2), then fl(. + fl(dv^2)): tf.norm's own roundings
-  upk2(add2(dx2, pk2(vy0, vy0)), d2[0], d2[1]);
-  upk2(add2(dx2, pk2(vy1, vy1)), d2[2], d2[3]);
+  const f32x2 dx2 = mul2(dx, dx);                                  // fl(du^2), kept as a product of its own (see the header)
+  // fl(du^2) * 1 + fl(dv^2), ONE2 = (1, 1) from a kernel parameter
+  upk2(fma2(dx2, ONE2, pk2(vy0, vy0)), d2[0], d2[1]);
+  upk2(fma2(dx2, ONE2, pk2(vy1, vy1)), d2[2], d2[3]);
 }
 
 // One survivor against a lane's 2 x 2 pixel block: best[q] = min squared distance, barg[q] = code of its arg-min,
@@ -442,9 +452,9 @@ __device__ __forceinline__ void block_d2(float2 e, f32x2 GX, f32x2 GY, float (&d
 // only words 7 and up can hold them.  FIRST: the block's first candidate of this part: no comparison needed.
 template <bool TRACK, bool CLAMP, bool FIRST>
 __device__ __forceinline__ void compare_vertex(float2 e, unsigned b, int w, unsigned sh, unsigned shmul, unsigned wcode,
-                                               f32x2 GX, f32x2 GY, float (&best)[kNB], unsigned (&barg)[kNB]) {
+                                               f32x2 GX, f32x2 GY, float (&best)[kNB], unsigned (&barg)[kNB], f32x2 ONE2) {
   float d2[kNB];
-  block_d2(e, GX, GY, d2);
+  block_d2(e, GX, GY, d2, ONE2);
   if (FIRST) {
     const unsigned vcode = CLAMP ? (unsigned)min(w * 32 + (int)b + 1, 255) << sh : b * shmul + wcode;
 #pragma unroll
@@ -466,7 +476,7 @@ __device__ __forceinline__ void compare_vertex(float2 e, unsigned b, int w, unsi
 // FRESH: best / barg hold nothing yet: the word's first survivor initialises them (an empty word leaves kBigD2 / 0).
 template <bool TRACK, bool CLAMP, bool FRESH>
 __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsigned sh, f32x2 GX, f32x2 GY,
-                                          float (&best)[kNB], unsigned (&barg)[kNB]) {
+                                          float (&best)[kNB], unsigned (&barg)[kNB], f32x2 ONE2) {
   const unsigned shmul = 1u << sh, wcode = (unsigned)(w * 32 + 1) << sh;
   if (FRESH) {
     if (m == 0u) {
@@ -476,7 +486,7 @@ __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsign
     }
     const unsigned b0 = bfind_u32(m);
     m ^= 1u << b0;
-    compare_vertex<TRACK, CLAMP, true>(lds_f2_nv(eb + b0 * 16u), b0, w, sh, shmul, wcode, GX, GY, best, barg);
+    compare_vertex<TRACK, CLAMP, true>(lds_f2_nv(eb + b0 * 16u), b0, w, sh, shmul, wcode, GX, GY, best, barg, ONE2);
   }
   // survivors two at a time: both coordinate loads are in flight before either vertex is compared
   while (m) {
@@ -487,10 +497,10 @@ __device__ __forceinline__ void scan_word(unsigned m, uint32_t eb, int w, unsign
       const unsigned b1 = bfind_u32(m);
       m ^= 1u << b1;
       const float2 e1 = lds_f2_nv(eb + b1 * 16u);
-      compare_vertex<TRACK, CLAMP, false>(e0, b0, w, sh, shmul, wcode, GX, GY, best, barg);
-      compare_vertex<TRACK, CLAMP, false>(e1, b1, w, sh, shmul, wcode, GX, GY, best, barg);
+      compare_vertex<TRACK, CLAMP, false>(e0, b0, w, sh, shmul, wcode, GX, GY, best, barg, ONE2);
+      compare_vertex<TRACK, CLAMP, false>(e1, b1, w, sh, shmul, wcode, GX, GY, best, barg, ONE2);
     } else {
-      compare_vertex<TRACK, CLAMP, false>(e0, b0, w, sh, shmul, wcode, GX, GY, best, barg);
+      compare_vertex<TRACK, CLAMP, false>(e0, b0, w, sh, shmul, wcode, GX, GY, best, barg, ONE2);
     }
   }
 }
@@ -548,8 +558,10 @@ template <bool TRACK, bool LOSS, int WH, bool C32>
 __global__ void __launch_bounds__(LOSS ? 288 : 256, LOSS ? 2 : 3)   // LOSS: 112 registers (three 6-warp blocks per SM), 8-warp launches allowed
 seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mask, int N, int Vs,
                const int* __restrict__ ptr, const int* __restrict__ idx, int P, int E, int wh_arg,
-               float* __restrict__ seg, unsigned char* __restrict__ saved, const SegLossArgs la, int KW, int kw_rows) {
+               float* __restrict__ seg, unsigned char* __restrict__ saved, const SegLossArgs la, int KW, int kw_rows,
+               float one) {
   extern __shared__ __align__(16) unsigned char raw[];
+  const f32x2 ONE2 = pk2(one, one);
   const int wh = WH ? WH : wh_arg;
   constexpr bool kWhole = WH != 0 && WH % kTW == 0 && WH % kTH == 0;   // no partial tiles: every pixel of a tile is in the image
   const SegSmem sm = carve(raw, E, wh);
@@ -642,15 +654,15 @@ seg_fwd_kernel(const float* __restrict__ projects, const float* __restrict__ mas
           unsigned barg[kNB];                                        // arg-min code, already shifted to its byte
           // survivors are visited from the highest index down and replace on <=, so the LOWEST index wins exact ties
           if (pd.y == 1) {                                           // at most 32 visible vertices: the common case
-            scan_word<TRACK, false, true>(m0, (uint32_t)pd.x, 0, sh, GX, GY, best, barg);
+            scan_word<TRACK, false, true>(m0, (uint32_t)pd.x, 0, sh, GX, GY, best, barg, ONE2);
           } else {
 #pragma unroll
             for (int q = 0; q < kNB; ++q) { best[q] = kBigD2; barg[q] = 0u; }
             for (int w = pd.y; w-- > 0;) {
               const unsigned m = w ? kw[pd.z + w] : m0;              // same address on every lane: broadcast
               const uint32_t eb = (uint32_t)pd.x + (uint32_t)(w * 32) * 16u;
-              if (TRACK && w >= 7) scan_word<TRACK, true, false>(m, eb, w, sh, GX, GY, best, barg);
-              else scan_word<TRACK, false, false>(m, eb, w, sh, GX, GY, best, barg);
+              if (TRACK && w >= 7) scan_word<TRACK, true, false>(m, eb, w, sh, GX, GY, best, barg, ONE2);
+              else scan_word<TRACK, false, false>(m, eb, w, sh, GX, GY, best, barg, ONE2);
             }
           }
           float sc[kNB];
@@ -1226,7 +1238,7 @@ cudaError_t launch_fwd_impl(const SmplB200Parts* p, const float* projects, const
     cudaError_t e = cudaFuncSetAttribute(seg_fwd_kernel<TR, LO, W, C3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                    \
     seg_fwd_kernel<TR, LO, W, C3><<<grid, warps * 32, smem, st>>>(projects, mask, N, Vs, p->ptr, p->idx, p->P, p->E, wh, seg, \
-                                                                  saved, la ? *la : none, KW, kw_rows);               \
+                                                                  saved, la ? *la : none, KW, kw_rows, 1.0f);               \
   } while (0)
   // the training resolution with the 31-part table: img_wh and the channel count folded into the code
 #define SMPL_SEG_FWD(TR, LO)                                                                                           \
