@@ -35,10 +35,13 @@ namespace {
 
 constexpr int kMaxGrid = 64;        // fine grid: at most kMaxGrid x kMaxGrid cells
 constexpr int kStrip = 8;           // cells per strip; a top tile is kStrip x kStrip cells
-constexpr int kCap1 = 1024, kCap2 = 512, kCap3 = 256;   // survivor lists per warp (sorted positions, 16 bits each)
+constexpr int kCap1 = 1536, kCap2 = 512, kCap3 = 256;   // survivor lists per warp (sorted positions, 16 bits each)
 constexpr int kLeafMax = 8;         // a 16x8 sub-tile with at most this many survivors is evaluated directly
 constexpr float kMargin = 0.01f, kRel = 4e-6f;          // pruning margin: 0.01 px^2 + 4e-6 d^2 (>> fp32 rounding)
-constexpr int kSilWarps = 32;   // measured at 256x256, 6890 vertices: 16 warps (top-tile lists of 2048) 9.51 ms per 2048 samples, 32 warps (1024) 8.26
+constexpr int kSilWarps = 32;   // measured at 256x256, 6890 vertices, ms per 2048 samples (lists kCap1/kCap2/kCap3): 16 warps 2048/512/256
+                                // 9.51; 32 warps 1024/512/256 8.26, 1536/512/256 7.51, 1280/384/256 7.52, 1728/384/192 7.90,
+                                // 1920/256/128 9.50 (a tile whose list overflows falls back to the ring search: a third of
+                                // the kernel's samples at 1024); a 128 x 128 cell grid with 16-pixel top tiles 11.9
 
 struct SilSmem {
   float2* pts;             // [Vs] vertices sorted by cell
