@@ -528,6 +528,51 @@ def test_seg_duplicate_entries_tie_gradient(pkg):
     assert np.all(got[:, 7] == 0) and np.abs(ref64[:, 3] - ref64[:, 7]).max() <= 1e-12 * scale   # first arg-max vs even split
 
 
+def test_seg_hot_loop_keeps_tf_norm_roundings(pkg):
+    """Q13: tf.norm forms d2 = fl(fl(du^2) + fl(dv^2)) (projects_to_seg.py:52-53); fma(du, du, fl(dv^2)) -- what ptxas makes
+    of a packed mul.rn + add.rn pair -- has one rounding fewer.  Three (vertex A, vertex B, pixel) triples found by search
+    on the CPU where the two forms order the pair DIFFERENTLY: with the reference's roundings A is nearer, with the fused
+    form B.  The rasteriser's packed hot loop must pick A (the whole gradient of that pixel lands on A, none on B); rounds 1
+    and 2 picked B."""
+    f32 = np.float32
+    cases = [(16.4890193939209, 18.45115852355957, 17.89776611328125, 13.83559513092041),
+             (14.508923530578613, 23.694658279418945, 11.48696517944336, 15.41930103302002),
+             (24.387985229492188, 21.174949645996094, 14.013175010681152, 17.91790199279785)]
+    gx, gy, wh, Vs = 20, 17, 48, 33
+
+    def two(u, v):
+        du, dv = f32(f32(u) - f32(gx)), f32(f32(v) - f32(gy))
+        return f32(f32(du * du) + f32(dv * dv))
+
+    def fused(u, v):
+        du, dv = f32(f32(u) - f32(gx)), f32(f32(v) - f32(gy))
+        return f32(np.float64(du) * np.float64(du) + np.float64(f32(dv * dv)))
+
+    pr = np.zeros((len(cases), Vs, 3), np.float32)
+    pr[:, 2:, 0] = 200.0 + np.arange(Vs - 2)                              # every other part: one vertex far outside the image
+    pr[:, 2:, 1] = -150.0
+    for i, (ua, va, ub, vb) in enumerate(cases):
+        assert two(ua, va) < two(ub, vb) and fused(ua, va) > fused(ub, vb)   # the premise of the case
+        pr[i, 0, :2] = (ua, va)
+        pr[i, 1, :2] = (ub, vb)
+    mask = np.ones((len(cases), Vs), np.float32)
+    parts = [[0, 1]] + [[2 + k] for k in range(30)]
+    g = np.zeros((len(cases), wh, wh, 32), np.float32)
+    g[:, wh - 1 - gy, gx, 1] = 1.0                                        # part 0's channel at the pixel (rows flipped)
+    x = t(pr).requires_grad_(True)
+    out = pkg.projects_to_seg([x, t(mask)], wh, None, parts=parts)
+    (out * t(g)).sum().backward()
+    got = x.grad.cpu().numpy().astype(np.float64)
+    for i, (ua, va, ub, vb) in enumerate(cases):
+        # (TF's reduce_max runs over exp(-sqrt(d2)), where a one-ulp difference of d2 usually vanishes -- an exact tie,
+        # split evenly upstream; the kernels' documented rule gives a tie to ONE vertex, and which one is what is pinned.)
+        assert np.all(got[i, 1] == 0), (i, got[i, :2])
+        da = np.array([ua - gx, va - gy], np.float64)
+        d = np.sqrt((da * da).sum())
+        want = -np.exp(-d) * da / d                                       # d exp(-|p - g|) / dp at vertex A
+        assert np.abs(got[i, 0, :2] - want).max() <= 2e-5 * np.abs(want).max(), (i, got[i, 0], want)
+
+
 def test_seg_backward_misaligned_upstream_gradient(pkg, host_model, parts_by_vs, make_params):
     """A contiguous upstream gradient whose storage offset is 4 bytes off 16-byte alignment (e.g. a slice of a cat's
     backward): the backward must not issue its 16-byte bulk L2 prefetch on it, and the result must not change."""
