@@ -29,7 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // ---- built-in profiler: CUDA-event pairs around every launch, on the launching stream ---------------------------
 static const char* const kKernelNames[KID_COUNT] = {
     "pose_fwd", "blend_fwd", "lbs_fwd", "joints_reg", "lbs_bwd_vertex", "lbs_bwd_joint", "blend_bwd", "pose_bwd",
-    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd", "dense", "render_vertex", "render_raster"};
+    "project_fwd", "project_bwd", "mask", "seg_fwd", "seg_bwd", "sil_fwd", "sil_bwd", "focal_fwd", "focal_bwd", "dense", "render_vertex", "render_raster", "render_face"};
 struct ProfRecord { int kid; cudaEvent_t a, b; };
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mutex;
@@ -958,7 +958,8 @@ int smpl_b200_renderer_create(int device, const int32_t* faces, int num_faces, i
 
 size_t smpl_b200_render_workspace_bytes(const SmplB200Renderer* r, int N) {
   if (!r || N < 0) return 0;
-  return (size_t)N * r->V * 2 * sizeof(float4);
+  // [N][V] screen positions + [N][V] colours (float4 each) + [N][F] packed tile ranges of the faces
+  return (size_t)N * r->V * 2 * sizeof(float4) + (((size_t)N * r->F * sizeof(uint32_t) + 15) & ~(size_t)15);
 }
 
 int smpl_b200_render(const SmplB200Renderer* r, const float* verts, const float* cam, const float* near_far, int N,
@@ -983,8 +984,9 @@ int smpl_b200_render(const SmplB200Renderer* r, const float* verts, const float*
     for (int c = 0; c < 3; ++c) { L.pos[l][c] = lights[l * 6 + c]; L.color[l][c] = lights[l * 6 + 3 + c]; }
   float4* vscreen = reinterpret_cast<float4*>(workspace);
   float4* vcolor = vscreen + (size_t)N * r->V;
+  uint32_t* fbox = reinterpret_cast<uint32_t*>(vcolor + (size_t)N * r->V);
   CHECK_LAUNCH(launch_render(r, verts, cam, near_far, N, height, width, albedo, albedo_per_vertex, L, background,
-                             background_per_image, channels, vscreen, vcolor, image, (cudaStream_t)stream));
+                             background_per_image, channels, vscreen, vcolor, fbox, image, (cudaStream_t)stream));
   return SMPL_B200_OK;
 }
 

@@ -24,7 +24,7 @@ void count_launch();
 enum KernelId {
   KID_POSE_FWD = 0, KID_BLEND_FWD, KID_LBS_FWD, KID_JOINTS_REG, KID_LBS_BWD_VERTEX, KID_LBS_BWD_JOINT, KID_BLEND_BWD,
   KID_POSE_BWD, KID_PROJECT_FWD, KID_PROJECT_BWD, KID_MASK, KID_SEG_FWD, KID_SEG_BWD, KID_SIL_FWD, KID_SIL_BWD,
-  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_DENSE, KID_RENDER_VERTEX, KID_RENDER_RASTER, KID_COUNT
+  KID_FOCAL_FWD, KID_FOCAL_BWD, KID_DENSE, KID_RENDER_VERTEX, KID_RENDER_RASTER, KID_RENDER_FACE, KID_COUNT
 };
 // RAII scope around one kernel launch: counts it and, while profiling is enabled, brackets it with CUDA events
 // recorded on the launching stream.
@@ -213,11 +213,11 @@ cudaError_t launch_dense_bwd(const float* X, int ldx, const float* W, const floa
 cudaError_t launch_axpy_cols(const float* a, int lda, const float* d, int ldd, float scale, int rows, int cols, float* out,
                              int ldo, cudaStream_t st);
 
-// mesh visualiser (renderer.py): vscreen / vcolor = [N][V] float4 scratch
+// mesh visualiser (renderer.py): vscreen / vcolor = [N][V] float4 scratch, fbox = [N][F] packed tile ranges of the faces
 cudaError_t launch_render(const SmplB200Renderer* r, const float* verts, const float* cam, const float* near_far, int N,
                           int h, int w, const float* albedo, int albedo_per_vertex, const RenderLights& lights,
                           const unsigned char* background, int bg_per_image, int channels, float4* vscreen, float4* vcolor,
-                          unsigned char* out, cudaStream_t st);
+                          uint32_t* fbox, unsigned char* out, cudaStream_t st);
 
 // small device helpers
 // Asynchronous request of [p, p + bytes) into L2 (cp.async.bulk.prefetch: no register, no scoreboard; one thread moves a

@@ -13,11 +13,14 @@
 // Not restated: OpenDR's `overdraw` anti-aliasing of silhouette edges (GL line rasterisation) and GL's fixed-point vertex
 // snapping -- a visualiser's boundary pixels may differ from a GL driver's by one pixel.
 //
-// Two kernels.  render_vertex: thread = (image, vertex): normal from the vertex's faces (CSR built at create time, face
-// order, so the sum is deterministic), lighting, projection.  render_raster: block = (16 x 16 pixel tile, image): the
-// faces are streamed in chunks of 256, the ones whose bounding box meets the tile are compacted IN FACE ORDER into a
-// shared-memory list (ballot + block scan), and every thread resolves its pixel against the list; ties in depth keep
-// the lowest face index (GL_LESS, draw order).
+// Three kernels.  render_vertex: thread = (image, vertex): normal from the vertex's faces (CSR built at create time, face
+// order, so the sum is deterministic), lighting, projection.  render_face: thread = (image, face): the range of 16 x 16
+// tiles the face's bounding box can meet, packed in four bytes (an empty range for faces behind the camera or without
+// area).  render_raster: block = (tile, image): the faces' packed ranges are streamed in chunks of 256 (one coalesced
+// 4-byte load per face and tile; the three corner gathers only for the faces whose range holds the tile -- before, every
+// tile gathered all 13776 faces' corners: 661 KB through L2 per tile, 130 MB per image), the ones whose bounding box meets
+// the tile (the exact test, as before) are compacted IN FACE ORDER into a shared-memory list (ballot + block scan), and
+// every thread resolves its pixel against the list; ties in depth keep the lowest face index (GL_LESS, draw order).
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -27,9 +30,10 @@ namespace {
 
 constexpr int kTile = 16;
 constexpr int kRasterThreads = kTile * kTile;
-constexpr int kListCap = 768;          // faces per shared-memory round; a round is rasterised when fewer than 256 slots are left
+constexpr int kListCap = 768;          // faces per shared-memory round (56 B each); a round is rasterised when fewer than 256 slots are left
 
 struct RFace {
+  float bx0, bx1, by0, by1;            // bounding box of the corners: a pixel outside it is outside the triangle
   float x0, y0, x1, y1, x2, y2;        // projected corners
   float iz0, iz1, iz2;                 // 1 / Z of the corners (linear in screen space)
   int f;
@@ -86,12 +90,40 @@ __device__ __forceinline__ bool edge_owns(float ax, float ay, float bx, float by
   return dy < 0.f || (dy == 0.f && dx < 0.f);
 }
 
+// Packed tile range of a face: bytes {tx_lo, tx_hi, ty_lo, ty_hi}; a superset of the tiles its bounding box meets (the
+// rasteriser applies the exact test to the faces it keeps), lo > hi for a face that can never be drawn.
+constexpr uint32_t kNoTiles = 0x00010001u;   // tx 1..0, ty 1..0
+__global__ void __launch_bounds__(256)
+render_face_kernel(const float4* __restrict__ vscreen, int N, int V, const int* __restrict__ faces, int F, int tiles_x,
+                   int tiles_y, uint32_t* __restrict__ fbox) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * F) return;
+  const int n = (int)(t / F), f = (int)(t - (long long)n * F);
+  const float4* vs = vscreen + (size_t)n * V;
+  const float4 a = vs[faces[f * 3]], b = vs[faces[f * 3 + 1]], c = vs[faces[f * 3 + 2]];
+  const float xmin = fminf(a.x, fminf(b.x, c.x)), xmax = fmaxf(a.x, fmaxf(b.x, c.x));
+  const float ymin = fminf(a.y, fminf(b.y, c.y)), ymax = fmaxf(a.y, fmaxf(b.y, c.y));
+  uint32_t box = kNoTiles;
+  const bool finite = fabsf(xmin) <= 1e30f && fabsf(xmax) <= 1e30f && fabsf(ymin) <= 1e30f && fabsf(ymax) <= 1e30f;
+  if (finite && a.w > 0.f && b.w > 0.f && c.w > 0.f && edge_fn(a.x, a.y, b.x, b.y, c.x, c.y) != 0.f) {
+    // tile tx holds pixels 16 tx .. 16 tx + 15: the box meets it iff xmin <= 16 tx + 15 and xmax >= 16 tx; widened by a
+    // thousandth of a tile so that rounding here can only add tiles
+    const float inv = 1.0f / (float)kTile;
+    const int x_lo = max(0, (int)ceilf(fmaxf((xmin - (float)(kTile - 1)) * inv - 1e-3f, -1.0f)));
+    const int x_hi = min(tiles_x - 1, (int)floorf(fminf(xmax * inv + 1e-3f, (float)tiles_x)));
+    const int y_lo = max(0, (int)ceilf(fmaxf((ymin - (float)(kTile - 1)) * inv - 1e-3f, -1.0f)));
+    const int y_hi = min(tiles_y - 1, (int)floorf(fminf(ymax * inv + 1e-3f, (float)tiles_y)));
+    if (x_lo <= x_hi && y_lo <= y_hi) box = (uint32_t)x_lo | ((uint32_t)x_hi << 8) | ((uint32_t)y_lo << 16) | ((uint32_t)y_hi << 24);
+  }
+  fbox[t] = box;
+}
+
 __global__ void __launch_bounds__(kRasterThreads)
 render_raster_kernel(const float4* __restrict__ vscreen, const float4* __restrict__ vcolor, int N, int V,
                      const int* __restrict__ faces, int F, int h, int w, const float* __restrict__ near_far,
                      const unsigned char* __restrict__ background, int bg_per_image, const unsigned char* __restrict__ q8,
-                     int channels, unsigned char* __restrict__ out) {
-  __shared__ RFace list[kListCap];
+                     int channels, const uint32_t* __restrict__ fbox, unsigned char* __restrict__ out) {
+  __shared__ __align__(8) RFace list[kListCap];
   __shared__ int warp_cnt[kRasterThreads / 32];
   __shared__ int list_n;
   const int n = blockIdx.y;
@@ -111,9 +143,13 @@ render_raster_kernel(const float4* __restrict__ vscreen, const float4* __restric
   if (threadIdx.x == 0) list_n = 0;
   __syncthreads();
 
-  auto rasterise = [&](int count) {
+  auto rasterise = [&](const RFace* lst, int count) {
     for (int e = 0; e < count; ++e) {
-      const RFace t = list[e];                                     // same address on every thread: broadcast
+      // same address on every thread: broadcast.  The box first: SMPL's faces cover a few pixels at 224 x 224, so ~95 % of
+      // the (pixel, face) pairs of a tile end here instead of in three edge functions (same result: inside => in the box)
+      const float2 bx = *reinterpret_cast<const float2*>(&lst[e].bx0), by = *reinterpret_cast<const float2*>(&lst[e].by0);
+      if (px < bx.x || px > bx.y || py < by.x || py > by.y) continue;
+      const RFace t = lst[e];
       float w0 = edge_fn(t.x1, t.y1, t.x2, t.y2, px, py);
       float w1 = edge_fn(t.x2, t.y2, t.x0, t.y0, px, py);
       float w2 = edge_fn(t.x0, t.y0, t.x1, t.y1, px, py);
@@ -140,9 +176,64 @@ render_raster_kernel(const float4* __restrict__ vscreen, const float4* __restric
     }
   };
 
-  for (int base = 0; base < F; base += kRasterThreads) {
+  // With the packed tile ranges: no barrier per chunk.  Each warp owns a contiguous eighth of the faces; it counts the
+  // faces whose range holds this tile, the eight counts are scanned once, and each warp then writes its exact survivors
+  // at its own offset -- the concatenation is in face order.  (More candidates than the list holds: the streaming path.)
+  bool done = false;
+  if (fbox) {
+    constexpr int kW = kRasterThreads / 32;
+    __shared__ int woff[kW + 1];
+    const uint32_t* fb = fbox + (size_t)n * F;
+    const int per = (F + kW - 1) / kW, f0 = warp * per, f1 = min(F, f0 + per);
+    auto in_range = [&](int f) {
+      const uint32_t bb = fb[f];
+      return (uint32_t)tx >= (bb & 0xffu) && (uint32_t)tx <= ((bb >> 8) & 0xffu) && (uint32_t)ty >= ((bb >> 16) & 0xffu) &&
+             (uint32_t)ty <= (bb >> 24);
+    };
+    int cnt = 0;
+    for (int base = f0; base < f1; base += 32) {
+      const int f = base + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, f < f1 && in_range(f)));
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int q = 0; q < kW; ++q) { woff[q] = tot; tot += warp_cnt[q]; }
+      woff[kW] = tot;
+    }
+    __syncthreads();
+    if (woff[kW] <= kListCap) {                                    // uniform
+      int pos = woff[warp];
+      for (int base = f0; base < f1; base += 32) {
+        const int f = base + lane;
+        bool keep = false;
+        RFace t;
+        if (f < f1 && in_range(f)) {
+          const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
+          const float4 a = vs[i0], b = vs[i1], c = vs[i2];
+          t.x0 = a.x; t.y0 = a.y; t.x1 = b.x; t.y1 = b.y; t.x2 = c.x; t.y2 = c.y;
+          t.iz0 = a.z; t.iz1 = b.z; t.iz2 = c.z; t.f = f;
+          const float xmin = fminf(a.x, fminf(b.x, c.x)), xmax = fmaxf(a.x, fmaxf(b.x, c.x));
+          const float ymin = fminf(a.y, fminf(b.y, c.y)), ymax = fmaxf(a.y, fmaxf(b.y, c.y));
+          t.bx0 = xmin; t.bx1 = xmax; t.by0 = ymin; t.by1 = ymax;
+          keep = a.w > 0.f && b.w > 0.f && c.w > 0.f && xmin <= tx1 && xmax >= tx0 && ymin <= ty1 && ymax >= ty0 &&
+                 edge_fn(a.x, a.y, b.x, b.y, c.x, c.y) != 0.f;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[pos + __popc(bal & ((1u << lane) - 1u))] = t;
+        pos += __popc(bal);
+      }
+      __syncthreads();                                             // every warp's counts have been read: reuse them
+      if (lane == 0) warp_cnt[warp] = pos - woff[warp];
+      __syncthreads();
+      for (int q = 0; q < kW; ++q) rasterise(list + woff[q], warp_cnt[q]);
+      done = true;
+    }
+  }
+  for (int base = 0; !done && base < F; base += kRasterThreads) {
     if (list_n > kListCap - kRasterThreads) {                      // uniform: list_n is read after a barrier
-      rasterise(list_n);
+      rasterise(list, list_n);
       __syncthreads();
       if (threadIdx.x == 0) list_n = 0;
       __syncthreads();
@@ -150,13 +241,20 @@ render_raster_kernel(const float4* __restrict__ vscreen, const float4* __restric
     const int f = base + threadIdx.x;
     bool keep = false;
     RFace t;
-    if (f < F) {
+    bool maybe = f < F;
+    if (maybe && fbox) {                                           // the packed range first: one coalesced load per face
+      const uint32_t bb = fbox[(size_t)n * F + f];
+      maybe = (uint32_t)tx >= (bb & 0xffu) && (uint32_t)tx <= ((bb >> 8) & 0xffu) && (uint32_t)ty >= ((bb >> 16) & 0xffu) &&
+              (uint32_t)ty <= (bb >> 24);
+    }
+    if (maybe) {
       const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
       const float4 a = vs[i0], b = vs[i1], c = vs[i2];
       t.x0 = a.x; t.y0 = a.y; t.x1 = b.x; t.y1 = b.y; t.x2 = c.x; t.y2 = c.y;
       t.iz0 = a.z; t.iz1 = b.z; t.iz2 = c.z; t.f = f;
       const float xmin = fminf(a.x, fminf(b.x, c.x)), xmax = fmaxf(a.x, fmaxf(b.x, c.x));
       const float ymin = fminf(a.y, fminf(b.y, c.y)), ymax = fmaxf(a.y, fmaxf(b.y, c.y));
+      t.bx0 = xmin; t.bx1 = xmax; t.by0 = ymin; t.by1 = ymax;
       keep = a.w > 0.f && b.w > 0.f && c.w > 0.f && xmin <= tx1 && xmax >= tx0 && ymin <= ty1 && ymax >= ty0 &&
              edge_fn(a.x, a.y, b.x, b.y, c.x, c.y) != 0.f;
     }
@@ -174,7 +272,7 @@ render_raster_kernel(const float4* __restrict__ vscreen, const float4* __restric
     }
     __syncthreads();
   }
-  rasterise(list_n);
+  if (!done) rasterise(list, list_n);
 
   if (pc < w && pr < h) {
     const size_t opx = ((size_t)n * h + pr) * w + pc;
@@ -211,7 +309,7 @@ render_raster_kernel(const float4* __restrict__ vscreen, const float4* __restric
 cudaError_t launch_render(const SmplB200Renderer* r, const float* verts, const float* cam, const float* near_far, int N,
                           int h, int w, const float* albedo, int albedo_per_vertex, const RenderLights& lights,
                           const unsigned char* background, int bg_per_image, int channels, float4* vscreen, float4* vcolor,
-                          unsigned char* out, cudaStream_t st) {
+                          uint32_t* fbox, unsigned char* out, cudaStream_t st) {
   {
     LaunchScope scope(KID_RENDER_VERTEX, st);
     const long long total = (long long)N * r->V;
@@ -221,10 +319,19 @@ cudaError_t launch_render(const SmplB200Renderer* r, const float* verts, const f
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+  const int tiles_x = (w + kTile - 1) / kTile, tiles_y = (h + kTile - 1) / kTile;
+  const bool boxed = fbox && tiles_x <= 255 && tiles_y <= 255;     // a tile index is one byte of the packed range
+  if (boxed) {
+    LaunchScope scope(KID_RENDER_FACE, st);
+    const long long total = (long long)N * r->F;
+    render_face_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(vscreen, N, r->V, r->faces, r->F, tiles_x, tiles_y, fbox);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   LaunchScope scope(KID_RENDER_RASTER, st);
-  const int tiles = ((w + kTile - 1) / kTile) * ((h + kTile - 1) / kTile);
-  render_raster_kernel<<<dim3(tiles, N), kRasterThreads, 0, st>>>(vscreen, vcolor, N, r->V, r->faces, r->F, h, w, near_far,
-                                                                 background, bg_per_image, r->q8, channels, out);
+  render_raster_kernel<<<dim3(tiles_x * tiles_y, N), kRasterThreads, 0, st>>>(vscreen, vcolor, N, r->V, r->faces, r->F, h, w,
+                                                                             near_far, background, bg_per_image, r->q8, channels,
+                                                                             boxed ? fbox : nullptr, out);
   return cudaGetLastError();
 }
 
