@@ -432,11 +432,12 @@ size_t sil_smem_bytes(int Vs, int G, int nwarps, bool bwd) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(kSilWarps * 32)
+__global__ void __launch_bounds__(kSilWarps * 32, 1)
 sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, int N, int Vs, int wh, int B, int G,
            int dense, float* __restrict__ out, unsigned short* __restrict__ saved) {
   extern __shared__ __align__(16) unsigned char raw[];
-  __shared__ int next_tile;
+  __shared__ int next_tile, n_items;
+  __shared__ unsigned short items[8 * 64];                // work items: tile | part << 8 (part 0..7 = an eighth of the tile, 15 = all)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   SilSmem sm = carve_sil(raw, Vs, G * G, nwarps, BWD);
   sm.saved = BWD ? nullptr : saved;
@@ -445,10 +446,8 @@ sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, 
   gr.B = B; gr.G = G; gr.S = (G + kStrip - 1) / kStrip; gr.wh = wh;
   if (BWD)
     for (int i = threadIdx.x; i < Vs * 2; i += blockDim.x) sm.gacc[i] = 0.f;
-  if (threadIdx.x == 0) {                                 // first tile handed out on demand (see the tile loop); ordered
-    const int T = kStrip * B, tt = (wh + T - 1) / T;      // before its first use by the barriers of bin_vertices
-    next_tile = (int)(((long long)tt * tt * blockIdx.y) / gridDim.y) + nwarps;
-  }
+  if (threadIdx.x == 0) next_tile = nwarps;               // first item handed out on demand (see the loop); ordered before
+                                                          // its first use by the barriers below
   bin_vertices(sm, projects + (size_t)n * Vs * 3, Vs, gr);
   // from here on `scratch` holds the per-warp survivor lists
   unsigned short* L1 = reinterpret_cast<unsigned short*>(sm.scratch) + (size_t)warp * (kCap1 + kCap2 + kCap3);
@@ -458,21 +457,69 @@ sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, 
   const int ttx = (wh + TT - 1) / TT, ntop = ttx * ttx;
   const int t0 = (int)(((long long)ntop * blockIdx.y) / gridDim.y);
   const int t1 = (int)(((long long)ntop * (blockIdx.y + 1)) / gridDim.y);
-  // Top tiles are handed to the warps on demand, the image's centre first: the body sits there and its tiles cost many
-  // times a background tile.  (A static t -> warp map with t = row * ttx + column gave warp w the SAME column in every
-  // row -- all of the body to two or three of the sixteen warps: ncu had 14.7 % warp occupancy against the 25 % one
-  // block per SM allows.)
-  for (int k = t0 + warp; k < t1;) {
-    const int ka = k / ttx, kb = k - ka * ttx;
-    const int tyi = (ttx >> 1) + ((ka & 1) ? -((ka + 1) >> 1) : (ka >> 1));
-    const int txi = (ttx >> 1) + ((kb & 1) ? -((kb + 1) >> 1) : (kb >> 1));
+  // Work items, handed to the warps on demand.  A top tile is one item, except where the body is: a tile that holds more
+  // than kHeavyTile vertices becomes eight items (a quarter of its rows x half its columns: one 16 x 8 sub-tile at 256 x 256),
+  // each pruned and searched as a region of its own (its lists are shorter than the whole tile's, so little is redone).  Heavy items come first, then the light tiles,
+  // each group from the image's centre outwards.  (History: a static t -> warp map with t = row * ttx + column gave warp w
+  // the SAME column in every row -- all of the body to two or three of the sixteen warps, 14.7 % warp occupancy in ncu
+  // against the 25 % one block per SM allowed; whole tiles on demand, centre first, left 64 items for 32 warps and the
+  // block waiting for its few interior tiles.)
+  if (warp == 0) {
+#ifndef SIL_HEAVY
+#define SIL_HEAVY 10
+#endif
+    constexpr int kHeavyTile = SIL_HEAVY;
+    const bool can_split = !dense && TT >= 32;
+    int cnt = 0;
+    for (int pass = 0; pass < 2; ++pass) {                // 0: heavy tiles (four items each), 1: the others
+      for (int k0 = t0; k0 < t1; k0 += 32) {
+        const int k = k0 + lane;
+        bool take = false;
+        int tile = 0;
+        if (k < t1) {
+          const int ka = k / ttx, kb = k - ka * ttx;
+          const int tyi = (ttx >> 1) + ((ka & 1) ? -((ka + 1) >> 1) : (ka >> 1));
+          const int txi = (ttx >> 1) + ((kb & 1) ? -((kb + 1) >> 1) : (kb >> 1));
+          tile = tyi * ttx + txi;
+          int nv = 0;                                     // vertices binned into the tile's own cells
+          const int cx0 = txi * kStrip, cx1 = min(cx0 + kStrip, G);
+          for (int row = tyi * kStrip; row < min(tyi * kStrip + kStrip, G); ++row)
+            nv += (int)sm.cstart[row * G + cx1] - (int)sm.cstart[row * G + cx0];
+          const bool heavy = can_split && nv > kHeavyTile;
+          take = heavy == (pass == 0);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        const int per = pass == 0 ? 8 : 1;
+        if (take) {
+          const int pos = cnt + per * __popc(bal & ((1u << lane) - 1u));
+          if (pass == 0) { for (int q = 0; q < 8; ++q) items[pos + q] = (unsigned short)(tile | (q << 8)); }
+          else items[pos] = (unsigned short)(tile | (15 << 8));
+        }
+        cnt += per * __popc(bal);
+      }
+    }
+    if (lane == 0) n_items = cnt;
+  }
+  __syncthreads();
+  const int nit = n_items;
+  for (int k = warp; k < nit;) {
+    const int item = items[k];
     {
       int nk = 0;
       if (lane == 0) nk = atomicAdd(&next_tile, 1);
       k = __shfl_sync(0xffffffffu, nk, 0);
     }
-    const int tx0 = txi * TT, ty0 = tyi * TT;
-    const int tw = min(TT, wh - tx0), th = min(TT, wh - ty0);    // the part of the tile inside the image
+    const int tile = item & 0xff, band = item >> 8;
+    const int tyi = tile / ttx, txi = tile - tyi * ttx;
+    int tx0 = txi * TT;
+    int tw = min(TT, wh - tx0);
+    int ty0 = tyi * TT, th = min(TT, wh - ty0);                  // the part of the tile inside the image ...
+    if (band != 15) {                                            // ... or one eighth of it: a quarter of its rows, half its columns
+      const int y_lo = ty0 + (band >> 1) * (TT / 4), y_hi = min(y_lo + TT / 4, ty0 + th);
+      const int x_lo = tx0 + (band & 1) * (TT / 2), x_hi = min(x_lo + TT / 2, tx0 + tw);
+      if (y_lo >= y_hi || x_lo >= x_hi) continue;
+      ty0 = y_lo; th = y_hi - y_lo; tx0 = x_lo; tw = x_hi - x_lo;
+    }
     int n1 = -1;
     if (!dense) {
       const float hw = 0.5f * (float)(tw - 1), hh = 0.5f * (float)(th - 1);
@@ -509,7 +556,9 @@ sil_kernel(const float* __restrict__ projects, const float* __restrict__ g_sil, 
       for (int sx0 = tx0; sx0 < tx0 + tw; sx0 += 16) {
         int n2 = -1;
         const unsigned short* list2 = L1;
-        if (n1 >= 0) {
+        if (n1 >= 0 && tw <= 16 && th <= 8) {
+          n2 = n1;                                        // the region IS this sub-tile: L1 was pruned for exactly these pixels
+        } else if (n1 >= 0) {
           const int sw = min(16, wh - sx0), sh = min(8, wh - sy0);
           const float shw = 0.5f * (float)(sw - 1), shh = 0.5f * (float)(sh - 1);
           n2 = prune_list(sm, L1, n1, (float)sx0 + shw, (float)sy0 + shh, shw, shh, L2, kCap2);
