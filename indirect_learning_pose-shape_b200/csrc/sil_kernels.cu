@@ -220,21 +220,32 @@ __device__ float probe_upper2(const SilSmem& sm, const Grid& gr, float cx, float
   return u2;
 }
 
-// Visit every vertex of the strips whose box is within sqrt(rc2) of (cx, cy): f(sorted position, point), lanes strided.
+// Visit every vertex within sqrt(rc2) of (cx, cy) (and some more): f(sorted position, point), lanes strided.  Cells are
+// row-major, so the cells of one grid row that the disc can reach are ONE contiguous range of the sorted array: lane = row,
+// its chord of the disc -> first and last cell -> [cstart, cstart).  (Whole 8-cell strips, tested one by one against the
+// disc, visited about twice the vertices: a strip is 32 pixels wide at 256 x 256, the disc of a 16 x 8 region 36.)
+// Vertices outside the image are clamped INTO the border cells, which only moves their cell closer: the bounds hold.
 template <typename F>
 __device__ __forceinline__ void for_each_candidate(const SilSmem& sm, const Grid& gr, float cx, float cy, float rc2, F f) {
   const int lane = threadIdx.x & 31;
-  rc2 = rc2 * 1.0001f + 0.01f;                           // the strip bound and the vertex distances round differently
+  rc2 = rc2 * 1.0001f + 0.01f;                           // the cell bounds and the vertex distances round differently
   const float rc = sqrtf(rc2) + 1.0f;
-  const int r_lo = max(0, (int)floorf((cy - rc) / (float)gr.B)), r_hi = min(gr.G - 1, (int)floorf((cy + rc) / (float)gr.B));
-  const int nst = (r_hi - r_lo + 1) * gr.S;
-  for (int base = 0; base < nst; base += 32) {
-    const int t = base + lane;
+  const float fB = (float)gr.B, invB = 1.0f / fB;        // B is a power of two
+  const int r_lo = max(0, (int)floorf((cy - rc) * invB)), r_hi = min(gr.G - 1, (int)floorf((cy + rc) * invB));
+  for (int base = r_lo; base <= r_hi; base += 32) {
+    const int row = base + lane;
     int a = 0, b = 0;
-    if (t < nst) {
-      const int row = r_lo + t / gr.S, sx = t % gr.S;
-      strip_range(sm, gr, row, sx, a, b);
-      if (!(strip_lb2(gr, row, sx, cx, cy) <= rc2)) b = a;
+    if (row <= r_hi) {
+      const float y0 = (float)row * fB, y1 = y0 + fB;                // the row's band of pixels
+      const float dy = fmaxf(fmaxf(y0 - cy, cy - y1), 0.f);
+      const float rem = rc2 - dy * dy;
+      if (rem >= 0.f) {
+        const float dx = sqrtf(rem) * 1.0001f + 0.01f;
+        const int c_lo = min(max((int)floorf((cx - dx) * invB), 0), gr.G - 1);
+        const int c_hi = min(max((int)floorf((cx + dx) * invB), 0), gr.G - 1);
+        a = sm.cstart[row * gr.G + c_lo];
+        b = sm.cstart[row * gr.G + c_hi + 1];
+      }
     }
     unsigned todo = __ballot_sync(0xffffffffu, b > a);
     while (todo) {
