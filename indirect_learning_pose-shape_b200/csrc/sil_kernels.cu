@@ -645,35 +645,53 @@ sil_bwd_saved_kernel(const float* __restrict__ projects, const float* __restrict
   const int p1 = (blockIdx.y + 1 == gridDim.y) ? npx : ((int)(((long long)npx * (blockIdx.y + 1)) / gridDim.y) & ~31);
   const unsigned short* sv = saved + (size_t)n * npx;
   const float2* g2 = reinterpret_cast<const float2*>(g_sil) + (size_t)n * npx;
-  for (int base = p0 + (threadIdx.x & ~31); base < p1; base += blockDim.x) {
-    const int i = base + lane;
-    const bool in = i < p1;
-    const unsigned vid = in ? sv[i] : kSilNone;
-    float cu = 0.f, cv = 0.f;
-    if (vid != kSilNone) {
-      const float2 g = g2[i];
-      const int ro = i / wh, c = i - ro * wh, r = wh - 1 - ro;     // output row -> grid row (:42)
-      const float2 p = pts[vid];
-      const float du = __fsub_rn(p.x, (float)c), dv = __fsub_rn(p.y, (float)r);
-      const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
-      const float s = expf(__fdiv_rn(-d, 1.2f));
-      const float coef = (d > 0.f) ? (-(g.y - g.x) * s / 1.2f) / d : 0.f;
-      cu = coef * du; cv = coef * dv;
-    }
-    // runs of equal vertex ids among consecutive lanes
-    const unsigned prev = __shfl_up_sync(0xffffffffu, vid, 1);
-    const bool head = lane == 0 || prev != vid;
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    const unsigned above = heads & ~((2u << lane) - 1u);           // heads strictly after this lane
-    const int end = above ? (__ffs(above) - 2) : 31;               // last lane of my run
+  // Four 32-pixel groups per trip, their loads (2 + 8 bytes per pixel) issued before any is used: with one group per trip
+  // and 32 warps per SM the kernel sat on the latency of these loads (ncu: half of its stall samples on their first use).
+  constexpr int kU = 8;
+  const float inv_wh = 1.0f / (float)wh;
+  for (int base = p0 + (threadIdx.x & ~31); base < p1; base += kU * blockDim.x) {
+    unsigned vids[kU];
+    float2 gs[kU];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float tu = __shfl_down_sync(0xffffffffu, cu, o), tv = __shfl_down_sync(0xffffffffu, cv, o);
-      if (lane + o <= end) { cu += tu; cv += tv; }
+    for (int k = 0; k < kU; ++k) {
+      const int i = base + k * blockDim.x + lane;
+      const bool in = i < p1;
+      vids[k] = in ? sv[i] : kSilNone;
+      gs[k] = in ? g2[i] : make_float2(0.f, 0.f);
     }
-    if (head && vid != kSilNone) {
-      atomicAdd(&gacc[2 * vid], cu);
-      atomicAdd(&gacc[2 * vid + 1], cv);
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      if (base + k * (int)blockDim.x >= p1) break;                   // warp-uniform
+      const int i = base + k * blockDim.x + lane;
+      const unsigned vid = vids[k];
+      float cu = 0.f, cv = 0.f;
+      if (vid != kSilNone) {
+        const float2 g = gs[k];
+        int ro = (int)((float)i * inv_wh), c = i - ro * wh;          // i / wh for i < 2^24: the float quotient is off by at most one
+        if (c < 0) { --ro; c += wh; } else if (c >= wh) { ++ro; c -= wh; }
+        const int r = wh - 1 - ro;                                   // output row -> grid row (:42)
+        const float2 p = pts[vid];
+        const float du = __fsub_rn(p.x, (float)c), dv = __fsub_rn(p.y, (float)r);
+        const float d = sqrtf(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+        const float s = expf(__fdiv_rn(-d, 1.2f));
+        const float coef = (d > 0.f) ? (-(g.y - g.x) * s / 1.2f) / d : 0.f;
+        cu = coef * du; cv = coef * dv;
+      }
+      // runs of equal vertex ids among consecutive lanes
+      const unsigned prev = __shfl_up_sync(0xffffffffu, vid, 1);
+      const bool head = lane == 0 || prev != vid;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const unsigned above = heads & ~((2u << lane) - 1u);           // heads strictly after this lane
+      const int end = above ? (__ffs(above) - 2) : 31;               // last lane of my run
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float tu = __shfl_down_sync(0xffffffffu, cu, o), tv = __shfl_down_sync(0xffffffffu, cv, o);
+        if (lane + o <= end) { cu += tu; cv += tv; }
+      }
+      if (head && vid != kSilNone) {
+        atomicAdd(&gacc[2 * vid], cu);
+        atomicAdd(&gacc[2 * vid + 1], cv);
+      }
     }
   }
   __syncthreads();
@@ -698,6 +716,7 @@ cudaError_t launch_sil(const float* projects, const float* g_sil, int N, int Vs,
                        cudaStream_t st) {
   if (Vs >= 65535) return cudaErrorInvalidValue;         // sorted positions and vertex ids are kept as 16 bits
   if (BWD && saved) {                                    // search-free backward
+    if (wh > 4096) return cudaErrorInvalidValue;         // pixel indices are split into (row, column) through a float quotient: < 2^24
     const size_t smem = (size_t)Vs * 16;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(sil_bwd_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
