@@ -263,13 +263,16 @@ class Harness:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
-    def timed(self, fn, steps):
+    def timed(self, fn, steps, finish=None):
+        """finish: called after the last step and before the closing event (e.g. join side streams into the timed one)"""
         torch = self.torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
@@ -351,7 +354,15 @@ def run_c5(args, rank, world, local_rank, torch, dist, dev, h: Harness):
         def step_value():
             graphed.replay()
 
+        # e2e: the same graph fed from pinned host memory every step.  Two graphed steps alternate (PipelinedDecoderSteps):
+        # step k+1's parameters are uploaded on a copy stream while step k runs, step k's gradient is read back while step
+        # k+1 runs; every step does its own H2D and D2H inside the timed region, the closing event waits for the last copies.
+        pipe = None if args.no_pipeline else pkg.PipelinedDecoderSteps(dec, B, device=dev, micro_batches=mb, first=graphed)
+
         def step_e2e():
+            if pipe is not None:
+                pipe.step(params_host, grad_host)
+                return
             graphed.params.copy_(params_host, non_blocking=True)     # H2D of this step's inputs (pinned)
             graphed.replay()
             grad_host.copy_(graphed.g_params, non_blocking=True)     # D2H of this step's result
@@ -394,7 +405,10 @@ def run_c5(args, rank, world, local_rank, torch, dist, dev, h: Harness):
     # ---- e2e: host params in, host gradient out, every step ----------------------------------------------------
     for _ in range(2):
         step_e2e()
-    ms_e2e = h.timed(step_e2e, args.steps) / args.steps
+    e2e_join = pipe.join if (use_graph and pipe is not None) else None
+    ms_e2e = h.timed(step_e2e, args.steps, finish=e2e_join) / args.steps
+    if use_graph and pipe is not None:
+        graphed.params.copy_(params_dev)                             # the validation / profiler legs below use the device copy
     e2e_value = global_batch / (ms_e2e * 1e-3)
 
     # ---- validation leg (untimed, N > 1): NCCL all-gather of every rank's labels and parameter gradients -----------------
@@ -480,7 +494,10 @@ def run_c5(args, rank, world, local_rank, torch, dist, dev, h: Harness):
                        args.scaling == "strong" else "16384 samples per GPU, no collective on the path"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": global_batch * 86 * 4,
-                    "d2h_bytes_per_step": global_batch * 86 * 4},
+                    "d2h_bytes_per_step": global_batch * 86 * 4,
+                    "copies": ("two alternating graphed steps; step k+1's H2D and step k's D2H run on copy streams beside the "
+                               "kernels, every step does both inside the timed region") if (use_graph and pipe is not None)
+                    else "H2D, step, D2H in order on one stream"},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline,
             "step_roofline": {"algorithmic_bytes_per_sample": step_bytes, "frac_of_hbm_peak": step_frac,
@@ -620,6 +637,8 @@ def main():
                     help="replay the step as a CUDA graph in the timed region (auto = on; off: the eager API)")
     ap.add_argument("--micro-batches", type=int, default=0,
                     help="slices of the per-GPU batch captured on separate streams of the CUDA graph (0 = auto)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="e2e: copy, replay, copy back on one stream instead of the two-graph pipeline with copy streams")
     ap.add_argument("--no-fused", action="store_true", help="chain the modular ops instead of smpl_b200_full_fwd/_bwd")
     ap.add_argument("--no-validate", action="store_true", help="skip the NCCL all-gather validation leg at N > 1")
     ap.add_argument("--cpu-sample", type=int, default=16, help="samples per CPU-port step")

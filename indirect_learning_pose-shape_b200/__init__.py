@@ -10,6 +10,7 @@ from ._lib import SmplB200Error, launch_count, load as load_library, profile_col
 from .layers import (  # noqa: F401
     DeviceModel,
     GraphedDecoderStep,
+    PipelinedDecoderSteps,
     PartTable,
     SMPLLayer,
     SmplDecoder,
@@ -30,7 +31,7 @@ from .regressor import Dense, IEFRegressor, PlainRegressor  # noqa: F401
 from .renderer import SMPLRenderer  # noqa: F401
 from .sharding import all_gather_outputs, shard_bounds, shard_slice  # noqa: F401
 
-__all__ = ["SMPLLayer", "SMPLRenderer", "SmplDecoder", "GraphedDecoderStep", "Dense", "IEFRegressor", "PlainRegressor", "orthographic_project", "compute_mask", "projects_to_seg",
+__all__ = ["SMPLLayer", "SMPLRenderer", "SmplDecoder", "GraphedDecoderStep", "PipelinedDecoderSteps", "Dense", "IEFRegressor", "PlainRegressor", "orthographic_project", "compute_mask", "projects_to_seg",
            "projects_to_silhouette", "projects_to_seg_focal_loss", "categorical_focal_loss", "categorical_crossentropy", "concat_mean_param", "set_cam_params", "load_mean_set_cam_params",
            "DeviceModel", "PartTable", "get_device_model", "get_part_table", "smpl_io", "SmplB200Error",
            "launch_count", "load_library", "profile_enable", "profile_collect", "shard_bounds", "shard_slice", "all_gather_outputs"]

@@ -767,7 +767,8 @@ class GraphedDecoderStep:
     The arithmetic is the eager path's own kernels in the same order; outputs of the last replay are in ``step.out``.
     """
 
-    def __init__(self, decoder: "SmplDecoder", batch: int, device=None, warmup: int = 3, micro_batches: int = 1):
+    def __init__(self, decoder: "SmplDecoder", batch: int, device=None, warmup: int = 3, micro_batches: int = 1,
+                 g_seg: Optional[torch.Tensor] = None):
         """micro_batches > 1: the batch is cut into that many contiguous slices and each slice's forward + backward is
         captured on its own stream (fork / join inside the one graph).  Samples are independent, so the arithmetic of a
         slice is unchanged; what changes is that the last, partly filled wave of blocks of one slice's kernel runs beside
@@ -783,7 +784,8 @@ class GraphedDecoderStep:
         with torch.cuda.device(dev):
             self.params = torch.zeros((self.batch, NUM_PARAMS), dtype=torch.float32, device=dev)
             self.params[:, :4] = torch.tensor([wh / 2.0, wh / 2.0, wh / 2.0, wh / 1.6], device=dev)
-            self.g_seg = torch.zeros((self.batch, wh, wh, 32), dtype=torch.float32, device=dev)
+            # g_seg: an existing (batch, wh, wh, 32) buffer to use as the static upstream gradient (shared between steps)
+            self.g_seg = g_seg if g_seg is not None else torch.zeros((self.batch, wh, wh, 32), dtype=torch.float32, device=dev)
             self.g_params = torch.zeros((self.batch, NUM_PARAMS), dtype=torch.float32, device=dev)
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.micro_batches - 1)]
             _lib.profile_enable(False)                               # event pairs cannot be recorded into a capture
@@ -839,3 +841,63 @@ class GraphedDecoderStep:
         if g_seg is not None:
             self.g_seg.copy_(g_seg, non_blocking=True)
         return self.replay()
+
+
+class PipelinedDecoderSteps:
+    """Host-fed training steps with the copies off the critical path: two GraphedDecoderSteps (sharing one upstream-gradient
+    buffer) alternate, an upload stream copies step k+1's parameters from pinned host memory while step k's graph runs, and a
+    download stream copies step k's parameter gradient back while step k+1 runs.  Every step still does its own H2D and D2H.
+
+        pipe = PipelinedDecoderSteps(decoder, batch, micro_batches=2)
+        for params_host, grad_host in batches:          # pinned host tensors (batch, 86)
+            pipe.step(params_host, grad_host)            # returns at once; grad_host is valid after pipe.synchronize()
+        pipe.synchronize()
+
+    A caller that reuses ONE grad_host must consume it between steps (the bench only measures the traffic)."""
+
+    def __init__(self, decoder: "SmplDecoder", batch: int, device=None, micro_batches: int = 1,
+                 g_seg: Optional[torch.Tensor] = None, first: Optional["GraphedDecoderStep"] = None):
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        a = first if first is not None else GraphedDecoderStep(decoder, batch, device=dev, micro_batches=micro_batches, g_seg=g_seg)
+        b = GraphedDecoderStep(decoder, batch, device=dev, micro_batches=micro_batches, g_seg=a.g_seg)
+        self.steps = [a, b]
+        self.g_seg = a.g_seg
+        with torch.cuda.device(dev):
+            self._up, self._down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self._uploaded = [torch.cuda.Event() for _ in range(2)]
+            self._computed = [torch.cuda.Event() for _ in range(2)]
+            self._downloaded = [torch.cuda.Event() for _ in range(2)]
+            cur = torch.cuda.current_stream(dev)
+            for e in self._computed + self._downloaded:
+                e.record(cur)
+        self._k = 0
+
+    def step(self, params_host: torch.Tensor, grad_host: torch.Tensor) -> None:
+        i = self._k & 1
+        self._k += 1
+        s = self.steps[i]
+        cur = torch.cuda.current_stream(self.device)
+        # upload: the graph that last read s.params (two steps ago) and the download of ITS gradient must be done
+        self._up.wait_event(self._computed[i])
+        with torch.cuda.stream(self._up):
+            s.params.copy_(params_host, non_blocking=True)
+            self._uploaded[i].record(self._up)
+        cur.wait_event(self._uploaded[i])
+        cur.wait_event(self._downloaded[i])              # s.g_params is about to be rewritten
+        s.replay()
+        self._computed[i].record(cur)
+        self._down.wait_event(self._computed[i])
+        with torch.cuda.stream(self._down):
+            grad_host.copy_(s.g_params, non_blocking=True)
+            self._downloaded[i].record(self._down)
+
+    def join(self) -> None:
+        """Make the current stream wait for the copies in flight (no host synchronisation)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self._up)
+        cur.wait_stream(self._down)
+
+    def synchronize(self) -> None:
+        self.join()
+        torch.cuda.current_stream(self.device).synchronize()

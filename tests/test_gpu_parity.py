@@ -494,6 +494,17 @@ def test_fused_decoder_backward_matches_modular(pkg, host_model, parts_by_vs, ma
     assert float((got3 - ref3).abs().max()) <= 1e-5 * float(ref3.abs().max())
     assert torch.equal(gs3.out["projects"], gs1.out["projects"])
     assert torch.equal(gs3.out["seg"].argmax(-1), gs1.out["seg"].argmax(-1))
+    # host-fed steps with the copies on side streams (two alternating graphs): every step's gradient must be its own
+    pipe = pkg.PipelinedDecoderSteps(dec, n3, device=dev(), micro_batches=2)
+    pipe.g_seg.copy_(g3)
+    hosts = [make_params(n3, wh, seed=90 + k) for k in range(4)]
+    outs = [torch.empty((n3, 86)).pin_memory() for _ in range(4)]
+    for k in range(4):
+        pipe.step(torch.from_numpy(hosts[k]).pin_memory(), outs[k])
+    pipe.synchronize()
+    for k in range(4):
+        want = gs1(t(hosts[k]), g3).clone().cpu()
+        assert float((outs[k] - want).abs().max()) <= 1e-5 * float(want.abs().max()), k
 
 
 def test_seg_duplicate_entries_tie_gradient(pkg):
